@@ -1,0 +1,105 @@
+"""CPU restatement of Dynspec.calc_sspec / calc_acf (float64 numpy).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+Follows (reference = /root/reference/scintools):
+  get_window   scint_utils.py:810-832
+  calc_sspec   dynspec.py:3584-3748  (prewhite / halve / window paths; the
+               lamsteps / velocity / trap variants only swap the input array)
+  calc_acf     dynspec.py:3750-3814  ('direct' and 'sspec' methods)
+"""
+import numpy as np
+from scipy.signal import convolve2d
+
+_WINDOWS = {"hanning": np.hanning, "hamming": np.hamming,
+            "blackman": np.blackman, "bartlett": np.bartlett}
+
+
+def get_window(nt, nf, window="hanning", frac=0.1):
+    """scint_utils.py:810-832. Returns (chan_window[nt], subint_window[nf])."""
+    fn = _WINDOWS[window.lower()]
+    cw = fn(int(np.floor(frac * nt)))
+    sw = fn(int(np.floor(frac * nf)))
+    chan = np.insert(cw, int(np.ceil(len(cw) / 2)), np.ones([nt - len(cw)]))
+    sub = np.insert(sw, int(np.ceil(len(sw) / 2)), np.ones([nf - len(sw)]))
+    return chan, sub
+
+
+def fft_lengths(nf, nt):
+    """dynspec.py:3677-3678."""
+    return (int(2 ** (np.ceil(np.log2(nf)) + 1)),
+            int(2 ** (np.ceil(np.log2(nt)) + 1)))
+
+
+def sspec_axes(nf, nt, dt, df, halve=True):
+    """dynspec.py:3691-3699: fdop [mHz], tdel [us]."""
+    nrfft, ncfft = fft_lengths(nf, nt)
+    td = np.arange(0, nrfft // 2 if halve else nrfft)
+    fd = np.arange(-ncfft // 2, ncfft // 2)
+    fdop = np.multiply(fd, 1e3 / (ncfft * dt))
+    tdel = np.divide(td, (nrfft * df))
+    return fdop, tdel
+
+
+def calc_sspec(dyn, dt, df, prewhite=False, halve=True, window="hanning",
+               window_frac=0.1, db=True):
+    """dynspec.py:3664-3721. Returns (fdop, tdel, sec)."""
+    dyn = np.array(dyn, dtype=np.float64)
+    nf, nt = dyn.shape
+    dyn = dyn - np.mean(dyn)
+    if window is not None:
+        chan, sub = get_window(nt, nf, window=window, frac=window_frac)
+        dyn = chan * dyn
+        dyn = (sub * dyn.T).T
+    nrfft, ncfft = fft_lengths(nf, nt)
+    dyn = dyn - np.mean(dyn)
+    if prewhite:
+        simpw = convolve2d([[1, -1], [-1, 1]], dyn, mode="valid")
+    else:
+        simpw = dyn
+    simf = np.fft.fft2(simpw, s=[nrfft, ncfft])
+    sec = np.fft.fftshift(np.real(simf * np.conj(simf)))
+    if halve:
+        sec = sec[nrfft // 2:]
+    fdop, tdel = sspec_axes(nf, nt, dt, df, halve)
+    if prewhite:
+        if not halve:
+            raise RuntimeError("Cannot apply prewhite to full frame")
+        fd = np.arange(-ncfft // 2, ncfft // 2)
+        td = np.arange(0, nrfft // 2)
+        v1 = np.sin(np.pi / ncfft * fd) ** 2
+        v2 = np.sin(np.pi / nrfft * td) ** 2
+        postdark = np.outer(v2, v1)
+        postdark[:, ncfft // 2] = 1
+        postdark[0, :] = 1
+        sec = sec / postdark
+    if db:
+        with np.errstate(divide="ignore"):
+            sec = 10 * np.log10(sec)
+    return fdop, tdel, sec
+
+
+def calc_acf(dyn, normalise=True, subtract_mean=True):
+    """dynspec.py:3780-3797 (method='direct')."""
+    arr = np.array(dyn, dtype=np.float64)
+    nf, nt = arr.shape
+    if subtract_mean:
+        arr = arr - np.mean(arr[np.isfinite(arr)])
+    arr = np.fft.fft2(arr, s=[2 * nf, 2 * nt])
+    arr = np.abs(arr)
+    arr **= 2
+    arr = np.real(np.fft.fftshift(np.fft.ifft2(arr)))
+    if normalise:
+        arr /= np.max(arr)
+    return arr
+
+
+def calc_acf_sspec(dyn, dt, df, normalise=True, window_frac=0.1):
+    """dynspec.py:3798-3807 (method='sspec')."""
+    _, _, sspec = calc_sspec(dyn, dt, df, prewhite=False, halve=False,
+                             window_frac=window_frac)
+    sspec = np.fft.fftshift(sspec)
+    arr = np.real(np.fft.fftshift(np.fft.fft2(10 ** (sspec / 10))))
+    if normalise:
+        arr /= np.max(arr)
+    return arr

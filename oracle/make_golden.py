@@ -1,0 +1,164 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference/scintools, via oracle/ref_loader.py) on seeded inputs.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Run in the build container only:
+
+    python -m oracle.make_golden
+
+The fixtures are committed; the GPU box never needs /root/reference.  Every
+fixture stores the inputs and the reference's outputs, so
+tests/test_oracle_golden.py can check the numpy restatements against them and
+the gpu tests can check the CUDA path against both.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+from oracle import ref_loader  # noqa: E402
+
+
+def _ref_dynspec(pkg, dyn, dt, df, f0=1400.0):
+    nf, nt = dyn.shape
+    freqs = f0 + df * np.arange(nf)
+    times = dt * np.arange(nt)
+    bd = pkg.dynspec.BasicDyn(dyn, name="golden", header=["golden"],
+                              times=times, freqs=freqs, nchan=nf, nsub=nt,
+                              bw=df * nf, df=df, freq=float(np.mean(freqs)),
+                              tobs=dt * nt, dt=dt, mjd=60000)
+    return pkg.dynspec.Dynspec(dyn=bd, verbose=False, process=False)
+
+
+def golden_sspec_acf(pkg):
+    """calc_sspec / calc_acf on a non power-of-two exponential field."""
+    rng = np.random.default_rng(1)
+    nf, nt, dt, df = 48, 80, 10.0, 0.1
+    dyn = rng.exponential(1.0, (nf, nt))
+    ds = _ref_dynspec(pkg, dyn.copy(), dt, df)
+    ds.calc_sspec()
+    out = dict(dyn=dyn, dt=dt, df=df, sspec=ds.sspec, fdop=ds.fdop,
+               tdel=ds.tdel)
+    ds.calc_acf()
+    out["acf"] = ds.acf
+    fd, td, sec = ds.calc_sspec(prewhite=True, return_sspec=True)
+    out["sspec_prewhite"] = sec
+    fd, td, sec = ds.calc_sspec(halve=False, window="blackman",
+                                window_frac=0.25, return_sspec=True)
+    out["sspec_full_blackman"] = sec
+    out["tdel_full"] = td
+    fd, td, sec = ds.calc_sspec(window=None, return_sspec=True)
+    out["sspec_nowindow"] = sec
+    ds.calc_acf(method="sspec")
+    out["acf_sspec"] = ds.acf
+    np.savez_compressed(os.path.join(GOLD, "sspec_acf_48x80.npz"), **out)
+    # power-of-two case (C1 of BASELINE.json at reduced size)
+    rng = np.random.default_rng(11)
+    dyn = rng.exponential(1.0, (64, 128))
+    ds = _ref_dynspec(pkg, dyn.copy(), dt, df)
+    ds.calc_sspec()
+    ds.calc_acf()
+    np.savez_compressed(os.path.join(GOLD, "sspec_acf_64x128.npz"), dyn=dyn,
+                        dt=dt, df=df, sspec=ds.sspec, fdop=ds.fdop,
+                        tdel=ds.tdel, acf=ds.acf)
+
+
+def golden_thth(pkg):
+    """ththmod on a chunk of Sample_Data.npz (tutorial recipe,
+    docs/source/tutorials/thth_intro.rst:238-310) with seeded noise."""
+    u = sys.modules["astropy.units"]
+    thth = pkg.ththmod
+    arch = np.load(os.path.join(ref_loader.REFERENCE_ROOT, "scintools",
+                                "examples", "data", "ththsims",
+                                "Sample_Data.npz"))
+    rng = np.random.default_rng(7)
+    wf = arch["Espec"]
+    dspec = np.abs(wf) ** 2 + rng.normal(0, 20, wf.shape)
+    cwf, npad = 64, 3
+    dspec2 = np.copy(dspec[:cwf])
+    freq2 = arch["f_MHz"][:cwf]
+    time2 = arch["t_s"]
+    mn = dspec2.mean()
+    pad = np.pad(dspec2 - mn, ((0, npad * cwf), (0, npad * dspec2.shape[1])),
+                 mode="constant", constant_values=0)
+    CS = np.fft.fftshift(np.fft.fft2(pad))
+    fd = thth.fft_axis(time2 * u.s, u.mHz, npad)
+    tau = thth.fft_axis(freq2 * u.MHz, u.us, npad)
+    edges = np.linspace(-0.4, 0.4, 512)
+    etas = np.linspace(12.5, 100.0, 100)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        eigs = np.array([thth.Eval_calc(CS, tau, fd, e * u.s ** 3,
+                                        edges * u.mHz) for e in etas])
+        # index arrays + maps for two curvatures (full and cropped regime)
+        extra = {}
+        for tag, eta in (("a", etas[10]), ("b", etas[80])):
+            red, er = thth.thth_redmap(CS, tau, fd, eta * u.s ** 3,
+                                       edges * u.mHz)
+            extra["eta_" + tag] = eta
+            extra["red_" + tag] = np.asarray(red)
+            extra["edges_red_" + tag] = np.asarray(er.value)
+        # single_search end-to-end (pads with dspec2.mean(); coherent)
+        d0 = dspec2 - mn
+        res = thth.single_search([d0, freq2 * u.MHz, time2 * u.s,
+                                  etas * u.s ** 3, edges * u.mHz, None, False,
+                                  0.1, npad, True, 0 * u.us, False])
+        res_inc = thth.single_search([d0, freq2 * u.MHz, time2 * u.s,
+                                      etas[::4] * u.s ** 3, edges * u.mHz,
+                                      None, False, 0.1, npad, False,
+                                      0.5 * u.us, False])
+    np.savez_compressed(
+        os.path.join(GOLD, "thth_sample_64x150.npz"),
+        dspec2=dspec2, freq=freq2, time=time2, npad=npad, edges=edges,
+        etas=etas, eigs=eigs, fd=np.asarray(fd.value),
+        tau=np.asarray(tau.value),
+        ss_eta_fit=float(res[0].value), ss_eta_sig=float(res[1].value),
+        ss_eigs=np.asarray(res[4]),
+        inc_etas=etas[::4], inc_eigs=np.asarray(res_inc[4]),
+        inc_eta_fit=float(np.asarray(getattr(res_inc[0], "value",
+                                             res_inc[0]))),
+        **extra)
+    print("thth: peak eta = %.3f (tutorial states ~44)" %
+          etas[np.argmax(eigs)])
+
+
+def golden_sim(pkg):
+    """scint_sim.Simulation at 64^2 / 32x96, seeded (legacy MT19937)."""
+    Sim = pkg.scint_sim.Simulation
+    out = {}
+    cfgs = {
+        "iso": dict(mb2=2, ns=64, nf=8, dlam=0.25, seed=1),
+        "aniso": dict(mb2=20, ar=2, psi=30, nx=32, ny=96, nf=4, dlam=0.33,
+                      seed=5, inner=0.01),
+        "lam": dict(mb2=2, ns=64, nf=4, dlam=0.25, seed=3, lamsteps=True),
+    }
+    for tag, kw in cfgs.items():
+        s = Sim(verbose=False, **kw)
+        for name in ("w", "xyp", "xyi", "spe", "spi", "dyn", "freqs",
+                     "times"):
+            out[tag + "_" + name] = np.asarray(getattr(s, name))
+        out[tag + "_eta"] = s.eta
+        out[tag + "_df"] = s.df
+    np.savez_compressed(os.path.join(GOLD, "sim_small.npz"), **out)
+    import json
+    with open(os.path.join(GOLD, "sim_small_cfg.json"), "w") as f:
+        json.dump(cfgs, f, indent=1)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    pkg = ref_loader.load()
+    golden_sspec_acf(pkg)
+    golden_thth(pkg)
+    golden_sim(pkg)
+    for fn in sorted(os.listdir(GOLD)):
+        print(fn, os.path.getsize(os.path.join(GOLD, fn)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
