@@ -1,0 +1,137 @@
+/* libscint_b200 -- C ABI of the B200-native scintools arc-measurement hot path.
+ *
+ * The reference (danielreardon/scintools) is pure Python and has no FFI; each
+ * entry point below names the reference callable whose arithmetic it replaces
+ * (file:line relative to the reference checkout).  INTEGRATION.md shows the
+ * ctypes binding a scintools maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on failure (sb_last_error()
+ *    holds the message); nothing throws, nothing is printed;
+ *  - pointers are DEVICE pointers unless the parameter name ends in _host;
+ *    buffers are caller owned; `stream` is a cudaStream_t passed as void*;
+ *  - 2-D arrays are C-contiguous (row-major); complex = interleaved
+ *    (re, im) float pairs; dyn is [freq][time] like Dynspec.dyn;
+ *  - one CUDA context per process, calls into one device from one host
+ *    thread at a time (the library keeps a grow-only scratch workspace per
+ *    process; sb_release() frees it).  Not fork-safe (CUDA is not).
+ *  - sm_100a only; there is no CPU fallback.
+ */
+#ifndef SCINT_B200_H
+#define SCINT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK 0
+#define SB_ERR_CUDA (-1)
+#define SB_ERR_ARG (-2)
+#define SB_ERR_NOMEM (-3)
+#define SB_ERR_UNSUPPORTED (-4)
+
+/* per-eta status bits written by sb_eta_sweep */
+#define SB_ETA_OK 0
+#define SB_ETA_INDEX_ERROR 1   /* numpy would raise IndexError -> NaN (ththmod.py:795-799) */
+#define SB_ETA_ZERO_START 2    /* start row all zero -> NaN v0 -> ARPACK error -> NaN */
+#define SB_ETA_TOO_SMALL 4     /* cropped matrix smaller than 3x3 -> eigsh raises -> NaN */
+#define SB_ETA_NOT_CONVERGED 8 /* Lanczos hit max_iter; best Ritz value returned */
+
+int sb_abi_version(void);
+const char* sb_last_error(void);
+/* select device, create the context, query SM count. */
+int sb_init(int device);
+/* free the scratch workspace. */
+int sb_release(void);
+
+/* ---- theta-theta ------------------------------------------------------- */
+
+/* Geometry of a conjugate spectrum + theta grid.  Scalars are the
+ * reference's own numpy expressions evaluated by the host layer
+ * (scintools/ththmod.py:83-97,153-156):
+ *   tau0 = tau[0]; dtau = np.diff(tau).mean(); tau_absmax = abs(tau.max())
+ *   fd0  = fd[0];  dfd  = np.diff(fd).mean();  fd_half = abs(fd.max())/2
+ *   th_cents = recentred bin centres of `edges` (device, float64, n of them)
+ */
+typedef struct sb_thth_geom {
+    const void* cs;        /* float2 [ntau][nfd], fftshifted conjugate spectrum */
+    int64_t ntau, nfd;
+    double tau0, dtau, tau_absmax;
+    double fd0, dfd, fd_half;
+    const double* th_cents;      /* device */
+    const double* th_cents_host; /* same values on the host */
+    int32_t n_th;
+    int32_t coherent;      /* 1: complex CS; 0: |CS| (ththmod.py:801) */
+} sb_thth_geom;
+
+/* Replaces the eta loop of ththmod.single_search (ththmod.py:789-811) /
+ * Dynspec.thetatheta_single (dynspec.py:1587-1600), i.e. neta calls of
+ * ththmod.Eval_calc (ththmod.py:371-401 -> thth_redmap :119-173 -> thth_map
+ * :56-116 -> scipy eigsh(k=1, which="LA")).
+ * etas: device float64[neta].  Outputs (device): eigs float64[neta] (NaN where
+ * the reference would have produced NaN), status int32[neta] (SB_ETA_*),
+ * nred int32[neta] (size of the cropped matrix), iters int32[neta].
+ * tol: relative residual tolerance of the Lanczos solve (<=0 -> 2e-5);
+ * max_iter: <=0 -> 256. */
+int sb_eta_sweep(const sb_thth_geom* geom, const double* etas, int32_t neta,
+                 double tol, int32_t max_iter, double* eigs, int32_t* status,
+                 int32_t* nred, int32_t* iters, void* stream);
+
+/* Replaces ththmod.thth_map (ththmod.py:56-116) for one eta.  Any output may
+ * be NULL.  thth: float2 [n][n]; tau_inv / fd_inv: int32 [n][n]
+ * (ththmod.py:94-97, bit exact); pnts: uint8 [n][n] (ththmod.py:100);
+ * th_pnts: uint8 [n] crop mask of thth_redmap (ththmod.py:153-156);
+ * err: int32[1], SB_ETA_INDEX_ERROR if numpy would have raised. */
+int sb_thth_map(const sb_thth_geom* geom, double eta, int32_t hermitian,
+                void* thth, int32_t* tau_inv, int32_t* fd_inv, uint8_t* pnts,
+                uint8_t* th_pnts, int32_t* err, void* stream);
+
+/* ---- Dynspec 2-D FFT paths ---------------------------------------------- */
+
+/* Replaces the arithmetic of Dynspec.calc_sspec (scintools/dynspec.py:3664-3721):
+ *   x = win_t[t]*win_f[f]*(dyn - mean(dyn)); x -= mean(x); [prewhite: 2x2
+ *   first difference]; |FFT2 zero-padded to nrfft x ncfft|^2; fftshift;
+ *   [halve: keep tau >= 0]; [postdark]; [10 log10].
+ * nrfft = 2^(ceil(log2 nf)+1), ncfft likewise (dynspec.py:3677-3678).
+ * dyn: float32 [nf][nt].  win_t [nt] / win_f [nf]: tapers from
+ * scint_utils.get_window (scint_utils.py:810-832) or both NULL (window=None);
+ * sum_win_*: their sums.  pd_fd [ncfft], pd_td [nrfft/2]: the sin^2 post-darken
+ * vectors of dynspec.py:3706-3711 (only read when prewhite).  sec: float32
+ * [nrfft/2 or nrfft][ncfft]; db=0 returns linear power. */
+int sb_sspec_f32(const float* dyn, int32_t nf, int32_t nt, const float* win_t,
+                 const float* win_f, double sum_win_t, double sum_win_f,
+                 int32_t prewhite, int32_t halve, int32_t db, const float* pd_fd,
+                 const float* pd_td, float* sec, void* stream);
+
+/* Replaces Dynspec.calc_acf(method='direct') (scintools/dynspec.py:3780-3797):
+ * real(fftshift(ifft2(|fft2(dyn - mean(valid), [2nf, 2nt])|^2))) [/ max].
+ * acf: float32 [2nf][2nt].  subtract_mean=0 reproduces the input_dyn branch
+ * (dynspec.py:3786-3789).  Any 2nf x 2nt is accepted: the transform runs on the
+ * next power of two and the lags [-nf,nf) x [-nt,nt) are extracted (identical
+ * by the correlation theorem).  The normalisation divides by the zero-lag
+ * value, which is the maximum of an autocovariance. */
+int sb_acf_f32(const float* dyn, int32_t nf, int32_t nt, int32_t subtract_mean,
+               int32_t normalise, float* acf, void* stream);
+
+/* Replaces the CS stage of ththmod.single_search (scintools/ththmod.py:777-787)
+ * and Dynspec.thetatheta_single (scintools/dynspec.py:1572-1579):
+ *   CS = fftshift(fft2(pad(dspec, npad copies, constant pad_value)));
+ *   CS[tau_rowmask] = 0
+ * dspec float32 [nf][nt]; cs: float2 [(npad+1)nf][(npad+1)nt]; tau_rowmask:
+ * uint8 [(npad+1)nf] (1 = zero that fftshifted row) or NULL.  Padded sizes must
+ * be powers of two in this version. */
+int sb_cs_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad,
+              float pad_value, const uint8_t* tau_rowmask, void* cs, void* stream);
+
+/* element-wise float64 -> float32 (n elements); complex128 -> complex64 is the
+ * same call with 2n.  Lets the host layer upload the reference's float64
+ * arrays unchanged. */
+int sb_convert_f64_f32(const double* src, float* dst, int64_t n, void* stream);
+int sb_convert_f32_f64(const float* src, double* dst, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCINT_B200_H */

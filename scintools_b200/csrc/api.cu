@@ -1,0 +1,193 @@
+// extern "C" surface of libscint_b200 (see include/scint_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/scint_b200.h"
+#include "common.cuh"
+#include "thth.cuh"
+
+namespace sb {
+
+static thread_local char g_err[512] = "";
+static void* g_ws[8] = {nullptr};
+static size_t g_ws_bytes[8] = {0};
+static int g_sms = 148;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+int num_sms() { return g_sms; }
+
+void* workspace(int slot, size_t bytes) {
+    if (slot < 0 || slot >= 8) return nullptr;
+    if (bytes <= g_ws_bytes[slot] && g_ws[slot]) return g_ws[slot];
+    if (g_ws[slot]) {
+        cudaDeviceSynchronize();
+        cudaFree(g_ws[slot]);
+        g_ws[slot] = nullptr;
+        g_ws_bytes[slot] = 0;
+    }
+    size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        set_error("workspace slot %d: cudaMalloc(%zu) -> %s", slot, want,
+                  cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    g_ws[slot] = p;
+    g_ws_bytes[slot] = want;
+    return p;
+}
+
+void workspace_release() {
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 8; ++i) {
+        if (g_ws[i]) cudaFree(g_ws[i]);
+        g_ws[i] = nullptr;
+        g_ws_bytes[i] = 0;
+    }
+}
+
+int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
+              int neta, double tol, int max_iter, double* d_eigs,
+              int* d_status, int* d_nred, int* d_iters, cudaStream_t st);
+int thth_map(const ThthGeom& g, double eta, int hermitian, float2* d_out,
+             int* d_tau_inv, int* d_fd_inv, unsigned char* d_pnts,
+             unsigned char* d_th_pnts, int* d_err, cudaStream_t st);
+
+int sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
+          double swt, double swf, int prewhite, int halve, int db,
+          const float* pd1, const float* pd2, float* sec, cudaStream_t st);
+int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
+                  const unsigned char* rowmask, float2* CS, cudaStream_t st);
+int acf(const float* dyn, int nf, int nt, int subtract_mean, int normalise,
+        float* out, cudaStream_t st);
+void twiddle_release();
+
+template <typename A, typename B>
+__global__ void convert_kernel(const A* __restrict__ a, B* __restrict__ b, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        b[i] = (B)a[i];
+}
+
+static int to_geom(const sb_thth_geom* in, ThthGeom* g) {
+    SB_ARG(in != nullptr);
+    SB_ARG(in->ntau > 0 && in->nfd > 0);
+    SB_ARG(in->th_cents != nullptr && in->th_cents_host != nullptr);
+    SB_ARG(in->n_th > 0);
+    g->cs = (const float2*)in->cs;
+    g->ntau = in->ntau;
+    g->nfd = in->nfd;
+    g->tau0 = in->tau0;
+    g->dtau = in->dtau;
+    g->half_dtau = in->dtau / 2;  // dtau / 2 (ththmod.py:95)
+    g->tau_absmax = in->tau_absmax;
+    g->fd0 = in->fd0;
+    g->dfd = in->dfd;
+    g->half_dfd = in->dfd / 2;
+    g->fd_half = in->fd_half;
+    g->th = in->th_cents;
+    g->n = in->n_th;
+    g->coherent = in->coherent;
+    return SB_OK;
+}
+
+}  // namespace sb
+
+extern "C" {
+
+int sb_abi_version(void) { return 1; }
+const char* sb_last_error(void) { return sb::last_error(); }
+
+int sb_init(int device) {
+    SB_CUDA(cudaSetDevice(device));
+    SB_CUDA(cudaFree(0));
+    cudaDeviceProp prop;
+    SB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        sb::set_error("device %d is sm_%d%d; libscint_b200 is sm_100a only",
+                      device, prop.major, prop.minor);
+        return SB_ERR_UNSUPPORTED;
+    }
+    sb::g_sms = prop.multiProcessorCount;
+    return SB_OK;
+}
+
+int sb_release(void) {
+    sb::workspace_release();
+    sb::twiddle_release();
+    return SB_OK;
+}
+
+int sb_eta_sweep(const sb_thth_geom* geom, const double* etas, int32_t neta,
+                 double tol, int32_t max_iter, double* eigs, int32_t* status,
+                 int32_t* nred, int32_t* iters, void* stream) {
+    sb::ThthGeom g;
+    int rc = sb::to_geom(geom, &g);
+    if (rc) return rc;
+    SB_ARG(neta >= 0 && etas && eigs && status && nred && iters);
+    SB_ARG(geom->cs != nullptr);
+    if (!(tol > 0)) tol = 2e-5;
+    return sb::eta_sweep(g, geom->th_cents_host, etas, neta, tol, max_iter,
+                         eigs, status, nred, iters, (cudaStream_t)stream);
+}
+
+int sb_thth_map(const sb_thth_geom* geom, double eta, int32_t hermitian,
+                void* thth, int32_t* tau_inv, int32_t* fd_inv, uint8_t* pnts,
+                uint8_t* th_pnts, int32_t* err, void* stream) {
+    sb::ThthGeom g;
+    int rc = sb::to_geom(geom, &g);
+    if (rc) return rc;
+    const bool wants_map = thth || tau_inv || fd_inv || pnts;
+    SB_ARG(!wants_map || (err != nullptr && geom->cs != nullptr));
+    return sb::thth_map(g, eta, hermitian, (float2*)thth, tau_inv, fd_inv,
+                        pnts, th_pnts, err, (cudaStream_t)stream);
+}
+
+int sb_sspec_f32(const float* dyn, int32_t nf, int32_t nt, const float* win_t,
+                 const float* win_f, double sum_win_t, double sum_win_f,
+                 int32_t prewhite, int32_t halve, int32_t db, const float* pd_fd,
+                 const float* pd_td, float* sec, void* stream) {
+    SB_ARG(dyn && sec && nf >= 2 && nt >= 2);
+    SB_ARG((win_t == nullptr) == (win_f == nullptr));
+    SB_ARG(!prewhite || (halve && pd_fd && pd_td));
+    return sb::sspec(dyn, nf, nt, win_t, win_f, sum_win_t, sum_win_f, prewhite,
+                     halve, db, pd_fd, pd_td, sec, (cudaStream_t)stream);
+}
+
+int sb_acf_f32(const float* dyn, int32_t nf, int32_t nt, int32_t subtract_mean,
+               int32_t normalise, float* acf, void* stream) {
+    SB_ARG(dyn && acf && nf >= 1 && nt >= 1);
+    return sb::acf(dyn, nf, nt, subtract_mean, normalise, acf, (cudaStream_t)stream);
+}
+
+int sb_cs_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad,
+              float pad_value, const uint8_t* tau_rowmask, void* cs, void* stream) {
+    SB_ARG(dspec && cs && nf >= 1 && nt >= 1 && npad >= 0);
+    return sb::conj_spectrum(dspec, nf, nt, npad, pad_value, tau_rowmask,
+                             (float2*)cs, (cudaStream_t)stream);
+}
+
+int sb_convert_f64_f32(const double* src, float* dst, int64_t n, void* stream) {
+    SB_ARG(src && dst && n >= 0);
+    if (n == 0) return SB_OK;
+    sb::convert_kernel<double, float><<<sb::num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+int sb_convert_f32_f64(const float* src, double* dst, int64_t n, void* stream) {
+    SB_ARG(src && dst && n >= 0);
+    if (n == 0) return SB_OK;
+    sb::convert_kernel<float, double><<<sb::num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+}  // extern "C"

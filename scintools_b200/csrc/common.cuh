@@ -1,0 +1,87 @@
+// Shared helpers for libscint_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/scint_b200.h"
+
+namespace sb {
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+// grow-only per-process device workspace (one CUDA context per process,
+// one caller thread at a time; see include/scint_b200.h)
+void* workspace(int slot, size_t bytes);
+void workspace_release();
+int num_sms();
+
+#define SB_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t _e = (call);                                             \
+        if (_e != cudaSuccess) {                                             \
+            sb::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,       \
+                          cudaGetErrorString(_e));                           \
+            return SB_ERR_CUDA;                                              \
+        }                                                                    \
+    } while (0)
+
+#define SB_LAUNCH_CHECK()                                                    \
+    do {                                                                     \
+        cudaError_t _e = cudaGetLastError();                                 \
+        if (_e != cudaSuccess) {                                             \
+            sb::set_error("%s:%d launch -> %s", __FILE__, __LINE__,          \
+                          cudaGetErrorString(_e));                           \
+            return SB_ERR_CUDA;                                              \
+        }                                                                    \
+    } while (0)
+
+#define SB_ARG(cond)                                                         \
+    do {                                                                     \
+        if (!(cond)) {                                                       \
+            sb::set_error("%s:%d bad argument: %s", __FILE__, __LINE__,      \
+                          #cond);                                            \
+            return SB_ERR_ARG;                                               \
+        }                                                                    \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Exact floor(a / b) for finite doubles -- the value numpy's floor_divide
+// (npy_divmod: fmod, (a-mod)/b, snap) returns.  Inputs must be bit-identical
+// to the host's; callers build them with __dmul_rn/__dadd_rn (no FMA
+// contraction).  Reference use: ththmod.py:94-97.
+__device__ __forceinline__ double floor_div_exact(double a, double b) {
+    if (b > 0.0 && isfinite(a)) {
+        double q = floor(__ddiv_rn(a, b));
+        double r = __fma_rn(-q, b, a);  // sign-exact remainder
+        if (r < 0.0) q -= 1.0;
+        else if (r >= b) q += 1.0;
+        return q;
+    }
+    // literal npy_divmod for the unusual sign / non-finite cases
+    if (b == 0.0) return __ddiv_rn(a, b);
+    double mod = fmod(a, b);
+    double div = __ddiv_rn(__dsub_rn(a, mod), b);
+    if (mod != 0.0) {
+        if ((b < 0.0) != (mod < 0.0)) div -= 1.0;
+    }
+    if (div != 0.0) {
+        double fl = floor(div);
+        if (div - fl > 0.5) fl += 1.0;
+        return fl;
+    }
+    return copysign(0.0, __ddiv_rn(a, b));
+}
+
+}  // namespace sb

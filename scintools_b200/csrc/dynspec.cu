@@ -1,0 +1,462 @@
+// Dynspec hot path on the device: secondary spectrum (calc_sspec), ACF
+// (calc_acf, method='direct') and the padded conjugate spectrum that feeds the
+// theta-theta sweep.  All three are real 2-D FFTs done as
+//   rows  : one CTA per live row, real->half-spectrum in shared memory
+//   cols  : four-step split, two tile passes (A: stride-R2 rows + twiddle,
+//           B: R2 consecutive rows) with the epilogue fused into pass B.
+// Zero padding is never materialised: only live rows are transformed and the
+// column pass A reads zeros for the padded rows.
+//
+// Reference: scintools/dynspec.py:3664-3721 (sspec), :3780-3797 (acf),
+//            scintools/ththmod.py:777-787 + dynspec.py:1572-1579 (CS).
+#include <map>
+
+#include "fft_kernels.cuh"
+
+namespace sb {
+
+// ---------------------------------------------------------------- twiddles
+template <typename T>
+__global__ void twiddle_fill_kernel(cx<T>* out, int N, int dir) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double s, c;
+    sincospi(2.0 * (double)i / (double)N, &s, &c);
+    out[i] = mkc<T>((T)c, (T)(dir < 0 ? -s : s));
+}
+
+template <typename T> static std::map<long, void*>& tw_cache() {
+    static std::map<long, void*> m;
+    return m;
+}
+
+template <typename T>
+const cx<T>* twiddle_table(int N, int dir, cudaStream_t st) {
+    long key = (long)N * 2 + (dir > 0 ? 1 : 0);
+    auto& m = tw_cache<T>();
+    auto it = m.find(key);
+    if (it != m.end()) return (const cx<T>*)it->second;
+    void* p = nullptr;
+    if (cudaMalloc(&p, (size_t)N * sizeof(cx<T>)) != cudaSuccess) {
+        set_error("twiddle table N=%d: out of memory", N);
+        cudaGetLastError();
+        return nullptr;
+    }
+    twiddle_fill_kernel<T><<<(N + 255) / 256, 256, 0, st>>>((cx<T>*)p, N, dir);
+    m[key] = p;
+    return (const cx<T>*)p;
+}
+template const float2* twiddle_table<float>(int, int, cudaStream_t);
+template const double2* twiddle_table<double>(int, int, cudaStream_t);
+
+void twiddle_release() {
+    for (auto& kv : tw_cache<float>()) cudaFree(kv.second);
+    for (auto& kv : tw_cache<double>()) cudaFree(kv.second);
+    tw_cache<float>().clear();
+    tw_cache<double>().clear();
+}
+
+// ------------------------------------------------------------------- stats
+// out[0] = sum dyn, out[1] = sum wt*wf*dyn, out[2] = #finite, out[3] = sum finite
+__global__ void dyn_stats_kernel(const float* __restrict__ dyn, long nf, long nt,
+                                 const float* __restrict__ wt,
+                                 const float* __restrict__ wf,
+                                 double* __restrict__ out) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    const long total = nf * nt;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long)gridDim.x * blockDim.x) {
+        float v = dyn[i];
+        s0 += v;
+        if (wt) s1 += (double)(wt[i % nt] * wf[i / nt]) * v;
+        if (isfinite(v)) { s2 += 1.0; s3 += v; }
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out + 0, s0); atomicAdd(out + 1, s1);
+        atomicAdd(out + 2, s2); atomicAdd(out + 3, s3);
+    }
+}
+// stats[4] = mu1 (mean), stats[5] = mu2 (mean after window), stats[6] = mean of finite
+__global__ void dyn_stats_final_kernel(double* st, double n, double swt, double swf,
+                                       int windowed) {
+    double mu1 = st[0] / n;
+    st[4] = mu1;
+    st[5] = windowed ? (st[1] - mu1 * swt * swf) / n : 0.0;
+    st[6] = st[3] / st[2];
+    st[7] = 0.0;  // accumulator for the ACF power sum
+}
+
+// --------------------------------------------------------- row load functors
+struct DynRowLoad {
+    const float* dyn;
+    int nf, nt;            // live size of the source
+    const float* wt;       // time taper [nt] or null
+    const float* wf;       // frequency taper [nf] or null
+    const double* stats;   // device: [4]=mu1 [5]=mu2 [6]=mean(finite)
+    int mode;              // 0: sspec (x = wt wf (d-mu1) - mu2), 1: acf (d - mean finite),
+                           // 2: raw minus constant `sub`
+    int prewhite;
+    float sub;
+    __device__ __forceinline__ float val(int f, int t, float m1, float m2) const {
+        float v = dyn[(size_t)f * nt + t] - m1;
+        if (wt) v *= wt[t] * wf[f];
+        return v - m2;
+    }
+    __device__ __forceinline__ float get(int f, int t, float m1, float m2) const {
+        if (!prewhite) return (t < nt) ? val(f, t, m1, m2) : 0.f;
+        if (t >= nt - 1) return 0.f;
+        return val(f + 1, t + 1, m1, m2) - val(f + 1, t, m1, m2) -
+               val(f, t + 1, m1, m2) + val(f, t, m1, m2);
+    }
+    __device__ __forceinline__ float2 operator()(long row, int n) const {
+        float m1, m2 = 0.f;
+        if (mode == 0) { m1 = (float)stats[4]; m2 = (float)stats[5]; }
+        else if (mode == 1) { m1 = (float)stats[6]; }
+        else { m1 = sub; }
+        const int f = (int)row, t = 2 * n;
+        return make_float2(get(f, t, m1, m2), get(f, t + 1, m1, m2));
+    }
+};
+
+struct HalfStore {   // X[k] -> H[row][k]
+    float2* H;
+    long pitch;
+    __device__ __forceinline__ void operator()(long row, int k, float2 v) const {
+        H[row * pitch + k] = v;
+    }
+};
+
+// ------------------------------------------------------ column pass functors
+struct ColALoad {    // y = r2, i = r1: row r1*R2 + r2, zero beyond the live rows
+    const float2* H;
+    long pitch;
+    int R2, live;
+    __device__ __forceinline__ float2 operator()(int y, int i, int c) const {
+        const int row = i * R2 + y;
+        return row < live ? H[(size_t)row * pitch + c] : make_float2(0.f, 0.f);
+    }
+};
+struct ColAStore {   // multiply by W_R^(dir r2 k1), write row k1*R2 + r2
+    float2* A;
+    long pitch;
+    int R2, R;
+    const float2* wR;
+    __device__ __forceinline__ void operator()(int y, int k, int c, float2 v) const {
+        const float2 w = wR[(y * k) & (R - 1)];
+        A[(size_t)(k * R2 + y) * pitch + c] = cmul(v, w);
+    }
+};
+struct ColBLoad {    // y = k1, i = r2
+    const float2* A;
+    long pitch;
+    int R2;
+    __device__ __forceinline__ float2 operator()(int y, int i, int c) const {
+        return A[(size_t)(y * R2 + i) * pitch + c];
+    }
+};
+
+// conjugate spectrum epilogue: fftshift both axes, Hermitian expansion to the
+// full plane, tau row mask, DC correction for a non-zero pad constant
+struct CsStore {
+    float2* CS;
+    int NF, NT, R1;
+    const unsigned char* rowmask;   // [NF] in fftshifted row order, or null
+    float dc;
+    __device__ __forceinline__ void operator()(int y, int k, int c, float2 v) const {
+        const int kf = y + R1 * k;
+        if (kf == 0 && c == 0) v.x += dc;
+        const int rs = (kf + NF / 2) & (NF - 1);
+        const int cs = (c + NT / 2) & (NT - 1);
+        const bool m0 = rowmask && rowmask[rs];
+        CS[(size_t)rs * NT + cs] = m0 ? make_float2(0.f, 0.f) : v;
+        if (c != 0 && c != NT / 2) {
+            const int mr = ((NF - kf) + NF / 2) & (NF - 1);
+            const int mc = ((NT - c) + NT / 2) & (NT - 1);
+            const bool m1 = rowmask && rowmask[mr];
+            CS[(size_t)mr * NT + mc] = m1 ? make_float2(0.f, 0.f) : make_float2(v.x, -v.y);
+        }
+    }
+};
+
+// secondary spectrum epilogue: |.|^2, fftshift, keep tau >= 0, post-darken, dB
+struct SspecStore {
+    float* sec;
+    int NF, NT, R1;
+    int halve, db;
+    const float* pd1;   // [NT] sin^2 over the shifted fd axis, or null
+    const float* pd2;   // [NF/2] sin^2 over td
+    __device__ __forceinline__ void put(int kf, int cs, float p) const {
+        int row;
+        if (halve) {
+            if (kf >= NF / 2) return;
+            row = kf;
+        } else {
+            row = (kf + NF / 2) & (NF - 1);
+        }
+        if (pd1) {
+            const float pd = (cs == NT / 2 || row == 0) ? 1.f : pd1[cs] * pd2[row];
+            p = p / pd;
+        }
+        if (db) p = 10.f * log10f(p);
+        sec[(size_t)row * NT + cs] = p;
+    }
+    __device__ __forceinline__ void operator()(int y, int k, int c, float2 v) const {
+        const int kf = y + R1 * k;
+        const float p = v.x * v.x + v.y * v.y;
+        put(kf, (c + NT / 2) & (NT - 1), p);
+        if (c != 0 && c != NT / 2)
+            put((NF - kf) & (NF - 1), ((NT - c) + NT / 2) & (NT - 1), p);
+    }
+};
+
+// ------------------------------------------------------------- ACF kernels
+// forward over r2 -> |.|^2 (+ weighted power sum) -> inverse over k2 ->
+// twiddle W_R^(+n2 k1); all inside one shared-memory tile.
+template <int L, int W>
+__global__ void __launch_bounds__(256)
+acf_mid_kernel(const float2* __restrict__ A, float2* __restrict__ G, long pitch,
+               int R1, int ncols, int NT, const float2* __restrict__ twf,
+               const float2* __restrict__ twi, const float2* __restrict__ wRi,
+               double* __restrict__ psum) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    float2* tf = s + L * W;
+    float2* ti = tf + L;
+    const int tid = threadIdx.x;
+    constexpr int NTH = 256;
+    const int c0 = blockIdx.x * W, k1 = blockIdx.y;
+    const int R = R1 * L;
+    for (int i = tid; i < L; i += NTH) { tf[i] = twf[i]; ti[i] = twi[i]; }
+    for (int idx = tid; idx < L * W; idx += NTH) {
+        const int i = idx / W, c = idx % W;
+        s[idx] = (c0 + c < ncols) ? A[(size_t)(k1 * L + i) * pitch + c0 + c]
+                                  : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    fft_axis<float, L, -1, false>(s, W, ILog2<W>::value, 1, tf, tid, NTH);
+    double part = 0.0;
+    for (int idx = tid; idx < L * W; idx += NTH) {
+        const int c = c0 + (idx % W);
+        float2 v = s[idx];
+        const float p = v.x * v.x + v.y * v.y;
+        s[idx] = make_float2(p, 0.f);
+        if (c < ncols) part += (c == 0 || c == NT / 2) ? (double)p : 2.0 * (double)p;
+    }
+    part = warp_sum(part);
+    if ((tid & 31) == 0) atomicAdd(psum, part);
+    __syncthreads();
+    // the DIF output order is exactly the DIT input order
+    fft_axis<float, L, +1, true>(s, W, ILog2<W>::value, 1, ti, tid, NTH);
+    for (int idx = tid; idx < L * W; idx += NTH) {
+        const int n2 = idx / W, c = idx % W;
+        if (c0 + c < ncols) {
+            const float2 w = wRi[(n2 * k1) & (R - 1)];
+            G[(size_t)(k1 * L + n2) * pitch + c0 + c] = cmul(s[idx], w);
+        }
+    }
+}
+
+struct AcfInvLoad {   // y = n2, i = k1
+    const float2* G;
+    long pitch;
+    int R2;
+    __device__ __forceinline__ float2 operator()(int y, int i, int c) const {
+        return G[(size_t)(i * R2 + y) * pitch + c];
+    }
+};
+struct AcfInvStore {  // n = n2 + R2 n1
+    float2* Q;
+    long pitch;
+    int R2;
+    __device__ __forceinline__ void operator()(int y, int k, int c, float2 v) const {
+        Q[(size_t)(y + R2 * k) * pitch + c] = v;
+    }
+};
+struct AcfRowLoad {   // output row i <- circular row (i - nf) mod PF
+    const float2* Q;
+    long pitch;
+    int nf, PF;
+    __device__ __forceinline__ float2 operator()(long row, int k) const {
+        const int n = ((int)row - nf + PF) & (PF - 1);
+        return Q[(size_t)n * pitch + k];
+    }
+};
+struct AcfRowStore {
+    float* acf;
+    int nt, PT;
+    const double* stats;   // [7] = full-plane power sum
+    int normalise;
+    double raw_scale;
+    __device__ __forceinline__ void one(long row, int t, float x, float sc) const {
+        int j;
+        if (t < nt) j = t + nt;
+        else if (t >= PT - nt) j = t - (PT - nt);
+        else return;
+        acf[(size_t)row * (2 * nt) + j] = x * sc;
+    }
+    __device__ __forceinline__ void operator()(long row, int n, float2 z) const {
+        const float sc = (float)(normalise ? 1.0 / stats[7] : raw_scale);
+        one(row, 2 * n, z.x, sc);
+        one(row, 2 * n + 1, z.y, sc);
+    }
+};
+
+// ------------------------------------------------------------ host drivers
+static long half_pitch(long NT) { return ((NT / 2 + 1) + 15) & ~15L; }
+
+static int next_pow2(long v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// rows: real dyn [nf_live][*] -> H[nf_live][pitch] half spectra of length NT
+static int rows_r2c(const DynRowLoad& ld, float2* H, long pitch, int NT,
+                    long nrows, cudaStream_t st) {
+    HalfStore hs{H, pitch};
+    const int N = NT / 2;
+    SB_ROW_DISPATCH(N, return (launch_row_r2c<float, N1, N2>(ld, hs, nrows, st)));
+    return SB_OK;
+}
+
+template <class StoreB>
+static int cols_forward(const float2* H, float2* A, long pitch, int NF, int live,
+                        int ncols, StoreB stb, cudaStream_t st) {
+    int R1, R2;
+    split_len(NF, &R1, &R2);
+    const float2* wR = twiddle_table<float>(NF, -1, st);
+    if (!wR) return SB_ERR_NOMEM;
+    ColALoad la{H, pitch, R2, live};
+    ColAStore sa{A, pitch, R2, NF, wR};
+    int rc = SB_OK;
+    SB_TILE_DISPATCH(R1, rc = (launch_tile_fft<float, LL, 32, -1>(la, sa, ncols, R2, st)));
+    if (rc) return rc;
+    ColBLoad lb{A, pitch, R2};
+    SB_TILE_DISPATCH(R2, rc = (launch_tile_fft<float, LL, 32, -1>(lb, stb, ncols, R1, st)));
+    return rc;
+}
+
+int stats_pass(const float* dyn, int nf, int nt, const float* wt, const float* wf,
+               double swt, double swf, double* stats, cudaStream_t st) {
+    SB_CUDA(cudaMemsetAsync(stats, 0, 8 * sizeof(double), st));
+    dyn_stats_kernel<<<num_sms() * 4, 256, 0, st>>>(dyn, nf, nt, wt, wf, stats);
+    SB_LAUNCH_CHECK();
+    dyn_stats_final_kernel<<<1, 1, 0, st>>>(stats, (double)nf * nt, swt, swf, wt != nullptr);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+// Dynspec.calc_sspec (dynspec.py:3664-3721)
+int sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
+          double swt, double swf, int prewhite, int halve, int db,
+          const float* pd1, const float* pd2, float* sec, cudaStream_t st) {
+    const int NF = 2 * next_pow2(nf), NT = 2 * next_pow2(nt);  // 2^(ceil(log2 n)+1)
+    if (NT / 2 < 8 || NT / 2 > 16384 || NF > 65536 || NF < 4) {
+        set_error("calc_sspec: dynspec %dx%d outside supported FFT sizes", nf, nt);
+        return SB_ERR_UNSUPPORTED;
+    }
+    const long pitch = half_pitch(NT);
+    double* stats = (double*)workspace(0, 64 * sizeof(double));
+    const int live = prewhite ? nf - 1 : nf;
+    float2* H = (float2*)workspace(3, (size_t)live * pitch * sizeof(float2));
+    float2* A = (float2*)workspace(4, (size_t)NF * pitch * sizeof(float2));
+    if (!stats || !H || !A) return SB_ERR_NOMEM;
+    int rc = stats_pass(dyn, nf, nt, wt, wf, swt, swf, stats, st);
+    if (rc) return rc;
+    DynRowLoad ld{dyn, nf, nt, wt, wf, stats, 0, prewhite, 0.f};
+    rc = rows_r2c(ld, H, pitch, NT, live, st);
+    if (rc) return rc;
+    int R1, R2;
+    split_len(NF, &R1, &R2);
+    SspecStore ss{sec, NF, NT, R1, halve, db, prewhite ? pd1 : nullptr, pd2};
+    return cols_forward(H, A, pitch, NF, live, NT / 2 + 1, ss, st);
+}
+
+// conjugate spectrum of a zero(/constant)-padded chunk
+// (ththmod.py:777-787, dynspec.py:1572-1579)
+int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
+                  const unsigned char* rowmask, float2* CS, cudaStream_t st) {
+    const long NFl = (long)(npad + 1) * nf, NTl = (long)(npad + 1) * nt;
+    if (!is_pow2(NFl) || !is_pow2(NTl) || NTl / 2 < 8 || NTl / 2 > 16384 ||
+        NFl > 65536 || NFl < 4) {
+        set_error("conjugate spectrum: padded size %ldx%ld must be powers of two "
+                  "(rows 4..65536, cols 16..32768)", NFl, NTl);
+        return SB_ERR_UNSUPPORTED;
+    }
+    const int NF = (int)NFl, NT = (int)NTl;
+    const long pitch = half_pitch(NT);
+    float2* H = (float2*)workspace(3, (size_t)nf * pitch * sizeof(float2));
+    float2* A = (float2*)workspace(4, (size_t)NF * pitch * sizeof(float2));
+    if (!H || !A) return SB_ERR_NOMEM;
+    DynRowLoad ld{dyn, nf, nt, nullptr, nullptr, nullptr, 2, 0, pad_value};
+    int rc = rows_r2c(ld, H, pitch, NT, nf, st);
+    if (rc) return rc;
+    int R1, R2;
+    split_len(NF, &R1, &R2);
+    CsStore cs{CS, NF, NT, R1, rowmask, pad_value * (float)NF * (float)NT};
+    return cols_forward(H, A, pitch, NF, nf, NT / 2 + 1, cs, st);
+}
+
+// Dynspec.calc_acf(method='direct') (dynspec.py:3780-3797)
+int acf(const float* dyn, int nf, int nt, int subtract_mean, int normalise,
+        float* out, cudaStream_t st) {
+    const int PF = next_pow2(2L * nf), PT = next_pow2(2L * nt);
+    if (PT / 2 < 8 || PT / 2 > 16384 || PF > 65536 || PF < 4) {
+        set_error("calc_acf: dynspec %dx%d outside supported FFT sizes", nf, nt);
+        return SB_ERR_UNSUPPORTED;
+    }
+    const long pitch = half_pitch(PT);
+    double* stats = (double*)workspace(0, 64 * sizeof(double));
+    float2* H = (float2*)workspace(3, (size_t)nf * pitch * sizeof(float2));
+    float2* A = (float2*)workspace(4, (size_t)PF * pitch * sizeof(float2));
+    float2* G = (float2*)workspace(5, (size_t)PF * pitch * sizeof(float2));
+    if (!stats || !H || !A || !G) return SB_ERR_NOMEM;
+    int rc = stats_pass(dyn, nf, nt, nullptr, nullptr, 0, 0, stats, st);
+    if (rc) return rc;
+    DynRowLoad ld{dyn, nf, nt, nullptr, nullptr, stats, subtract_mean ? 1 : 2, 0, 0.f};
+    rc = rows_r2c(ld, H, pitch, PT, nf, st);
+    if (rc) return rc;
+    int R1, R2;
+    split_len(PF, &R1, &R2);
+    const int ncols = PT / 2 + 1;
+    // forward pass A
+    {
+        const float2* wR = twiddle_table<float>(PF, -1, st);
+        if (!wR) return SB_ERR_NOMEM;
+        ColALoad la{H, pitch, R2, nf};
+        ColAStore sa{A, pitch, R2, PF, wR};
+        SB_TILE_DISPATCH(R1, rc = (launch_tile_fft<float, LL, 32, -1>(la, sa, ncols, R2, st)));
+        if (rc) return rc;
+    }
+    // fused forward pass B -> power -> inverse over k2
+    {
+        const float2* wRi = twiddle_table<float>(PF, +1, st);
+        const float2* twf = twiddle_table<float>(R2, -1, st);
+        const float2* twi = twiddle_table<float>(R2, +1, st);
+        if (!wRi || !twf || !twi) return SB_ERR_NOMEM;
+        dim3 grid((ncols + 31) / 32, R1);
+        SB_TILE_DISPATCH(R2, {
+            auto kern = acf_mid_kernel<LL, 32>;
+            const size_t smem = (size_t)(LL * 32 + 2 * LL) * sizeof(float2);
+            SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, 256, smem, st>>>(A, G, pitch, R1, ncols, PT, twf, twi, wRi, stats + 7);
+        });
+        SB_LAUNCH_CHECK();
+    }
+    // inverse over k1 -> Q (reuse A)
+    {
+        AcfInvLoad li{G, pitch, R2};
+        AcfInvStore si{A, pitch, R2};
+        SB_TILE_DISPATCH(R1, rc = (launch_tile_fft<float, LL, 32, +1>(li, si, ncols, R2, st)));
+        if (rc) return rc;
+    }
+    // rows: half spectrum -> real, crop to lags [-nf, nf) x [-nt, nt)
+    AcfRowLoad rl{A, pitch, nf, PF};
+    AcfRowStore rs{out, nt, PT, stats, normalise, 1.0 / ((double)PF * (double)PT)};
+    const int N = PT / 2;
+    SB_ROW_DISPATCH(N, return (launch_row_c2r<float, N1, N2>(rl, rs, 2L * nf, st)));
+    return SB_OK;
+}
+
+}  // namespace sb

@@ -1,0 +1,486 @@
+// theta-theta curvature sweep: crop mask, gather (nearest-bin remap of the
+// conjugate spectrum onto the theta-theta grid), Hermitian fill and the
+// dominant-eigenvalue solve.  General path: the per-eta matrix lives in a
+// global scratch slab (L2 / HBM), one CTA per eta runs a Lanczos iteration.
+//
+// Reference behaviour reproduced (scintools/ththmod.py):
+//   thth_map :56-116, thth_redmap :119-173, Eval_calc :371-401,
+//   eta loop of single_search :789-799 (failure -> NaN).
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+
+#include "thth.cuh"
+
+namespace sb {
+
+// status codes per eta (also in include/scint_b200.h)
+enum { ST_OK = 0, ST_INDEX_ERROR = 1, ST_ZERO_START = 2, ST_TOO_SMALL = 4,
+       ST_NOT_CONVERGED = 8 };
+
+// --------------------------------------------------------------------------
+// crop mask + compaction: th_pnts of thth_redmap (ththmod.py:153-156)
+// one warp per eta
+// --------------------------------------------------------------------------
+__global__ void thth_prep_kernel(ThthGeom g, const double* __restrict__ etas,
+                                 int neta, int ld, int* __restrict__ idx,
+                                 int* __restrict__ nred) {
+    int e = blockIdx.x;
+    if (e >= neta) return;
+    double eta = etas[e];
+    int lane = threadIdx.x;
+    int base = 0;
+    int* out = idx + (size_t)e * ld;
+    for (int k0 = 0; k0 < g.n; k0 += 32) {
+        int k = k0 + lane;
+        bool keep = false;
+        if (k < g.n) {
+            double t = g.th[k];
+            keep = (__dmul_rn(__dmul_rn(t, t), eta) < g.tau_absmax) &&
+                   (fabs(t) < g.fd_half);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) out[base + __popc(m & ((1u << lane) - 1u))] = k;
+        base += __popc(m);
+    }
+    if (lane == 0) nred[e] = base;
+}
+
+// --------------------------------------------------------------------------
+// rare path: would numpy raise IndexError anywhere in the full N x N map?
+// (fd_inv < -nfd on a point that passes the pnts mask, ththmod.py:100-104)
+// --------------------------------------------------------------------------
+__global__ void thth_indexerr_kernel(ThthGeom g, const double* __restrict__ etas,
+                                     int* __restrict__ status) {
+    int e = blockIdx.y;
+    double eta = etas[e];
+    long long total = (long long)g.n * g.n;
+    bool bad = false;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+         p < total; p += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(p / g.n), j = (int)(p % g.n);
+        ThthPoint pt = thth_point(g, eta, g.th[j], g.th[i]);
+        bad |= pt.index_error;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0)
+        atomicOr(status + e, ST_INDEX_ERROR);
+}
+
+// --------------------------------------------------------------------------
+// build the cropped Hermitian theta-theta matrix for a batch of etas.
+// grid = (tile pairs, etas in batch); block = 32 x 8.
+// M[e] is [ld][ld] float2, rows/cols < nred valid, zero padded inside the
+// active 32x32 tiles.
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0,
+                  int ld, const int* __restrict__ idx,
+                  const int* __restrict__ nred, float2* __restrict__ M) {
+    __shared__ float2 tile[32][33];
+    __shared__ int ia[32], ib[32];
+    __shared__ double ta_[32], tb_[32];
+    const int e = blockIdx.y;
+    const int n = nred[eta0 + e];
+    // pair index -> (ta <= tb)
+    int p = blockIdx.x, ta = 0;
+    const int T = ld / 32;
+    while (p >= T - ta) { p -= T - ta; ++ta; }
+    const int tb = ta + p;
+    if (tb * 32 >= n) return;  // never read by the eigen kernel
+    const double eta = etas[eta0 + e];
+    const int* id = idx + (size_t)(eta0 + e) * ld;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    if (ty == 0) {
+        int a = ta * 32 + tx;
+        ia[tx] = a < n ? id[a] : -1;
+        ta_[tx] = a < n ? g.th[id[a]] : 0.0;
+    } else if (ty == 1) {
+        int b = tb * 32 + tx;
+        ib[tx] = b < n ? id[b] : -1;
+        tb_[tx] = b < n ? g.th[id[b]] : 0.0;
+    }
+    __syncthreads();
+    float2* Me = M + (size_t)e * ld * ld;
+    const float2 zero = make_float2(0.f, 0.f);
+    if (ta != tb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int la = ty + 8 * k, lb = tx;
+            int i = ia[la], j = ib[lb];
+            float2 v = zero;
+            if (i >= 0 && j >= 0 && i + j != g.n - 1) {
+                ThthPoint pt = thth_point(g, eta, tb_[lb], ta_[la]);
+                v = thth_value(g, eta, tb_[lb], ta_[la], pt);
+                v.x = nan_to_num(v.x);
+                v.y = nan_to_num(v.y);
+            }
+            Me[(size_t)(ta * 32 + la) * ld + tb * 32 + lb] = v;
+            tile[la][lb] = make_float2(v.x, -v.y);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int lb = ty + 8 * k, la = tx;
+            Me[(size_t)(tb * 32 + lb) * ld + ta * 32 + la] = tile[la][lb];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int la = ty + 8 * k, lb = tx;
+            if (la < lb) {
+                int i = ia[la], j = ib[lb];
+                float2 v = zero;
+                if (i >= 0 && j >= 0 && i + j != g.n - 1) {
+                    ThthPoint pt = thth_point(g, eta, tb_[lb], ta_[la]);
+                    v = thth_value(g, eta, tb_[lb], ta_[la], pt);
+                    v.x = nan_to_num(v.x);
+                    v.y = nan_to_num(v.y);
+                }
+                tile[la][lb] = v;
+                tile[lb][la] = make_float2(v.x, -v.y);
+            } else if (la == lb) {
+                tile[la][lb] = zero;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int la = ty + 8 * k, lb = tx;
+            Me[(size_t)(ta * 32 + la) * ld + tb * 32 + lb] = tile[la][lb];
+        }
+    }
+}
+
+// --------------------------------------------------------------------------
+// Lanczos on the Hermitian matrix: largest ALGEBRAIC eigenvalue
+// (scipy eigsh(..., k=1, which="LA"), ththmod.py:398-401), start vector =
+// row n//2.  No re-orthogonalisation: only the top Ritz value is wanted.
+// --------------------------------------------------------------------------
+#define SB_LANCZOS_MAXIT 256
+
+struct LanczosShared {
+    double alpha[SB_LANCZOS_MAXIT];
+    double beta[SB_LANCZOS_MAXIT + 1];
+    double piv[SB_LANCZOS_MAXIT];
+    double red[2][32];
+    double theta, lo;
+    int done;
+};
+
+// Largest eigenvalue of the m x m tridiagonal (alpha[0..m), beta[1..m)) by
+// warp multisection on Sturm counts, then residual bound beta[m]*|s_m|
+// through the twisted (top-down LDL^T) recurrence.  Called by warp 0.
+__device__ void lanczos_check(LanczosShared& S, int m, double tol) {
+    const int lane = threadIdx.x & 31;
+    const double bnew = S.beta[m];
+    double gh = -DBL_MAX;
+    for (int i = lane; i < m; i += 32) {
+        double b0 = i > 0 ? fabs(S.beta[i]) : 0.0;
+        double b1 = i + 1 < m ? fabs(S.beta[i + 1]) : 0.0;
+        gh = fmax(gh, S.alpha[i] + b0 + b1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        gh = fmax(gh, __shfl_xor_sync(0xffffffffu, gh, o));
+    double hi = gh + 1e-9 * fabs(gh) + 1e-290;
+    double lo = (m == 1) ? S.alpha[0] - fabs(S.alpha[0]) * 1e-9 - 1e-290 : S.lo;
+    if (lo > hi) lo = hi - fabs(hi) - 1.0;
+    for (int round = 0; round < 7; ++round) {
+        double sig = lo + (hi - lo) * (double)(lane + 1) / 33.0;
+        double d = S.alpha[0] - sig;
+        int cnt = d < 0.0;
+        for (int i = 1; i < m; ++i) {
+            if (fabs(d) < 1e-280) d = -1e-280;
+            d = (S.alpha[i] - sig) - S.beta[i] * S.beta[i] / d;
+            cnt += d < 0.0;
+        }
+        unsigned ok = __ballot_sync(0xffffffffu, cnt == m);
+        int f = ok ? __ffs(ok) - 1 : 32;
+        double nhi = f < 32 ? __shfl_sync(0xffffffffu, sig, f & 31) : hi;
+        double nlo = f > 0 ? __shfl_sync(0xffffffffu, sig, (f - 1) & 31) : lo;
+        hi = nhi;
+        lo = nlo;
+    }
+    if (lane == 0) {
+        double sig = hi;
+        double d = S.alpha[0] - sig;
+        S.piv[0] = d;
+        for (int i = 1; i < m; ++i) {
+            if (fabs(d) < 1e-280) d = -1e-280;
+            d = (S.alpha[i] - sig) - S.beta[i] * S.beta[i] / d;
+            S.piv[i] = d;
+        }
+        double z = 1.0, nrm = 1.0;
+        for (int i = m - 2; i >= 0; --i) {
+            double pv = S.piv[i];
+            if (fabs(pv) < 1e-280) pv = -1e-280;
+            z = -(S.beta[i + 1] / pv) * z;
+            nrm += z * z;
+            if (nrm > 1e200) break;
+        }
+        double res = bnew * rsqrt(nrm);
+        S.theta = sig;
+        S.lo = lo;
+        S.done = (res <= tol * fabs(sig)) || !(bnew > 1e-30 * fabs(sig)) ? 1 : 0;
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
+                const int* __restrict__ nred, int eta0,
+                double* __restrict__ eigs, int* __restrict__ status,
+                int* __restrict__ iters, double tol, int max_iter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LanczosShared& S = *reinterpret_cast<LanczosShared*>(smem_raw);
+    float2* v = reinterpret_cast<float2*>(smem_raw + sizeof(LanczosShared));
+    float2* vp = v + ld;
+    float2* w = vp + ld;
+    constexpr int NW = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int e = blockIdx.x;
+    const int n = nred[eta0 + e];
+    const float2* M = Mbase + (size_t)e * ld * ld;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    if (status[eta0 + e] & ST_INDEX_ERROR) {
+        if (tid == 0) { eigs[eta0 + e] = qnan; iters[eta0 + e] = 0; }
+        return;
+    }
+    if (n < 3) {
+        if (tid == 0) {
+            eigs[eta0 + e] = qnan; iters[eta0 + e] = 0;
+            status[eta0 + e] |= ST_TOO_SMALL;
+        }
+        return;
+    }
+    // v0 = row n//2 (ththmod.py:398-399)
+    double part = 0.0;
+    for (int c = tid; c < ld; c += THREADS) {
+        float2 x = c < n ? M[(size_t)(n / 2) * ld + c] : make_float2(0.f, 0.f);
+        v[c] = x;
+        vp[c] = make_float2(0.f, 0.f);
+        part += (double)x.x * x.x + (double)x.y * x.y;
+    }
+    part = warp_sum(part);
+    if (lane == 0) S.red[0][warp] = part;
+    if (tid == 0) { S.done = 0; S.lo = 0.0; S.theta = 0.0; }
+    __syncthreads();
+    double nrm2 = 0.0;
+    for (int k = 0; k < NW; ++k) nrm2 += S.red[0][k];
+    if (!(nrm2 > 0.0) || !isfinite(nrm2)) {
+        if (tid == 0) {
+            eigs[eta0 + e] = qnan; iters[eta0 + e] = 0;
+            status[eta0 + e] |= ST_ZERO_START;
+        }
+        return;
+    }
+    {
+        float s = (float)(1.0 / sqrt(nrm2));
+        for (int c = tid; c < ld; c += THREADS) { v[c].x *= s; v[c].y *= s; }
+    }
+    __syncthreads();
+
+    const int ncol4 = (n + 1) >> 1;  // float4 = two complex columns
+    float beta_prev = 0.f;
+    int m = 0;
+    for (int it = 0; it < max_iter; ++it) {
+        // ---- w = A v, alpha = Re <v, w>
+        float apart = 0.f;
+        for (int r = warp; r < n; r += NW) {
+            const float4* row = reinterpret_cast<const float4*>(M + (size_t)r * ld);
+            float ax = 0.f, ay = 0.f;
+            for (int c0 = lane; c0 < ncol4; c0 += 128) {
+                float4 mm[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int c = c0 + 32 * u;
+                    mm[u] = c < ncol4 ? __ldg(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int c = c0 + 32 * u;
+                    if (c < ncol4) {
+                        float4 xx = *reinterpret_cast<const float4*>(v + 2 * c);
+                        ax += mm[u].x * xx.x - mm[u].y * xx.y + mm[u].z * xx.z - mm[u].w * xx.w;
+                        ay += mm[u].x * xx.y + mm[u].y * xx.x + mm[u].z * xx.w + mm[u].w * xx.z;
+                    }
+                }
+            }
+            ax = warp_sum(ax);
+            ay = warp_sum(ay);
+            if (lane == 0) {
+                w[r] = make_float2(ax, ay);
+                apart += v[r].x * ax + v[r].y * ay;
+            }
+        }
+        if (lane == 0) S.red[0][warp] = (double)apart;
+        __syncthreads();
+        double alpha = 0.0;
+        for (int k = 0; k < NW; ++k) alpha += S.red[0][k];
+        // ---- w -= alpha v + beta_prev vp ; beta = ||w||
+        const float af = (float)alpha;
+        double bpart = 0.0;
+        for (int c = tid; c < n; c += THREADS) {
+            float2 x = w[c];
+            x.x -= af * v[c].x + beta_prev * vp[c].x;
+            x.y -= af * v[c].y + beta_prev * vp[c].y;
+            w[c] = x;
+            bpart += (double)x.x * x.x + (double)x.y * x.y;
+        }
+        bpart = warp_sum(bpart);
+        if (lane == 0) S.red[1][warp] = bpart;
+        __syncthreads();
+        double b2 = 0.0;
+        for (int k = 0; k < NW; ++k) b2 += S.red[1][k];
+        const double beta = sqrt(b2);
+        m = it + 1;
+        if (tid == 0) { S.alpha[it] = alpha; S.beta[m] = beta; }
+        __syncthreads();
+        if (warp == 0) lanczos_check(S, m, tol);
+        __syncthreads();
+        if (S.done || !isfinite(alpha)) break;
+        // ---- rotate: vp = v, v = w / beta
+        const float ib = (float)(1.0 / beta);
+        for (int c = tid; c < n; c += THREADS) {
+            float2 x = w[c];
+            vp[c] = v[c];
+            v[c] = make_float2(x.x * ib, x.y * ib);
+        }
+        beta_prev = (float)beta;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        eigs[eta0 + e] = fabs(S.theta);  // np.abs(w[0])
+        iters[eta0 + e] = m;
+        if (!S.done) status[eta0 + e] |= ST_NOT_CONVERGED;
+    }
+}
+
+// --------------------------------------------------------------------------
+// Full N x N map for the thth_map API / parity tests (not the sweep path).
+// --------------------------------------------------------------------------
+__global__ void thth_map_kernel(ThthGeom g, double eta, int hermitian,
+                                float2* __restrict__ out,
+                                int* __restrict__ tau_inv,
+                                int* __restrict__ fd_inv,
+                                unsigned char* __restrict__ pnts,
+                                int* __restrict__ err) {
+    long long total = (long long)g.n * g.n;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+         p < total; p += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(p / g.n), j = (int)(p % g.n);
+        double thi = g.th[i], thj = g.th[j];
+        ThthPoint pt = thth_point(g, eta, thj, thi);
+        if (pt.index_error) atomicOr(err, ST_INDEX_ERROR);
+        if (tau_inv) tau_inv[p] = (int)max(min(pt.tq, (long long)INT_MAX), (long long)INT_MIN);
+        if (fd_inv) fd_inv[p] = (int)max(min(pt.fq, (long long)INT_MAX), (long long)INT_MIN);
+        if (pnts) pnts[p] = pt.pnt ? 1 : 0;
+        if (!out) continue;
+        float2 v;
+        if (!hermitian) {
+            v = thth_value(g, eta, thj, thi, pt);
+        } else if (i == j || i + j == g.n - 1) {
+            v = make_float2(0.f, 0.f);
+        } else if (j > i) {
+            v = thth_value(g, eta, thj, thi, pt);
+            v.x = nan_to_num(v.x);
+            v.y = nan_to_num(v.y);
+        } else {  // conj of the upper element (j, i)
+            ThthPoint pu = thth_point(g, eta, thi, thj);
+            v = thth_value(g, eta, thi, thj, pu);
+            v.x = nan_to_num(v.x);
+            v.y = -nan_to_num(v.y);
+        }
+        out[p] = v;
+    }
+}
+
+// --------------------------------------------------------------------------
+// host drivers
+// --------------------------------------------------------------------------
+static bool lower_check_needed(const ThthGeom& g, const double* th_host) {
+    // worst case fd argument over all (i, j): min(th) - max(th)
+    double tmin = th_host[0], tmax = th_host[0];
+    for (int k = 1; k < g.n; ++k) {
+        tmin = th_host[k] < tmin ? th_host[k] : tmin;
+        tmax = th_host[k] > tmax ? th_host[k] : tmax;
+    }
+    double worst = floor(((tmin - tmax) - g.fd0 + g.half_dfd) / g.dfd) - 2.0;
+    return !(worst >= -(double)g.nfd);
+}
+
+int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
+              int neta, double tol, int max_iter, double* d_eigs,
+              int* d_status, int* d_nred, int* d_iters, cudaStream_t st) {
+    if (neta <= 0) return SB_OK;
+    if (max_iter <= 0 || max_iter > SB_LANCZOS_MAXIT) max_iter = SB_LANCZOS_MAXIT;
+    const int ld = (g.n + 31) / 32 * 32;
+    if (ld > 4096) {
+        set_error("theta-theta grid of %d centres exceeds the supported 4096", g.n);
+        return SB_ERR_UNSUPPORTED;
+    }
+    int* d_idx = (int*)workspace(1, (size_t)neta * ld * sizeof(int));
+    if (!d_idx) return SB_ERR_NOMEM;
+    SB_CUDA(cudaMemsetAsync(d_status, 0, neta * sizeof(int), st));
+    thth_prep_kernel<<<neta, 32, 0, st>>>(g, d_etas, neta, ld, d_idx, d_nred);
+    SB_LAUNCH_CHECK();
+    if (lower_check_needed(g, th_host)) {
+        dim3 grid(64, neta);
+        thth_indexerr_kernel<<<grid, 256, 0, st>>>(g, d_etas, d_status);
+        SB_LAUNCH_CHECK();
+    }
+    // batch so that the matrix slab stays <= ~3 GiB
+    const size_t per = (size_t)ld * ld * sizeof(float2);
+    int batch = (int)((3ull << 30) / per);
+    if (batch < 1) batch = 1;
+    if (batch > neta) batch = neta;
+    float2* d_M = (float2*)workspace(2, per * batch);
+    if (!d_M) return SB_ERR_NOMEM;
+    const int T = ld / 32;
+    const int npairs = T * (T + 1) / 2;
+    constexpr int EIG_THREADS = 512;
+    const size_t smem = sizeof(LanczosShared) + 3 * (size_t)ld * sizeof(float2);
+    SB_CUDA(cudaFuncSetAttribute(thth_eig_kernel<EIG_THREADS>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    for (int e0 = 0; e0 < neta; e0 += batch) {
+        int nb = neta - e0 < batch ? neta - e0 : batch;
+        dim3 grid(npairs, nb), block(32, 8);
+        thth_build_kernel<<<grid, block, 0, st>>>(g, d_etas, e0, ld, d_idx, d_nred, d_M);
+        SB_LAUNCH_CHECK();
+        thth_eig_kernel<EIG_THREADS><<<nb, EIG_THREADS, smem, st>>>(
+            d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, max_iter);
+        SB_LAUNCH_CHECK();
+    }
+    return SB_OK;
+}
+
+__global__ void thth_mask_kernel(ThthGeom g, double eta,
+                                 unsigned char* __restrict__ mask) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= g.n) return;
+    double t = g.th[k];
+    mask[k] = ((__dmul_rn(__dmul_rn(t, t), eta) < g.tau_absmax) &&
+               (fabs(t) < g.fd_half)) ? 1 : 0;
+}
+
+int thth_map(const ThthGeom& g, double eta, int hermitian, float2* d_out,
+             int* d_tau_inv, int* d_fd_inv, unsigned char* d_pnts,
+             unsigned char* d_th_pnts, int* d_err, cudaStream_t st) {
+    if (d_th_pnts) {
+        thth_mask_kernel<<<(g.n + 255) / 256, 256, 0, st>>>(g, eta, d_th_pnts);
+        SB_LAUNCH_CHECK();
+    }
+    if (!d_err) return SB_OK;
+    SB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+    long long total = (long long)g.n * g.n;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    thth_map_kernel<<<blocks, 256, 0, st>>>(g, eta, hermitian, d_out, d_tau_inv,
+                                            d_fd_inv, d_pnts, d_err);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+}  // namespace sb

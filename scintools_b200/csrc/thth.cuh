@@ -1,0 +1,68 @@
+// theta-theta geometry shared by the gather / eigen kernels.
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+// Everything the per-point index math of thth_map needs
+// (reference: scintools/ththmod.py:83-107).  Scalars are computed on the
+// host with the reference's own numpy expressions so they are bit-identical.
+struct ThthGeom {
+    const float2* cs;      // conjugate spectrum [ntau][nfd], fftshifted
+    long long ntau, nfd;
+    double tau0, dtau, half_dtau, tau_absmax;  // tau[0], mean diff, /2, |tau.max()|
+    double fd0, dfd, half_dfd, fd_half;        // fd[0], mean diff, /2, |fd.max()|/2
+    const double* th;      // theta bin centres (recentred), length n
+    int n;
+    int coherent;          // 1: complex CS, 0: |CS| (incoherent theta-theta)
+};
+
+struct ThthPoint {
+    long long tq, fq;  // tau_inv, fd_inv (ththmod.py:94-97)
+    bool pnt;          // pnts mask (ththmod.py:100)
+    bool index_error;  // numpy would raise IndexError (fd_inv < -nfd)
+};
+
+// th1 = theta of the COLUMN, th2 = theta of the ROW (ththmod.py:86-87).
+__device__ __forceinline__ ThthPoint thth_point(const ThthGeom& g, double eta,
+                                                double th1, double th2) {
+    ThthPoint p;
+    double d = __dsub_rn(__dmul_rn(th1, th1), __dmul_rn(th2, th2));
+    double a = __dadd_rn(__dsub_rn(__dmul_rn(eta, d), g.tau0), g.half_dtau);
+    double b = __dadd_rn(__dsub_rn(__dsub_rn(th1, th2), g.fd0), g.half_dfd);
+    double tqd = floor_div_exact(a, g.dtau);
+    double fqd = floor_div_exact(b, g.dfd);
+    // .astype(int): NaN / out-of-range -> INT64_MIN like numpy on x86
+    p.tq = (tqd == tqd && fabs(tqd) < 9.0e18) ? (long long)tqd : LLONG_MIN;
+    p.fq = (fqd == fqd && fabs(fqd) < 9.0e18) ? (long long)fqd : LLONG_MIN;
+    p.pnt = (p.tq > 0) && (p.tq < g.ntau) && (p.fq < g.nfd);
+    p.index_error = p.pnt && (p.fq < -g.nfd);
+    return p;
+}
+
+// Gathered, Jacobian-weighted value before the Hermitian fill
+// (ththmod.py:104,107).  Negative fd_inv wraps like python indexing.
+__device__ __forceinline__ float2 thth_value(const ThthGeom& g, double eta,
+                                             double th1, double th2,
+                                             const ThthPoint& p) {
+    float2 v = make_float2(0.f, 0.f);
+    if (p.pnt && !p.index_error) {
+        long long fi = p.fq < 0 ? p.fq + g.nfd : p.fq;
+        v = __ldg(g.cs + (size_t)p.tq * (size_t)g.nfd + (size_t)fi);
+        if (!g.coherent) v = make_float2(hypotf(v.x, v.y), 0.f);
+    }
+    double w = sqrt(fabs(__dmul_rn(__dmul_rn(2.0, eta), __dsub_rn(th2, th1))));
+    float wf = (float)w;
+    v.x *= wf;
+    v.y *= wf;
+    return v;
+}
+
+// np.nan_to_num on one float component (NaN -> 0, +-inf -> +-FLT_MAX).
+__device__ __forceinline__ float nan_to_num(float x) {
+    if (x != x) return 0.f;
+    if (isinf(x)) return x > 0 ? 3.402823466e+38f : -3.402823466e+38f;
+    return x;
+}
+
+}  // namespace sb

@@ -1,0 +1,332 @@
+"""B200-native mirror of scintools.ththmod's curvature-search API.
+
+Same function names, argument order and failure behaviour as the reference
+(scintools/ththmod.py); the arithmetic runs in libscint_b200 on the GPU:
+
+  fft_axis       ththmod.py:473-493   (host numpy: bit-identical axes)
+  thth_map       ththmod.py:56-116    -> sb_thth_map
+  thth_redmap    ththmod.py:119-173   -> sb_thth_map + crop
+  Eval_calc      ththmod.py:371-401   -> sb_eta_sweep (one eta)
+  eta_sweep      the eta loop of single_search, ththmod.py:789-811 (batched)
+  single_search  ththmod.py:715-895   -> sb_cs_f32 + sb_eta_sweep + host fit
+  min_edges      ththmod.py:1671-1705 (host)
+  chi_par        ththmod.py:38-53     (host)
+
+``CS`` may be a numpy array (uploaded on every call, like the reference's
+per-call semantics) or a ``DeviceCS`` that keeps the spectrum resident.
+There is no CPU fallback.
+"""
+import ctypes
+import warnings
+
+import numpy as np
+from scipy.optimize import curve_fit
+
+from . import _device as D
+from . import _lib
+from . import units as U
+
+DEFAULT_TOL = 2e-5
+
+
+def chi_par(x, A, x0, C):
+    """Parabola for fitting to the eigenvalue curve (ththmod.py:38-53)."""
+    return A * (x - x0) ** 2 + C
+
+
+def unit_checks(var, name, desired):
+    """Reference: ththmod.py:1639-1668.  Returns the float64 value in the
+    desired unit ('us', 'mHz', 's3', 's', 'MHz')."""
+    return U.value(var, desired)
+
+
+def fft_axis(x, unit, pad=0):
+    """Fourier-conjugate coordinates (ththmod.py:473-493).
+
+    ``unit`` may be the strings 'mHz' / 'us' or the astropy units; ``x`` is in
+    s (for mHz) or MHz (for us) when it carries no unit."""
+    uname = unit if isinstance(unit, str) else str(unit)
+    if uname not in ("mHz", "us"):
+        raise ValueError("fft_axis: unit must be mHz or us, got %r" % (unit,))
+    xv = U.value(x, "s" if uname == "mHz" else "MHz")
+    f = np.fft.fftfreq((pad + 1) * xv.shape[0], xv[1] - xv[0])
+    if uname == "mHz":
+        f = f * 1.0e3
+    return U.wrap(np.fft.fftshift(f), uname, like=x)
+
+
+class DeviceCS:
+    """A conjugate spectrum resident in HBM: float32 tensor [ntau][nfd][2]."""
+
+    def __init__(self, tensor):
+        assert tensor.dim() == 3 and tensor.shape[2] == 2
+        self.t = tensor
+        self.shape = (int(tensor.shape[0]), int(tensor.shape[1]))
+
+    @classmethod
+    def from_numpy(cls, CS):
+        CS = np.asarray(CS)
+        if not np.iscomplexobj(CS):
+            CS = CS.astype(np.complex128)   # abs(CS) of the incoherent mode
+        return cls(D.upload_f32(CS))
+
+    def numpy(self):
+        a = self.t.cpu().numpy()
+        return (a[..., 0] + 1j * a[..., 1]).astype(np.complex128)
+
+
+def _as_device_cs(CS):
+    return CS if isinstance(CS, DeviceCS) else DeviceCS.from_numpy(CS)
+
+
+def theta_centres(edges):
+    """Recentred bin centres, ththmod.py:83-84 (same numpy expressions)."""
+    edges = np.asarray(edges, dtype=np.float64)
+    th = (edges[1:] + edges[:-1]) / 2
+    th = th - th[np.abs(th) == np.abs(th).min()]
+    return np.ascontiguousarray(th)
+
+
+class _Geom:
+    """Host-side evaluation of the scalars of thth_map / thth_redmap with the
+    reference's own expressions, packed into struct sb_thth_geom."""
+
+    def __init__(self, cs, tau, fd, edges, coherent=True):
+        tau = U.value(tau, "us")
+        fd = U.value(fd, "mHz")
+        edges = U.value(edges, "mHz")
+        if cs is not None and cs.shape != (tau.shape[0], fd.shape[0]):
+            raise ValueError("CS shape %r does not match (len(tau), len(fd)) "
+                             "= (%d, %d)" % (cs.shape, tau.shape[0], fd.shape[0]))
+        self.cs = cs
+        self.th = theta_centres(edges)
+        self.th_dev = D.upload(self.th)
+        g = _lib.ThthGeom()
+        g.cs = cs.t.data_ptr() if cs is not None else None
+        g.ntau, g.nfd = tau.shape[0], fd.shape[0]
+        g.tau0 = float(tau[0])
+        g.dtau = float(np.diff(tau).mean())
+        g.tau_absmax = float(np.abs(tau.max()))
+        g.fd0 = float(fd[0])
+        g.dfd = float(np.diff(fd).mean())
+        g.fd_half = float(np.abs(fd.max()) / 2)
+        g.th_cents = self.th_dev.data_ptr()
+        g.th_cents_host = self.th.ctypes.data
+        g.n_th = self.th.shape[0]
+        g.coherent = 1 if coherent else 0
+        self.g = g
+
+    @property
+    def ref(self):
+        return ctypes.byref(self.g)
+
+
+def eta_sweep(CS, tau, fd, etas, edges, coher=True, tol=DEFAULT_TOL,
+              max_iter=0, return_info=False):
+    """Largest-eigenvalue curve over ``etas`` (float64 array, NaN where the
+    reference's try/except would have stored NaN, ththmod.py:789-799).
+
+    One launch sequence for the whole sweep: crop masks, gather + Hermitian
+    fill, Lanczos; one eta per thread block."""
+    import torch
+    cs = _as_device_cs(CS)
+    geom = _Geom(cs, tau, fd, edges, coher)
+    ev = np.ascontiguousarray(np.atleast_1d(U.value(etas, "s3")))
+    neta = ev.shape[0]
+    d_etas = D.upload(ev)
+    eigs = D.empty((neta,), torch.float64)
+    status = D.empty((neta,), torch.int32)
+    nred = D.empty((neta,), torch.int32)
+    iters = D.empty((neta,), torch.int32)
+    _lib.check(_lib.lib.sb_eta_sweep(geom.ref, d_etas.data_ptr(), neta, tol,
+                                     max_iter, eigs.data_ptr(),
+                                     status.data_ptr(), nred.data_ptr(),
+                                     iters.data_ptr(), D.stream_ptr()))
+    out = eigs.cpu().numpy()
+    if return_info:
+        return out, dict(status=status.cpu().numpy(), nred=nred.cpu().numpy(),
+                         iters=iters.cpu().numpy())
+    return out
+
+
+def Eval_calc(CS, tau, fd, eta, edges):
+    """Dominant eigenvalue of the theta-theta matrix (ththmod.py:371-401).
+
+    Raises like the reference where scipy/numpy would have raised (callers such
+    as single_search turn that into NaN)."""
+    eigs, info = eta_sweep(CS, tau, fd, np.array([float(U.value(eta, "s3"))]),
+                           edges, True, return_info=True)
+    st = int(info["status"][0])
+    if st & 1:
+        raise IndexError("theta-theta point maps outside the conjugate "
+                         "spectrum (fd_inv < -nfd)")
+    if st & 2:
+        raise ValueError("starting vector is zero (row n//2 of the "
+                         "theta-theta matrix is empty)")
+    if st & 4:
+        raise TypeError("theta-theta matrix too small for eigsh (n < 3)")
+    return float(eigs[0])
+
+
+def thth_map(CS, tau, fd, eta, edges, hermetian=True, return_indices=False):
+    """Map from the conjugate spectrum to theta-theta space (ththmod.py:56-116).
+
+    Returns the complex128 N x N matrix; with ``return_indices`` also the
+    bit-exact tau_inv, fd_inv (int32) and pnts (bool) arrays of
+    ththmod.py:94-100."""
+    import torch
+    cs = _as_device_cs(CS)
+    geom = _Geom(cs, tau, fd, edges, True)
+    n = geom.g.n_th
+    out = D.empty((n, n, 2), torch.float32)
+    err = D.zeros((1,), torch.int32)
+    ti = fi = pn = None
+    if return_indices:
+        ti = D.empty((n, n), torch.int32)
+        fi = D.empty((n, n), torch.int32)
+        pn = D.empty((n, n), torch.uint8)
+    _lib.check(_lib.lib.sb_thth_map(geom.ref, float(U.value(eta, "s3")),
+                                    1 if hermetian else 0, out.data_ptr(),
+                                    D.ptr(ti), D.ptr(fi), D.ptr(pn), 0,
+                                    err.data_ptr(), D.stream_ptr()))
+    if int(err.cpu()[0]) & 1:
+        raise IndexError("index out of bounds (fd_inv < -nfd), ththmod.py:104")
+    a = out.cpu().numpy()
+    thth = a[..., 0].astype(np.float64) + 1j * a[..., 1].astype(np.float64)
+    if return_indices:
+        return thth, ti.cpu().numpy(), fi.cpu().numpy(), pn.cpu().numpy().astype(bool)
+    return thth
+
+
+def th_points(tau, fd, eta, edges):
+    """Crop mask of thth_redmap (ththmod.py:153-156), evaluated on the GPU."""
+    import torch
+    geom = _Geom(None, tau, fd, edges, True)
+    mask = D.empty((geom.g.n_th,), torch.uint8)
+    _lib.check(_lib.lib.sb_thth_map(geom.ref, float(U.value(eta, "s3")), 1, 0,
+                                    0, 0, 0, mask.data_ptr(), 0,
+                                    D.stream_ptr()))
+    return mask.cpu().numpy().astype(bool)
+
+
+def thth_redmap(CS, tau, fd, eta, edges, hermetian=True):
+    """Largest fully-covered square of the theta-theta map (ththmod.py:119-173).
+    Returns (thth_red, edges_red)."""
+    import torch
+    cs = _as_device_cs(CS)
+    geom = _Geom(cs, tau, fd, edges, True)
+    n = geom.g.n_th
+    out = D.empty((n, n, 2), torch.float32)
+    err = D.zeros((1,), torch.int32)
+    mask = D.empty((n,), torch.uint8)
+    _lib.check(_lib.lib.sb_thth_map(geom.ref, float(U.value(eta, "s3")),
+                                    1 if hermetian else 0, out.data_ptr(), 0,
+                                    0, 0, mask.data_ptr(), err.data_ptr(),
+                                    D.stream_ptr()))
+    if int(err.cpu()[0]) & 1:
+        raise IndexError("index out of bounds (fd_inv < -nfd), ththmod.py:104")
+    sel = mask.cpu().numpy().astype(bool)
+    a = out.cpu().numpy()
+    thth = a[..., 0].astype(np.float64) + 1j * a[..., 1].astype(np.float64)
+    red = thth[sel, :][:, sel]
+    er = geom.th[sel]
+    er = (er[:-1] + er[1:]) / 2
+    step = np.diff(er).mean()
+    edges_red = np.concatenate((np.array([er[0] - step]), er,
+                                np.array([er[-1] + step])))
+    return red, U.wrap(edges_red, "mHz", like=edges)
+
+
+def conjugate_spectrum(dspec2, npad, pad_value=None, tau=None, tau_mask=0.0):
+    """CS stage of single_search (ththmod.py:777-787): pad, fft2, fftshift,
+    zero |tau| < tau_mask.  Returns a DeviceCS.  ``pad_value=None`` pads with
+    dspec2.mean() like single_search; 0.0 reproduces
+    Dynspec.thetatheta_single (dynspec.py:1575-1579)."""
+    import torch
+    d = np.asarray(dspec2)
+    nf, nt = d.shape
+    if pad_value is None:
+        pad_value = float(d.mean())
+    dd = D.upload_f32(d)
+    NF, NT = (npad + 1) * nf, (npad + 1) * nt
+    cs = D.empty((NF, NT, 2), torch.float32)
+    mask = None
+    if tau is not None and tau_mask is not None:
+        m = np.abs(U.value(tau, "us")) < float(U.value(tau_mask, "us"))
+        if m.any():
+            mask = D.upload(m.astype(np.uint8))
+    _lib.check(_lib.lib.sb_cs_f32(dd.data_ptr(), nf, nt, npad, float(pad_value),
+                                  D.ptr(mask), cs.data_ptr(), D.stream_ptr()))
+    return DeviceCS(cs)
+
+
+def peak_fit(etas, eigs, fw):
+    """Parabola fit of the eigenvalue peak (ththmod.py:813-859); stays on the
+    host (scipy curve_fit) as in the reference.  NaNs on failure."""
+    try:
+        etas = np.asarray(etas, dtype=np.float64)
+        eigs = np.asarray(eigs, dtype=np.float64)
+        good = np.isfinite(eigs)
+        etas, eigs = etas[good], eigs[good]
+        pk = etas[eigs == eigs.max()]
+        win = np.abs(etas - pk) < fw * pk
+        ef, gf = etas[win], eigs[win]
+        C = gf.max()
+        x0 = ef[gf == C][0]
+        if x0 == ef[0]:
+            A = (gf[-1] - C) / ((ef[-1] - x0) ** 2)
+        else:
+            A = (gf[0] - C) / ((ef[0] - x0) ** 2)
+        popt, _ = curve_fit(chi_par, ef, gf, p0=np.array([A, x0, C]))
+        eta_fit = popt[1]
+        eta_sig = np.sqrt((gf - chi_par(ef, *popt)).std() / np.abs(popt[0]))
+        return eta_fit, eta_sig, popt
+    except Exception:  # noqa: BLE001  (reference: bare except -> NaN)
+        return np.nan, np.nan, None
+
+
+def single_search(params):
+    """Curvature search for one chunk (ththmod.py:715-895).
+
+    ``params`` is the reference's 12-element list
+    [dspec2, freq, time, etas, edges, name, plot, fw, npad, coher, tauMask,
+    verbose]; returns (eta_fit, eta_sig, freq.mean(), time.mean(), eigs).
+    Plotting is not part of the hot path: ``plot=True`` raises."""
+    (dspec2, freq, time, etas, edges, name, plot, fw, npad, coher, tauMask,
+     verbose) = params
+    if plot:
+        raise NotImplementedError("plotting is outside the B200 hot path; "
+                                  "use scintools.ththmod.plot_func on the "
+                                  "returned eigenvalues")
+    time_v = U.value(time, "s")
+    freq_v = U.value(freq, "MHz")
+    etas_v = U.value(etas, "s3")
+    fd = U.value(fft_axis(time_v, "mHz", npad), "mHz")
+    tau = U.value(fft_axis(freq_v, "us", npad), "us")
+    cs = conjugate_spectrum(dspec2, npad, None, tau, tauMask)
+    eigs = eta_sweep(cs, tau, fd, etas_v, edges, bool(coher))
+    eta_fit, eta_sig, _ = peak_fit(etas_v, eigs, fw)
+    if verbose:
+        print("Chunk completed (eta = %s +- %s at %s)" %
+              (eta_fit, eta_sig, freq_v.mean()), flush=True)
+    return (U.wrap(eta_fit, "s3", like=etas), U.wrap(eta_sig, "s3", like=etas),
+            U.wrap(freq_v.mean(), "MHz", like=freq),
+            U.wrap(time_v.mean(), "s", like=time), eigs)
+
+
+def min_edges(fd_lim, fd, tau, eta, factor=2):
+    """Minimum edges array that oversamples the CS (ththmod.py:1671-1705)."""
+    fd_lim_v = float(U.value(fd_lim, "mHz"))
+    fdv, tauv = U.value(fd, "mHz"), U.value(tau, "us")
+    eta_v = float(U.value(eta, "s3"))
+    dtau_lim = (tauv[1] - tauv[0]) / factor
+    dtau_lim /= 2 * eta_v * fd_lim_v
+    dfd_lim = (fdv[1] - fdv[0]) / factor
+    npoints = (2 * fd_lim_v) // (min(dfd_lim, dtau_lim))
+    npoints += np.mod(npoints, 2)
+    return U.wrap(np.linspace(-fd_lim_v, fd_lim_v, int(npoints)), "mHz",
+                  like=fd_lim)
+
+
+def _silence_unused():  # keep flake8 quiet about optional imports
+    return warnings

@@ -1,0 +1,205 @@
+"""GPU parity: CUDA path (through the C-ABI) vs the CPU oracle and the golden
+fixtures generated from the reference.  Tolerances follow BASELINE.json's
+north star: bit-exact index/mask arrays, <= 1e-5 relative (max-norm) for FFT
+floats, <= 1e-5 element-wise relative for eigenvalues."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dynspec_oracle as DO   # noqa: E402
+from oracle import thth_oracle as TO      # noqa: E402
+
+RTOL = 1e-5
+
+
+def maxrel(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import scintools_b200
+    from scintools_b200 import _device
+    _device.device()
+    return scintools_b200
+
+
+@pytest.fixture(scope="module")
+def sample(golden_dir):
+    g = np.load(os.path.join(golden_dir, "thth_sample_64x150.npz"))
+    npad = int(g["npad"])
+    d0 = g["dspec2"] - g["dspec2"].mean()
+    CS = TO.conjugate_spectrum(d0, npad, 0.0)
+    return g, CS
+
+
+def test_thth_indices_bit_exact(sb, sample):
+    g, CS = sample
+    thth = sb.ththmod
+    for eta in (float(g["eta_a"]), float(g["eta_b"]), 12.5, 99.9):
+        th, ti, fi, pn = TO.thth_indices(g["tau"], g["fd"], eta, g["edges"])
+        m, gti, gfi, gpn = thth.thth_map(CS, g["tau"], g["fd"], eta, g["edges"],
+                                         return_indices=True)
+        assert np.array_equal(gti, ti.astype(np.int32))
+        assert np.array_equal(gfi, fi.astype(np.int32))
+        assert np.array_equal(gpn, pn)
+        assert np.array_equal(thth.th_points(g["tau"], g["fd"], eta, g["edges"]),
+                              TO.th_points(g["tau"], g["fd"], eta, g["edges"]))
+
+
+def test_thth_map_values(sb, sample):
+    g, CS = sample
+    thth = sb.ththmod
+    for tag in ("a", "b"):
+        eta = float(g["eta_" + tag])
+        red, er = thth.thth_redmap(CS, g["tau"], g["fd"], eta, g["edges"])
+        ref = g["red_" + tag]
+        assert red.shape == ref.shape
+        assert maxrel(red, ref) < 1e-6
+        assert np.array_equal((red == 0), (ref == 0))
+        assert np.array_equal(er, g["edges_red_" + tag])
+    full = thth.thth_map(CS, g["tau"], g["fd"], 30.0, g["edges"], hermetian=False)
+    assert maxrel(full, TO.thth_map(CS, g["tau"], g["fd"], 30.0, g["edges"], False)) < 1e-6
+
+
+def test_eta_sweep_golden(sb, sample):
+    g, CS = sample
+    eigs, info = sb.ththmod.eta_sweep(CS, g["tau"], g["fd"], g["etas"], g["edges"],
+                                      return_info=True)
+    rel = np.abs(eigs - g["eigs"]) / g["eigs"]
+    assert rel.max() < RTOL, rel.max()
+    assert (info["status"] == 0).all()
+    assert info["iters"].max() < 64
+    # N_red shrinks with eta exactly like the reference crop
+    nred = np.array([TO.th_points(g["tau"], g["fd"], e, g["edges"]).sum()
+                     for e in g["etas"]])
+    assert np.array_equal(info["nred"], nred)
+    # documented known answer (thth_intro.rst:101-104): eta ~ 44 s^3
+    assert abs(g["etas"][np.argmax(eigs)] - 44.0) < 2.0
+    assert sb.ththmod.Eval_calc(CS, g["tau"], g["fd"], g["etas"][37], g["edges"]) == \
+        pytest.approx(g["eigs"][37], rel=RTOL)
+
+
+def test_eta_sweep_incoherent(sb, sample):
+    g, CS = sample
+    tau_mask = 0.5
+    CSm = CS.copy()
+    CSm[np.abs(g["tau"]) < tau_mask] = 0
+    eigs = sb.ththmod.eta_sweep(np.abs(CSm), g["tau"], g["fd"], g["inc_etas"],
+                                g["edges"], coher=True)
+    assert (np.abs(eigs - g["inc_eigs"]) / g["inc_eigs"]).max() < RTOL
+    eigs2 = sb.ththmod.eta_sweep(CSm, g["tau"], g["fd"], g["inc_etas"],
+                                 g["edges"], coher=False)
+    assert (np.abs(eigs2 - g["inc_eigs"]) / g["inc_eigs"]).max() < RTOL
+
+
+def test_eta_sweep_failure_modes(sb, sample):
+    g, CS = sample
+    thth = sb.ththmod
+    # edges far wider than the fd axis: numpy raises IndexError -> NaN
+    wide = np.linspace(-6.0, 6.0, 64)
+    ref = TO.eta_sweep(CS, g["tau"], g["fd"], np.array([20.0, 50.0]), wide)
+    got, info = thth.eta_sweep(CS, g["tau"], g["fd"], np.array([20.0, 50.0]), wide,
+                               return_info=True)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    if ok.any():
+        assert (np.abs(got[ok] - ref[ok]) / ref[ok]).max() < RTOL
+    # all-zero spectrum: NaN start vector -> NaN
+    z = thth.eta_sweep(np.zeros_like(CS), g["tau"], g["fd"], np.array([40.0]), g["edges"])
+    assert np.isnan(z).all()
+    with pytest.raises(Exception):
+        thth.Eval_calc(np.zeros_like(CS), g["tau"], g["fd"], 40.0, g["edges"])
+
+
+def _dyn(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _ds(sb, dyn, dt, df):
+    nf, nt = dyn.shape
+    bd = sb.BasicDyn(dyn, times=dt * np.arange(nt), freqs=1400 + df * np.arange(nf),
+                     dt=dt, df=df)
+    return sb.Dynspec(dyn=bd, verbose=False)
+
+
+def _check_db(got_db, ref_db):
+    lin_g, lin_r = 10 ** (got_db / 10), 10 ** (ref_db / 10)
+    assert maxrel(lin_g, lin_r) < RTOL
+    big = lin_r > 1e-6 * lin_r.max()
+    assert np.max(np.abs(got_db[big] - ref_db[big]) / np.abs(ref_db[big]).clip(1e-3)) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["sspec_acf_48x80.npz", "sspec_acf_64x128.npz"])
+def test_sspec_acf_golden(sb, golden_dir, name):
+    g = _dyn(golden_dir, name)
+    ds = _ds(sb, g["dyn"], float(g["dt"]), float(g["df"]))
+    ds.calc_sspec()
+    assert ds.sspec.shape == g["sspec"].shape
+    assert np.array_equal(ds.fdop, g["fdop"]) and np.array_equal(ds.tdel, g["tdel"])
+    _check_db(ds.sspec, g["sspec"])
+    ds.calc_acf()
+    assert ds.acf.shape == g["acf"].shape
+    assert maxrel(ds.acf, g["acf"]) < RTOL
+    raw = ds.calc_acf(input_dyn=g["dyn"] - g["dyn"].mean(), normalise=False)
+    assert maxrel(raw, DO.calc_acf(g["dyn"], normalise=False)) < RTOL
+
+
+def test_sspec_variants(sb, golden_dir):
+    g = _dyn(golden_dir, "sspec_acf_48x80.npz")
+    ds = _ds(sb, g["dyn"], float(g["dt"]), float(g["df"]))
+    _, _, pw = ds.calc_sspec(prewhite=True, return_sspec=True)
+    _check_db(pw, g["sspec_prewhite"])
+    _, td, full = ds.calc_sspec(halve=False, window="blackman", window_frac=0.25,
+                                return_sspec=True)
+    assert np.array_equal(td, g["tdel_full"])
+    _check_db(full, g["sspec_full_blackman"])
+    _, _, nw = ds.calc_sspec(window=None, return_sspec=True)
+    _check_db(nw, g["sspec_nowindow"])
+    with pytest.raises(RuntimeError):
+        ds.calc_sspec(prewhite=True, halve=False)
+
+
+@pytest.mark.parametrize("shape,npad", [((8, 16), 3), ((64, 128), 3), ((32, 512), 1),
+                                        ((256, 64), 0), ((128, 2048), 3)])
+def test_conjugate_spectrum(sb, shape, npad):
+    rng = np.random.default_rng(5)
+    d = rng.normal(size=shape)
+    d -= d.mean()
+    f = 1400 + 0.05 * np.arange(shape[0])
+    tau = TO.fft_axis(f, "us", npad)
+    for pad_value, mask in ((0.0, 0.0), (0.37, 0.0), (None, 2.0)):
+        ref = TO.conjugate_spectrum(d, npad, pad_value, tau, mask)
+        got = sb.ththmod.conjugate_spectrum(d, npad, pad_value, tau, mask).numpy()
+        assert got.shape == ref.shape
+        assert maxrel(got, ref) < RTOL
+        if mask:
+            assert np.array_equal(got == 0, ref == 0)
+
+
+def test_single_search_end_to_end(sb, golden_dir):
+    """Power-of-two chunk: CS on the GPU + sweep + host parabola fit."""
+    rng = np.random.default_rng(3)
+    nf, nt, npad = 64, 128, 3
+    t = np.arange(nt) * 20.0
+    f = 1400.0 + np.arange(nf) * 0.05
+    eta_true = 30.0
+    fdk = rng.uniform(-6, 6, 24)
+    ak = (rng.normal(size=24) + 1j * rng.normal(size=24)) * np.exp(-(fdk / 3) ** 2)
+    E = sum(a * np.exp(2j * np.pi * (k * 1e-3 * t[None, :] - eta_true * k ** 2 * (f[:, None] - f[0])))
+            for a, k in zip(ak, fdk))
+    dyn = np.abs(E) ** 2
+    dyn += rng.normal(0, 0.05 * dyn.mean(), dyn.shape)
+    d0 = dyn - dyn.mean()
+    edges = np.linspace(-8, 8, 256)
+    etas = np.linspace(15, 60, 46)
+    ref = TO.single_search(d0, f, t, etas, edges, 0.1, npad, True, 0.0)
+    got = sb.ththmod.single_search([d0, f, t, etas, edges, None, False, 0.1, npad,
+                                    True, 0.0, False])
+    assert (np.abs(got[4] - ref[4]) / ref[4]).max() < RTOL
+    assert got[0] == pytest.approx(ref[0], rel=1e-4)
+    assert got[1] == pytest.approx(ref[1], rel=5e-2)
+    assert abs(got[0] - eta_true) / eta_true < 0.1
