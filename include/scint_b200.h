@@ -46,6 +46,16 @@ int sb_init(int device);
 /* free the scratch workspace. */
 int sb_release(void);
 
+/* Per-kernel timing with CUDA events recorded on the launching stream.
+ * Slots: 0 cs_rows 1 cs_colA 2 cs_colB 3 thth_prep 4 thth_build 5 thth_eig
+ * 6 sspec 7 acf 8 sim_screen 9 sim_freq.  sb_profile_collect synchronises the
+ * device, writes accumulated milliseconds and launch counts (host arrays of
+ * at least 16 entries) and resets the accumulators. */
+/* number of kernels this library has launched so far in this process */
+int64_t sb_launch_count(void);
+int sb_profile_enable(int32_t on);
+int sb_profile_collect(double* ms_host, int32_t* count_host, int32_t n);
+
 /* ---- theta-theta ------------------------------------------------------- */
 
 /* Geometry of a conjugate spectrum + theta grid.  Scalars are the

@@ -45,6 +45,9 @@ _SIGS = {
     "sb_last_error": (ctypes.c_char_p, []),
     "sb_init": (c_int, [c_int]),
     "sb_release": (c_int, []),
+    "sb_launch_count": (c_i64, []),
+    "sb_profile_enable": (c_int, [c_int]),
+    "sb_profile_collect": (c_int, [vp, vp, c_int]),
     "sb_eta_sweep": (c_int, [ctypes.POINTER(ThthGeom), vp, c_int, c_dbl, c_int,
                              vp, vp, vp, vp, vp]),
     "sb_thth_map": (c_int, [ctypes.POINTER(ThthGeom), c_dbl, c_int, vp, vp, vp,

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/scint_b200.h"
 #include "common.cuh"
 #include "thth.cuh"
@@ -21,6 +23,38 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 int num_sms() { return g_sms; }
+
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
+// ---- profiling ---------------------------------------------------------
+struct ProfPair { int id; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfPair> g_prof_pending;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t g_prof_open[PROF_COUNT];
+
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) {
+        cudaEvent_t e = g_prof_pool.back();
+        g_prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(int id, cudaStream_t st) {
+    if (!g_prof_on) return;
+    g_prof_open[id] = prof_event();
+    cudaEventRecord(g_prof_open[id], st);
+}
+void prof_end(int id, cudaStream_t st) {
+    if (!g_prof_on) return;
+    cudaEvent_t b = prof_event();
+    cudaEventRecord(b, st);
+    g_prof_pending.push_back({id, g_prof_open[id], b});
+}
 
 void* workspace(int slot, size_t bytes) {
     if (slot < 0 || slot >= 8) return nullptr;
@@ -117,6 +151,29 @@ int sb_init(int device) {
         return SB_ERR_UNSUPPORTED;
     }
     sb::g_sms = prop.multiProcessorCount;
+    return SB_OK;
+}
+
+int64_t sb_launch_count(void) { return sb::g_launches; }
+
+int sb_profile_enable(int32_t on) {
+    sb::g_prof_on = on != 0;
+    return SB_OK;
+}
+
+int sb_profile_collect(double* ms_host, int32_t* count_host, int32_t n) {
+    SB_ARG(ms_host && count_host && n >= sb::PROF_COUNT);
+    for (int i = 0; i < n; ++i) { ms_host[i] = 0.0; count_host[i] = 0; }
+    SB_CUDA(cudaDeviceSynchronize());
+    for (auto& p : sb::g_prof_pending) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        ms_host[p.id] += ms;
+        count_host[p.id] += 1;
+        sb::g_prof_pool.push_back(p.a);
+        sb::g_prof_pool.push_back(p.b);
+    }
+    sb::g_prof_pending.clear();
     return SB_OK;
 }
 

@@ -17,6 +17,19 @@ void* workspace(int slot, size_t bytes);
 void workspace_release();
 int num_sms();
 
+// optional per-kernel timing with CUDA events on the launching stream
+// (sb_profile_enable / sb_profile_collect); ids below
+enum ProfId { PROF_CS_ROWS = 0, PROF_CS_COLA, PROF_CS_COLB, PROF_THTH_PREP,
+              PROF_THTH_BUILD, PROF_THTH_EIG, PROF_SSPEC, PROF_ACF, PROF_SIM_SCREEN,
+              PROF_SIM_FREQ, PROF_COUNT };
+void prof_begin(int id, cudaStream_t st);
+void prof_end(int id, cudaStream_t st);
+struct ProfScope {
+    int id; cudaStream_t st;
+    ProfScope(int i, cudaStream_t s) : id(i), st(s) { prof_begin(id, st); }
+    ~ProfScope() { prof_end(id, st); }
+};
+
 #define SB_CUDA(call)                                                        \
     do {                                                                     \
         cudaError_t _e = (call);                                             \
@@ -27,8 +40,11 @@ int num_sms();
         }                                                                    \
     } while (0)
 
+void count_launch();
+
 #define SB_LAUNCH_CHECK()                                                    \
     do {                                                                     \
+        sb::count_launch();                                                  \
         cudaError_t _e = cudaGetLastError();                                 \
         if (_e != cudaSuccess) {                                             \
             sb::set_error("%s:%d launch -> %s", __FILE__, __LINE__,          \

@@ -322,7 +322,8 @@ static int rows_r2c(const DynRowLoad& ld, float2* H, long pitch, int NT,
 
 template <class StoreB>
 static int cols_forward(const float2* H, float2* A, long pitch, int NF, int live,
-                        int ncols, StoreB stb, cudaStream_t st) {
+                        int ncols, StoreB stb, cudaStream_t st, int profA = -1,
+                        int profB = -1) {
     int R1, R2;
     split_len(NF, &R1, &R2);
     const float2* wR = twiddle_table<float>(NF, -1, st);
@@ -330,10 +331,14 @@ static int cols_forward(const float2* H, float2* A, long pitch, int NF, int live
     ColALoad la{H, pitch, R2, live};
     ColAStore sa{A, pitch, R2, NF, wR};
     int rc = SB_OK;
+    if (profA >= 0) prof_begin(profA, st);
     SB_TILE_DISPATCH(R1, rc = (launch_tile_fft<float, LL, 32, -1>(la, sa, ncols, R2, st)));
+    if (profA >= 0) prof_end(profA, st);
     if (rc) return rc;
     ColBLoad lb{A, pitch, R2};
+    if (profB >= 0) prof_begin(profB, st);
     SB_TILE_DISPATCH(R2, rc = (launch_tile_fft<float, LL, 32, -1>(lb, stb, ncols, R1, st)));
+    if (profB >= 0) prof_end(profB, st);
     return rc;
 }
 
@@ -351,6 +356,7 @@ int stats_pass(const float* dyn, int nf, int nt, const float* wt, const float* w
 int sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
           double swt, double swf, int prewhite, int halve, int db,
           const float* pd1, const float* pd2, float* sec, cudaStream_t st) {
+    ProfScope prof(PROF_SSPEC, st);
     const int NF = 2 * next_pow2(nf), NT = 2 * next_pow2(nt);  // 2^(ceil(log2 n)+1)
     if (NT / 2 < 8 || NT / 2 > 16384 || NF > 65536 || NF < 4) {
         set_error("calc_sspec: dynspec %dx%d outside supported FFT sizes", nf, nt);
@@ -390,17 +396,20 @@ int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
     float2* A = (float2*)workspace(4, (size_t)NF * pitch * sizeof(float2));
     if (!H || !A) return SB_ERR_NOMEM;
     DynRowLoad ld{dyn, nf, nt, nullptr, nullptr, nullptr, 2, 0, pad_value};
+    prof_begin(PROF_CS_ROWS, st);
     int rc = rows_r2c(ld, H, pitch, NT, nf, st);
+    prof_end(PROF_CS_ROWS, st);
     if (rc) return rc;
     int R1, R2;
     split_len(NF, &R1, &R2);
     CsStore cs{CS, NF, NT, R1, rowmask, pad_value * (float)NF * (float)NT};
-    return cols_forward(H, A, pitch, NF, nf, NT / 2 + 1, cs, st);
+    return cols_forward(H, A, pitch, NF, nf, NT / 2 + 1, cs, st, PROF_CS_COLA, PROF_CS_COLB);
 }
 
 // Dynspec.calc_acf(method='direct') (dynspec.py:3780-3797)
 int acf(const float* dyn, int nf, int nt, int subtract_mean, int normalise,
         float* out, cudaStream_t st) {
+    ProfScope prof(PROF_ACF, st);
     const int PF = next_pow2(2L * nf), PT = next_pow2(2L * nt);
     if (PT / 2 < 8 || PT / 2 > 16384 || PF > 65536 || PF < 4) {
         set_error("calc_acf: dynspec %dx%d outside supported FFT sizes", nf, nt);

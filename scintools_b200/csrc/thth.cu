@@ -423,7 +423,9 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
     int* d_idx = (int*)workspace(1, (size_t)neta * ld * sizeof(int));
     if (!d_idx) return SB_ERR_NOMEM;
     SB_CUDA(cudaMemsetAsync(d_status, 0, neta * sizeof(int), st));
+    prof_begin(PROF_THTH_PREP, st);
     thth_prep_kernel<<<neta, 32, 0, st>>>(g, d_etas, neta, ld, d_idx, d_nred);
+    prof_end(PROF_THTH_PREP, st);
     SB_LAUNCH_CHECK();
     if (lower_check_needed(g, th_host)) {
         dim3 grid(64, neta);
@@ -447,10 +449,14 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
     for (int e0 = 0; e0 < neta; e0 += batch) {
         int nb = neta - e0 < batch ? neta - e0 : batch;
         dim3 grid(npairs, nb), block(32, 8);
+        prof_begin(PROF_THTH_BUILD, st);
         thth_build_kernel<<<grid, block, 0, st>>>(g, d_etas, e0, ld, d_idx, d_nred, d_M);
+        prof_end(PROF_THTH_BUILD, st);
         SB_LAUNCH_CHECK();
+        prof_begin(PROF_THTH_EIG, st);
         thth_eig_kernel<EIG_THREADS><<<nb, EIG_THREADS, smem, st>>>(
             d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, max_iter);
+        prof_end(PROF_THTH_EIG, st);
         SB_LAUNCH_CHECK();
     }
     return SB_OK;

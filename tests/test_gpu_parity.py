@@ -129,8 +129,9 @@ def _ds(sb, dyn, dt, df):
 def _check_db(got_db, ref_db):
     lin_g, lin_r = 10 ** (got_db / 10), 10 ** (ref_db / 10)
     assert maxrel(lin_g, lin_r) < RTOL
-    big = lin_r > 1e-6 * lin_r.max()
-    assert np.max(np.abs(got_db[big] - ref_db[big]) / np.abs(ref_db[big]).clip(1e-3)) < 1e-4
+    big = lin_r > 1e-3 * lin_r.max()
+    # dB error = 4.34 * relative power error: absolute 1e-4 dB on significant bins
+    assert np.max(np.abs(got_db[big] - ref_db[big])) < 2e-4
 
 
 @pytest.mark.parametrize("name", ["sspec_acf_48x80.npz", "sspec_acf_64x128.npz"])
