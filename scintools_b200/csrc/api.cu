@@ -126,6 +126,8 @@ static int to_geom(const sb_thth_geom* in, ThthGeom* g) {
     g->fd0 = in->fd0;
     g->dfd = in->dfd;
     g->half_dfd = in->dfd / 2;
+    g->inv_dtau = 1.0 / in->dtau;
+    g->inv_dfd = 1.0 / in->dfd;
     g->fd_half = in->fd_half;
     g->th = in->th_cents;
     g->n = in->n_th;

@@ -100,4 +100,17 @@ __device__ __forceinline__ double floor_div_exact(double a, double b) {
     return copysign(0.0, __ddiv_rn(a, b));
 }
 
+// Same exact floor through a reciprocal: floor(a * (1/b)) is off by at most
+// one for |a/b| < 2^50 and the FMA remainder fixes it.
+__device__ __forceinline__ double floor_div_fast(double a, double b, double inv_b) {
+    double q = floor(a * inv_b);
+    if (b > 0.0 && fabs(q) < 1.0e15) {
+        double r = __fma_rn(-q, b, a);
+        if (r < 0.0) q -= 1.0;
+        else if (r >= b) q += 1.0;
+        return q;
+    }
+    return floor_div_exact(a, b);
+}
+
 }  // namespace sb

@@ -67,16 +67,16 @@ __global__ void thth_indexerr_kernel(ThthGeom g, const double* __restrict__ etas
 }
 
 // --------------------------------------------------------------------------
-// build the cropped Hermitian theta-theta matrix for a batch of etas.
-// grid = (tile pairs, etas in batch); block = 32 x 8.
-// M[e] is [ld][ld] float2, rows/cols < nred valid, zero padded inside the
-// active 32x32 tiles.
+// build the cropped theta-theta matrix for a batch of etas: STRICT UPPER
+// triangle only (the matrix is Hermitian with zero diagonal; the eigen kernel
+// uses every stored element twice).  grid = (tile pairs, etas in batch),
+// block = 32 x 8.  M[e] is [ld][ld] float2; inside the active 32x32 tiles
+// columns >= nred and the diagonal are zero, the lower triangle is not touched.
 // --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0,
                   int ld, const int* __restrict__ idx,
                   const int* __restrict__ nred, float2* __restrict__ M) {
-    __shared__ float2 tile[32][33];
     __shared__ int ia[32], ib[32];
     __shared__ double ta_[32], tb_[32];
     const int e = blockIdx.y;
@@ -101,53 +101,19 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0,
     }
     __syncthreads();
     float2* Me = M + (size_t)e * ld * ld;
-    const float2 zero = make_float2(0.f, 0.f);
-    if (ta != tb) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int la = ty + 8 * k, lb = tx;
-            int i = ia[la], j = ib[lb];
-            float2 v = zero;
-            if (i >= 0 && j >= 0 && i + j != g.n - 1) {
-                ThthPoint pt = thth_point(g, eta, tb_[lb], ta_[la]);
-                v = thth_value(g, eta, tb_[lb], ta_[la], pt);
-                v.x = nan_to_num(v.x);
-                v.y = nan_to_num(v.y);
-            }
-            Me[(size_t)(ta * 32 + la) * ld + tb * 32 + lb] = v;
-            tile[la][lb] = make_float2(v.x, -v.y);
+    for (int k = 0; k < 4; ++k) {
+        const int la = ty + 8 * k, lb = tx;
+        if (ta == tb && lb < la) continue;      // lower triangle: not stored
+        const int i = ia[la], j = ib[lb];
+        float2 v = make_float2(0.f, 0.f);
+        if (i >= 0 && j > i && i + j != g.n - 1) {
+            ThthPoint pt = thth_point(g, eta, tb_[lb], ta_[la]);
+            v = thth_value(g, eta, tb_[lb], ta_[la], pt);
+            v.x = nan_to_num(v.x);
+            v.y = nan_to_num(v.y);
         }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int lb = ty + 8 * k, la = tx;
-            Me[(size_t)(tb * 32 + lb) * ld + ta * 32 + la] = tile[la][lb];
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int la = ty + 8 * k, lb = tx;
-            if (la < lb) {
-                int i = ia[la], j = ib[lb];
-                float2 v = zero;
-                if (i >= 0 && j >= 0 && i + j != g.n - 1) {
-                    ThthPoint pt = thth_point(g, eta, tb_[lb], ta_[la]);
-                    v = thth_value(g, eta, tb_[lb], ta_[la], pt);
-                    v.x = nan_to_num(v.x);
-                    v.y = nan_to_num(v.y);
-                }
-                tile[la][lb] = v;
-                tile[lb][la] = make_float2(v.x, -v.y);
-            } else if (la == lb) {
-                tile[la][lb] = zero;
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int la = ty + 8 * k, lb = tx;
-            Me[(size_t)(ta * 32 + la) * ld + tb * 32 + lb] = tile[la][lb];
-        }
+        Me[(size_t)(ta * 32 + la) * ld + tb * 32 + lb] = v;
     }
 }
 
@@ -163,29 +129,18 @@ struct LanczosShared {
     double beta[SB_LANCZOS_MAXIT + 1];
     double piv[SB_LANCZOS_MAXIT];
     double red[2][32];
-    double theta, lo;
+    double theta, lo, lo2;
     int done;
 };
 
-// Largest eigenvalue of the m x m tridiagonal (alpha[0..m), beta[1..m)) by
-// warp multisection on Sturm counts, then residual bound beta[m]*|s_m|
-// through the twisted (top-down LDL^T) recurrence.  Called by warp 0.
-__device__ void lanczos_check(LanczosShared& S, int m, double tol) {
+// Sturm-count multisection by one warp: smallest sigma in (lo, hi] with
+// count(sigma) >= want, where count = #eigenvalues of the m x m tridiagonal
+// (alpha[0..m), beta[1..m)) below sigma.  Returns the bracket.
+__device__ __forceinline__ void sturm_multisect(const LanczosShared& S, int m,
+                                                int want, double& lo, double& hi,
+                                                int rounds) {
     const int lane = threadIdx.x & 31;
-    const double bnew = S.beta[m];
-    double gh = -DBL_MAX;
-    for (int i = lane; i < m; i += 32) {
-        double b0 = i > 0 ? fabs(S.beta[i]) : 0.0;
-        double b1 = i + 1 < m ? fabs(S.beta[i + 1]) : 0.0;
-        gh = fmax(gh, S.alpha[i] + b0 + b1);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-        gh = fmax(gh, __shfl_xor_sync(0xffffffffu, gh, o));
-    double hi = gh + 1e-9 * fabs(gh) + 1e-290;
-    double lo = (m == 1) ? S.alpha[0] - fabs(S.alpha[0]) * 1e-9 - 1e-290 : S.lo;
-    if (lo > hi) lo = hi - fabs(hi) - 1.0;
-    for (int round = 0; round < 7; ++round) {
+    for (int round = 0; round < rounds; ++round) {
         double sig = lo + (hi - lo) * (double)(lane + 1) / 33.0;
         double d = S.alpha[0] - sig;
         int cnt = d < 0.0;
@@ -194,13 +149,39 @@ __device__ void lanczos_check(LanczosShared& S, int m, double tol) {
             d = (S.alpha[i] - sig) - S.beta[i] * S.beta[i] / d;
             cnt += d < 0.0;
         }
-        unsigned ok = __ballot_sync(0xffffffffu, cnt == m);
+        unsigned ok = __ballot_sync(0xffffffffu, cnt >= want);
         int f = ok ? __ffs(ok) - 1 : 32;
         double nhi = f < 32 ? __shfl_sync(0xffffffffu, sig, f & 31) : hi;
         double nlo = f > 0 ? __shfl_sync(0xffffffffu, sig, (f - 1) & 31) : lo;
         hi = nhi;
         lo = nlo;
     }
+}
+
+// Largest Ritz value theta of T_m, residual bound beta[m]*|s_m| through the
+// twisted (top-down LDL^T) recurrence, and -- once the residual is small --
+// the second Ritz value for the Kato-Temple style error estimate res^2/gap.
+// Converged when res <= tol*theta or res^2 <= etol*theta*gap.  Warp 0 only.
+__device__ void lanczos_check(LanczosShared& S, int m, double tol, double etol) {
+    const int lane = threadIdx.x & 31;
+    const double bnew = S.beta[m];
+    double gh = -DBL_MAX, gl = DBL_MAX;
+    for (int i = lane; i < m; i += 32) {
+        double b0 = i > 0 ? fabs(S.beta[i]) : 0.0;
+        double b1 = i + 1 < m ? fabs(S.beta[i + 1]) : 0.0;
+        gh = fmax(gh, S.alpha[i] + b0 + b1);
+        gl = fmin(gl, S.alpha[i] - b0 - b1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        gh = fmax(gh, __shfl_xor_sync(0xffffffffu, gh, o));
+        gl = fmin(gl, __shfl_xor_sync(0xffffffffu, gl, o));
+    }
+    double hi = gh + 1e-9 * fabs(gh) + 1e-290;
+    double lo = (m == 1) ? S.alpha[0] - fabs(S.alpha[0]) * 1e-9 - 1e-290 : S.lo;
+    if (lo > hi) lo = hi - fabs(hi) - 1.0;
+    sturm_multisect(S, m, m, lo, hi, 7);
+    double res = 0.0;
     if (lane == 0) {
         double sig = hi;
         double d = S.alpha[0] - sig;
@@ -218,25 +199,45 @@ __device__ void lanczos_check(LanczosShared& S, int m, double tol) {
             nrm += z * z;
             if (nrm > 1e200) break;
         }
-        double res = bnew * rsqrt(nrm);
-        S.theta = sig;
+        res = bnew * rsqrt(nrm);
+    }
+    res = __shfl_sync(0xffffffffu, res, 0);
+    const double theta = hi;
+    bool done = (res <= tol * fabs(theta)) || !(bnew > 1e-30 * fabs(theta));
+    if (!done && m >= 3 && res <= 3e-2 * fabs(theta)) {
+        // second Ritz value: smallest sigma with count >= m-1
+        double lo2 = gl - 1e-9 * fabs(gl) - 1e-290, hi2 = theta;
+        sturm_multisect(S, m, m - 1, lo2, hi2, 5);
+        const double gap = theta - hi2;
+        done = gap > 0.0 && res * res <= etol * fabs(theta) * gap;
+    }
+    if (lane == 0) {
+        S.theta = theta;
         S.lo = lo;
-        S.done = (res <= tol * fabs(sig)) || !(bnew > 1e-30 * fabs(sig)) ? 1 : 0;
+        S.done = done ? 1 : 0;
     }
 }
 
+// One CTA per eta.  The matrix is stored as its strict upper triangle; a warp
+// owns rows a = warp, warp+NW, ... and for every stored element A[a][b] adds
+//   A[a][b] * v[b]        to the row sum of a   (warp-shuffle reduction), and
+//   conj(A[a][b]) * v[a]  to a per-lane accumulator of column b,
+// so each element is read once per iteration (half the traffic of a full
+// mat-vec).  Columns are processed in chunks of 512 (lane <-> fixed columns).
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
                 const int* __restrict__ nred, int eta0,
                 double* __restrict__ eigs, int* __restrict__ status,
-                int* __restrict__ iters, double tol, int max_iter) {
+                int* __restrict__ iters, double tol, double etol, int max_iter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = THREADS / 32;
     LanczosShared& S = *reinterpret_cast<LanczosShared*>(smem_raw);
     float2* v = reinterpret_cast<float2*>(smem_raw + sizeof(LanczosShared));
     float2* vp = v + ld;
-    float2* w = vp + ld;
-    constexpr int NW = THREADS / 32;
+    float2* w = vp + ld;          // row sums, then the new Lanczos vector
+    float2* u = w + ld;           // column sums
+    float2* part = u + ld;        // [NW][512] per-warp column partials
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int e = blockIdx.x;
     const int n = nred[eta0 + e];
@@ -254,16 +255,19 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
         }
         return;
     }
-    // v0 = row n//2 (ththmod.py:398-399)
-    double part = 0.0;
+    // v0 = row n//2 of the Hermitian matrix (ththmod.py:398-399)
+    const int h = n / 2;
+    double part0 = 0.0;
     for (int c = tid; c < ld; c += THREADS) {
-        float2 x = c < n ? M[(size_t)(n / 2) * ld + c] : make_float2(0.f, 0.f);
+        float2 x = make_float2(0.f, 0.f);
+        if (c < n && c > h) x = M[(size_t)h * ld + c];
+        else if (c < h) { x = M[(size_t)c * ld + h]; x.y = -x.y; }
         v[c] = x;
         vp[c] = make_float2(0.f, 0.f);
-        part += (double)x.x * x.x + (double)x.y * x.y;
+        part0 += (double)x.x * x.x + (double)x.y * x.y;
     }
-    part = warp_sum(part);
-    if (lane == 0) S.red[0][warp] = part;
+    part0 = warp_sum(part0);
+    if (lane == 0) S.red[0][warp] = part0;
     if (tid == 0) { S.done = 0; S.lo = 0.0; S.theta = 0.0; }
     __syncthreads();
     double nrm2 = 0.0;
@@ -281,40 +285,74 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
     }
     __syncthreads();
 
-    const int ncol4 = (n + 1) >> 1;  // float4 = two complex columns
+    const int ncol4 = (n + 1) >> 1;      // float4 = two complex columns
+    const int nchunk = (n + 511) / 512;  // column chunks of 512
     float beta_prev = 0.f;
     int m = 0;
     for (int it = 0; it < max_iter; ++it) {
-        // ---- w = A v, alpha = Re <v, w>
-        float apart = 0.f;
-        for (int r = warp; r < n; r += NW) {
-            const float4* row = reinterpret_cast<const float4*>(M + (size_t)r * ld);
-            float ax = 0.f, ay = 0.f;
-            for (int c0 = lane; c0 < ncol4; c0 += 128) {
-                float4 mm[4];
+        for (int c = tid; c < ld; c += THREADS) w[c] = make_float2(0.f, 0.f);
+        __syncthreads();
+        for (int cb = 0; cb < nchunk; ++cb) {
+            float4 yc[8];
+            float4 xv[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    int c = c0 + 32 * u;
-                    mm[u] = c < ncol4 ? __ldg(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            for (int j = 0; j < 8; ++j) {
+                yc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int c4 = cb * 256 + lane + 32 * j;
+                xv[j] = (2 * c4 < ld) ? *reinterpret_cast<const float4*>(v + 2 * c4)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const int chunk_end = min(n, (cb + 1) * 512);
+            for (int a = warp; a + 1 < chunk_end; a += NW) {
+                const float4* row = reinterpret_cast<const float4*>(M + (size_t)a * ld);
+                const int first4 = (a + 1) >> 1;
+                const float2 xa = v[a];
+                float4 mm[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    int c = c0 + 32 * u;
-                    if (c < ncol4) {
-                        float4 xx = *reinterpret_cast<const float4*>(v + 2 * c);
-                        ax += mm[u].x * xx.x - mm[u].y * xx.y + mm[u].z * xx.z - mm[u].w * xx.w;
-                        ay += mm[u].x * xx.y + mm[u].y * xx.x + mm[u].z * xx.w + mm[u].w * xx.z;
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const int c4 = cb * 256 + lane + 32 * j;
+                    mm[j] = (c4 >= first4 && c4 < ncol4) ? __ldg(row + c4)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                float rx = 0.f, ry = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 q = mm[j];
+                    rx += q.x * xv[j].x - q.y * xv[j].y + q.z * xv[j].z - q.w * xv[j].w;
+                    ry += q.x * xv[j].y + q.y * xv[j].x + q.z * xv[j].w + q.w * xv[j].z;
+                    // conj(A) * v[a]
+                    yc[j].x += q.x * xa.x + q.y * xa.y;
+                    yc[j].y += q.x * xa.y - q.y * xa.x;
+                    yc[j].z += q.z * xa.x + q.w * xa.y;
+                    yc[j].w += q.z * xa.y - q.w * xa.x;
+                }
+                rx = warp_sum(rx);
+                ry = warp_sum(ry);
+                if (lane == 0) { w[a].x += rx; w[a].y += ry; }
             }
-            ax = warp_sum(ax);
-            ay = warp_sum(ay);
-            if (lane == 0) {
-                w[r] = make_float2(ax, ay);
-                apart += v[r].x * ax + v[r].y * ay;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(part + warp * 512 + 2 * (lane + 32 * j)) = yc[j];
+            __syncthreads();
+            for (int c = tid; c < 512; c += THREADS) {
+                float sx = 0.f, sy = 0.f;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) { sx += part[k * 512 + c].x; sy += part[k * 512 + c].y; }
+                if (cb * 512 + c < ld) u[cb * 512 + c] = make_float2(sx, sy);
             }
+            __syncthreads();
         }
-        if (lane == 0) S.red[0][warp] = (double)apart;
+        // ---- alpha = Re <v, A v>
+        double apart = 0.0;
+        for (int c = tid; c < n; c += THREADS) {
+            float2 x = w[c];
+            x.x += u[c].x;
+            x.y += u[c].y;
+            w[c] = x;
+            apart += (double)(v[c].x * x.x + v[c].y * x.y);
+        }
+        apart = warp_sum(apart);
+        if (lane == 0) S.red[0][warp] = apart;
         __syncthreads();
         double alpha = 0.0;
         for (int k = 0; k < NW; ++k) alpha += S.red[0][k];
@@ -337,7 +375,7 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
         m = it + 1;
         if (tid == 0) { S.alpha[it] = alpha; S.beta[m] = beta; }
         __syncthreads();
-        if (warp == 0) lanczos_check(S, m, tol);
+        if (warp == 0) lanczos_check(S, m, tol, etol);
         __syncthreads();
         if (S.done || !isfinite(alpha)) break;
         // ---- rotate: vp = v, v = w / beta
@@ -442,7 +480,8 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
     const int T = ld / 32;
     const int npairs = T * (T + 1) / 2;
     constexpr int EIG_THREADS = 512;
-    const size_t smem = sizeof(LanczosShared) + 3 * (size_t)ld * sizeof(float2);
+    const size_t smem = sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2) +
+                        (size_t)(EIG_THREADS / 32) * 512 * sizeof(float2);
     SB_CUDA(cudaFuncSetAttribute(thth_eig_kernel<EIG_THREADS>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
@@ -455,7 +494,7 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
         SB_LAUNCH_CHECK();
         prof_begin(PROF_THTH_EIG, st);
         thth_eig_kernel<EIG_THREADS><<<nb, EIG_THREADS, smem, st>>>(
-            d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, max_iter);
+            d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter);
         prof_end(PROF_THTH_EIG, st);
         SB_LAUNCH_CHECK();
     }

@@ -12,6 +12,7 @@ struct ThthGeom {
     long long ntau, nfd;
     double tau0, dtau, half_dtau, tau_absmax;  // tau[0], mean diff, /2, |tau.max()|
     double fd0, dfd, half_dfd, fd_half;        // fd[0], mean diff, /2, |fd.max()|/2
+    double inv_dtau, inv_dfd;                  // reciprocals for the fast exact floor
     const double* th;      // theta bin centres (recentred), length n
     int n;
     int coherent;          // 1: complex CS, 0: |CS| (incoherent theta-theta)
@@ -30,8 +31,8 @@ __device__ __forceinline__ ThthPoint thth_point(const ThthGeom& g, double eta,
     double d = __dsub_rn(__dmul_rn(th1, th1), __dmul_rn(th2, th2));
     double a = __dadd_rn(__dsub_rn(__dmul_rn(eta, d), g.tau0), g.half_dtau);
     double b = __dadd_rn(__dsub_rn(__dsub_rn(th1, th2), g.fd0), g.half_dfd);
-    double tqd = floor_div_exact(a, g.dtau);
-    double fqd = floor_div_exact(b, g.dfd);
+    double tqd = floor_div_fast(a, g.dtau, g.inv_dtau);
+    double fqd = floor_div_fast(b, g.dfd, g.inv_dfd);
     // .astype(int): NaN / out-of-range -> INT64_MIN like numpy on x86
     p.tq = (tqd == tqd && fabs(tqd) < 9.0e18) ? (long long)tqd : LLONG_MIN;
     p.fq = (fqd == fqd && fabs(fqd) < 9.0e18) ? (long long)fqd : LLONG_MIN;
@@ -51,8 +52,8 @@ __device__ __forceinline__ float2 thth_value(const ThthGeom& g, double eta,
         v = __ldg(g.cs + (size_t)p.tq * (size_t)g.nfd + (size_t)fi);
         if (!g.coherent) v = make_float2(hypotf(v.x, v.y), 0.f);
     }
-    double w = sqrt(fabs(__dmul_rn(__dmul_rn(2.0, eta), __dsub_rn(th2, th1))));
-    float wf = (float)w;
+    // Jacobian sqrt|2 eta (th2 - th1)| (ththmod.py:107); fp32 sqrt is ample
+    float wf = sqrtf((float)fabs(2.0 * eta * (th2 - th1)));
     v.x *= wf;
     v.y *= wf;
     return v;
