@@ -135,6 +135,35 @@ int sb_acf_f32(const float* dyn, int32_t nf, int32_t nt, int32_t subtract_mean,
 int sb_cs_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad,
               float pad_value, const uint8_t* tau_rowmask, void* cs, void* stream);
 
+/* ---- scint_sim.Simulation ------------------------------------------------ */
+
+typedef struct sb_sim_params {
+    int32_t nx, ny;
+    double dx, dy, alpha, ar, psi, inner;
+    double consp;   /* Simulation.set_constants (scint_sim.py:137-167), host */
+} sb_sim_params;
+
+/* Spectral amplitude w[nx][ny] (float64): the swdsp fill of
+ * Simulation.get_screen (scint_sim.py:176-198, swdsp :276-292) including the
+ * reference's ky=0 mirror quirk (:185). */
+int sb_sim_weights(const sb_sim_params* p, double* w, void* stream);
+
+/* xyp = real(fft2(w * (n1 + i n2))) in float64 (scint_sim.py:201-204).
+ * noise_re / noise_im: float64 [nx][ny] (the reference's two randn fields, for
+ * seed parity) or both NULL -> counter-based device Gaussian noise from `seed`
+ * (statistically equivalent, not the MT19937 stream). */
+int sb_sim_screen(int32_t nx, int32_t ny, const double* w, const double* noise_re,
+                  const double* noise_im, uint64_t seed, double* xyp, void* stream);
+
+/* Simulation.get_intensity + frfilt3 (scint_sim.py:209-236, 294-311).
+ * scales_host: float64[nf] HOST array of the per-frequency `scale`
+ * (:218-224).  spe_t: complex64 [nf][nx] = spe transposed (spe[:, f] is
+ * column ny//2 of ifft2(filter * fft2(exp(i xyp scale)))); xyi: float32
+ * [nx][ny] intensity of the LAST frequency (:232) or NULL. */
+int sb_sim_intensity(int32_t nx, int32_t ny, int32_t nf, const double* xyp,
+                     const double* scales_host, double ffconx, double ffcony,
+                     void* spe_t, float* xyi, void* stream);
+
 /* element-wise float64 -> float32 (n elements); complex128 -> complex64 is the
  * same call with 2n.  Lets the host layer upload the reference's float64
  * arrays unchanged. */

@@ -136,6 +136,9 @@ def golden_sim(pkg):
         "aniso": dict(mb2=20, ar=2, psi=30, nx=32, ny=96, nf=4, dlam=0.33,
                       seed=5, inner=0.01),
         "lam": dict(mb2=2, ns=64, nf=4, dlam=0.25, seed=3, lamsteps=True),
+        "aniso2": dict(mb2=20, ar=2, psi=30, nx=32, ny=128, nf=4, dlam=0.33,
+                       seed=5, inner=0.01),
+        "strong": dict(mb2=200, ns=128, nf=6, dlam=0.1, seed=11, ar=1.5, psi=-20),
     }
     for tag, kw in cfgs.items():
         s = Sim(verbose=False, **kw)
@@ -153,9 +156,13 @@ def golden_sim(pkg):
 def main():
     os.makedirs(GOLD, exist_ok=True)
     pkg = ref_loader.load()
-    golden_sspec_acf(pkg)
-    golden_thth(pkg)
-    golden_sim(pkg)
+    only = sys.argv[1:]
+    if not only or "sspec" in only:
+        golden_sspec_acf(pkg)
+    if not only or "thth" in only:
+        golden_thth(pkg)
+    if not only or "sim" in only:
+        golden_sim(pkg)
     for fn in sorted(os.listdir(GOLD)):
         print(fn, os.path.getsize(os.path.join(GOLD, fn)) // 1024, "KiB")
 

@@ -40,6 +40,13 @@ class ThthGeom(ctypes.Structure):
     ]
 
 
+class SimParams(ctypes.Structure):
+    """struct sb_sim_params"""
+    _fields_ = [("nx", c_int), ("ny", c_int), ("dx", c_dbl), ("dy", c_dbl),
+                ("alpha", c_dbl), ("ar", c_dbl), ("psi", c_dbl),
+                ("inner", c_dbl), ("consp", c_dbl)]
+
+
 _SIGS = {
     "sb_abi_version": (c_int, []),
     "sb_last_error": (ctypes.c_char_p, []),
@@ -56,6 +63,10 @@ _SIGS = {
                              c_int, c_int, vp, vp, vp, vp]),
     "sb_acf_f32": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp]),
     "sb_cs_f32": (c_int, [vp, c_int, c_int, c_int, c_flt, vp, vp, vp]),
+    "sb_sim_weights": (c_int, [ctypes.POINTER(SimParams), vp, vp]),
+    "sb_sim_screen": (c_int, [c_int, c_int, vp, vp, vp, ctypes.c_uint64, vp, vp]),
+    "sb_sim_intensity": (c_int, [c_int, c_int, c_int, vp, vp, c_dbl, c_dbl, vp,
+                                 vp, vp]),
     "sb_convert_f64_f32": (c_int, [vp, vp, c_i64, vp]),
     "sb_convert_f32_f64": (c_int, [vp, vp, c_i64, vp]),
 }

@@ -103,6 +103,16 @@ int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
 int acf(const float* dyn, int nf, int nt, int subtract_mean, int normalise,
         float* out, cudaStream_t st);
 void twiddle_release();
+struct SimParams {
+    int nx, ny;
+    double dx, dy, alpha, ar, psi, inner, consp;
+};
+int sim_weights(const SimParams& p, double* w, cudaStream_t st);
+int sim_screen(int nx, int ny, const double* w, const double* n1, const double* n2,
+               unsigned long long seed, double* xyp, cudaStream_t st);
+int sim_intensity(int nx, int ny, int nf, const double* xyp, const double* scales_host,
+                  double ffconx, double ffcony, float2* spe_t, float* xyi,
+                  cudaStream_t st);
 
 template <typename A, typename B>
 __global__ void convert_kernel(const A* __restrict__ a, B* __restrict__ b, long long n) {
@@ -232,6 +242,26 @@ int sb_cs_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad,
     SB_ARG(dspec && cs && nf >= 1 && nt >= 1 && npad >= 0);
     return sb::conj_spectrum(dspec, nf, nt, npad, pad_value, tau_rowmask,
                              (float2*)cs, (cudaStream_t)stream);
+}
+
+int sb_sim_weights(const sb_sim_params* p, double* w, void* stream) {
+    SB_ARG(p && w);
+    sb::SimParams q{p->nx, p->ny, p->dx, p->dy, p->alpha, p->ar, p->psi, p->inner, p->consp};
+    return sb::sim_weights(q, w, (cudaStream_t)stream);
+}
+
+int sb_sim_screen(int32_t nx, int32_t ny, const double* w, const double* noise_re,
+                  const double* noise_im, uint64_t seed, double* xyp, void* stream) {
+    SB_ARG(w && xyp && ((noise_re == nullptr) == (noise_im == nullptr)));
+    return sb::sim_screen(nx, ny, w, noise_re, noise_im, seed, xyp, (cudaStream_t)stream);
+}
+
+int sb_sim_intensity(int32_t nx, int32_t ny, int32_t nf, const double* xyp,
+                     const double* scales_host, double ffconx, double ffcony,
+                     void* spe_t, float* xyi, void* stream) {
+    SB_ARG(xyp && scales_host && spe_t && nf >= 1);
+    return sb::sim_intensity(nx, ny, nf, xyp, scales_host, ffconx, ffcony,
+                             (float2*)spe_t, xyi, (cudaStream_t)stream);
 }
 
 int sb_convert_f64_f32(const double* src, float* dst, int64_t n, void* stream) {

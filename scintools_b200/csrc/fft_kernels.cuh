@@ -126,7 +126,7 @@ __device__ __forceinline__ int row_out_pos(int k) {  // where X[k] ends up
 
 // complex -> complex
 template <typename T, int N1, int N2, int DIR, class Load, class Store>
-__global__ void row_fft_c2c_kernel(Load ld, Store st, RowTables<T> tabs) {
+__global__ void __launch_bounds__(512) row_fft_c2c_kernel(Load ld, Store st, RowTables<T> tabs) {
     using C = cx<T>;
     constexpr int N = N1 * N2, RS = N2 + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -144,7 +144,7 @@ __global__ void row_fft_c2c_kernel(Load ld, Store st, RowTables<T> tabs) {
 // real (length 2N, packed two per complex) -> half spectrum X[0..N], forward
 // Load(row, n) returns (x[2n], x[2n+1]); Store(row, k, X[k]) for k in [0, N].
 template <typename T, int N1, int N2, class Load, class Store>
-__global__ void row_fft_r2c_kernel(Load ld, Store st, RowTables<T> tabs) {
+__global__ void __launch_bounds__(512) row_fft_r2c_kernel(Load ld, Store st, RowTables<T> tabs) {
     using C = cx<T>;
     constexpr int N = N1 * N2, RS = N2 + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -178,7 +178,7 @@ __global__ void row_fft_r2c_kernel(Load ld, Store st, RowTables<T> tabs) {
 // half spectrum X[0..N] -> real length 2N, UNNORMALISED inverse.
 // Load(row, k) returns X[k]; Store(row, n, z) receives (x[2n], x[2n+1]).
 template <typename T, int N1, int N2, class Load, class Store>
-__global__ void row_fft_c2r_kernel(Load ld, Store st, RowTables<T> tabs) {
+__global__ void __launch_bounds__(512) row_fft_c2r_kernel(Load ld, Store st, RowTables<T> tabs) {
     using C = cx<T>;
     constexpr int N = N1 * N2, RS = N2 + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -124,7 +124,7 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0,
 // --------------------------------------------------------------------------
 #define SB_LANCZOS_MAXIT 256
 
-struct LanczosShared {
+struct alignas(16) LanczosShared {
     double alpha[SB_LANCZOS_MAXIT];
     double beta[SB_LANCZOS_MAXIT + 1];
     double piv[SB_LANCZOS_MAXIT];
