@@ -78,5 +78,5 @@ def test_simulation_feeds_dynspec(Sim):
     s = Sim(mb2=2, ns=128, nf=64, dlam=0.1, seed=4)
     ds = Dynspec(dyn=s, verbose=False)
     ds.calc_sspec()
-    assert ds.sspec.shape == (128, 256) and np.isfinite(ds.sspec).any()
+    assert ds.sspec.shape == (64, 256) and np.isfinite(ds.sspec).any()
     assert ds.eta == s.eta
