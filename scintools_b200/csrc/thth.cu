@@ -9,6 +9,7 @@
 #include <float.h>
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "thth.cuh"
 
@@ -127,41 +128,57 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0,
 struct alignas(16) LanczosShared {
     double alpha[SB_LANCZOS_MAXIT];
     double beta[SB_LANCZOS_MAXIT + 1];
+    double beta2[SB_LANCZOS_MAXIT + 1];
     double piv[SB_LANCZOS_MAXIT];
     double red[2][32];
-    double theta, lo, lo2;
-    int done;
+    double theta, lo, res;
+    int done, next_check;
 };
 
-// Sturm-count multisection by one warp: smallest sigma in (lo, hi] with
-// count(sigma) >= want, where count = #eigenvalues of the m x m tridiagonal
-// (alpha[0..m), beta[1..m)) below sigma.  Returns the bracket.
+// Number of eigenvalues of the m x m tridiagonal (alpha[0..m), beta[1..m))
+// below sigma = sign changes of the Sturm sequence q_0 = 1, q_1 = alpha_0 -
+// sigma, q_{i+1} = (alpha_i - sigma) q_i - beta_i^2 q_{i-1}.  Division free;
+// q is rescaled by powers of two when it drifts out of range.
+__device__ __forceinline__ int sturm_count(const LanczosShared& S, int m, double sig) {
+    double q0 = 1.0, q1 = S.alpha[0] - sig;
+    bool neg = !(q1 > 0.0);          // a zero counts as a sign change
+    int cnt = neg ? 1 : 0;
+    for (int i = 1; i < m; ++i) {
+        double q2 = (S.alpha[i] - sig) * q1 - S.beta2[i] * q0;
+        const double aq = fabs(q2);
+        if (aq > 1e140) { q2 *= 1e-140; q1 *= 1e-140; }
+        else if (aq < 1e-140 && fabs(q1) < 1e-140) { q2 *= 1e140; q1 *= 1e140; }
+        const bool neg2 = (q2 == 0.0) ? !neg : (q2 < 0.0);
+        cnt += (neg2 != neg);
+        neg = neg2;
+        q0 = q1;
+        q1 = q2;
+    }
+    return cnt;
+}
+
+// warp multisection: smallest sigma in (lo, hi] with count(sigma) >= want
 __device__ __forceinline__ void sturm_multisect(const LanczosShared& S, int m,
                                                 int want, double& lo, double& hi,
                                                 int rounds) {
     const int lane = threadIdx.x & 31;
     for (int round = 0; round < rounds; ++round) {
-        double sig = lo + (hi - lo) * (double)(lane + 1) / 33.0;
-        double d = S.alpha[0] - sig;
-        int cnt = d < 0.0;
-        for (int i = 1; i < m; ++i) {
-            if (fabs(d) < 1e-280) d = -1e-280;
-            d = (S.alpha[i] - sig) - S.beta[i] * S.beta[i] / d;
-            cnt += d < 0.0;
-        }
-        unsigned ok = __ballot_sync(0xffffffffu, cnt >= want);
-        int f = ok ? __ffs(ok) - 1 : 32;
-        double nhi = f < 32 ? __shfl_sync(0xffffffffu, sig, f & 31) : hi;
-        double nlo = f > 0 ? __shfl_sync(0xffffffffu, sig, (f - 1) & 31) : lo;
+        const double sig = lo + (hi - lo) * (double)(lane + 1) / 33.0;
+        const int cnt = sturm_count(S, m, sig);
+        const unsigned ok = __ballot_sync(0xffffffffu, cnt >= want);
+        const int f = ok ? __ffs(ok) - 1 : 32;
+        const double nhi = f < 32 ? __shfl_sync(0xffffffffu, sig, f & 31) : hi;
+        const double nlo = f > 0 ? __shfl_sync(0xffffffffu, sig, (f - 1) & 31) : lo;
         hi = nhi;
         lo = nlo;
     }
 }
 
-// Largest Ritz value theta of T_m, residual bound beta[m]*|s_m| through the
-// twisted (top-down LDL^T) recurrence, and -- once the residual is small --
-// the second Ritz value for the Kato-Temple style error estimate res^2/gap.
-// Converged when res <= tol*theta or res^2 <= etol*theta*gap.  Warp 0 only.
+// Largest Ritz value theta of T_m, residual bound beta[m]*|s_m| (last
+// component of the Ritz vector through the ratios l_i = beta_{i+1} q_i /
+// q_{i+1} of the Sturm sequence at theta), and -- once the residual is small
+// -- the second Ritz value for the error estimate res^2/gap.  Converged when
+// res <= tol*theta or res^2 <= etol*theta*gap.  Called by warp 0.
 __device__ void lanczos_check(LanczosShared& S, int m, double tol, double etol) {
     const int lane = threadIdx.x & 31;
     const double bnew = S.beta[m];
@@ -180,64 +197,105 @@ __device__ void lanczos_check(LanczosShared& S, int m, double tol, double etol) 
     double hi = gh + 1e-9 * fabs(gh) + 1e-290;
     double lo = (m == 1) ? S.alpha[0] - fabs(S.alpha[0]) * 1e-9 - 1e-290 : S.lo;
     if (lo > hi) lo = hi - fabs(hi) - 1.0;
-    sturm_multisect(S, m, m, lo, hi, 7);
+    sturm_multisect(S, m, m, lo, hi, 6);
+    const double theta = hi;
+    // ratios l_i at sigma = theta: lanes in parallel, then a product chain
     double res = 0.0;
     if (lane == 0) {
-        double sig = hi;
-        double d = S.alpha[0] - sig;
-        S.piv[0] = d;
+        double q0 = 1.0, q1 = S.alpha[0] - theta;
         for (int i = 1; i < m; ++i) {
-            if (fabs(d) < 1e-280) d = -1e-280;
-            d = (S.alpha[i] - sig) - S.beta[i] * S.beta[i] / d;
-            S.piv[i] = d;
+            double q2 = (S.alpha[i] - theta) * q1 - S.beta2[i] * q0;
+            const double aq = fabs(q2);
+            if (aq > 1e140) { q2 *= 1e-140; q1 *= 1e-140; }
+            else if (aq < 1e-140 && fabs(q1) < 1e-140) { q2 *= 1e140; q1 *= 1e140; }
+            // l_{i-1} = beta_i * q_{i-1}/q_i in pivot terms: beta_i / d_{i-1}, d = q1/q0
+            S.piv[i - 1] = (q1 != 0.0) ? S.beta[i] * q0 / q1 : 1e300;
+            q0 = q1;
+            q1 = q2;
         }
         double z = 1.0, nrm = 1.0;
         for (int i = m - 2; i >= 0; --i) {
-            double pv = S.piv[i];
-            if (fabs(pv) < 1e-280) pv = -1e-280;
-            z = -(S.beta[i + 1] / pv) * z;
+            z = -S.piv[i] * z;
             nrm += z * z;
-            if (nrm > 1e200) break;
+            if (!(nrm < 1e200)) break;
         }
         res = bnew * rsqrt(nrm);
     }
     res = __shfl_sync(0xffffffffu, res, 0);
-    const double theta = hi;
     bool done = (res <= tol * fabs(theta)) || !(bnew > 1e-30 * fabs(theta));
     if (!done && m >= 3 && res <= 3e-2 * fabs(theta)) {
-        // second Ritz value: smallest sigma with count >= m-1
         double lo2 = gl - 1e-9 * fabs(gl) - 1e-290, hi2 = theta;
-        sturm_multisect(S, m, m - 1, lo2, hi2, 5);
+        sturm_multisect(S, m, m - 1, lo2, hi2, 4);
         const double gap = theta - hi2;
         done = gap > 0.0 && res * res <= etol * fabs(theta) * gap;
     }
     if (lane == 0) {
         S.theta = theta;
         S.lo = lo;
+        S.res = res;
         S.done = done ? 1 : 0;
+        // far from convergence: skip the next check
+        S.next_check = m + ((res > 0.3 * fabs(theta)) ? 2 : 1);
     }
+}
+
+// ---- TMA (bulk async copy) helpers ----------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
+                                         unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
 
 // One CTA per eta.  The matrix is stored as its strict upper triangle; a warp
 // owns rows a = warp, warp+NW, ... and for every stored element A[a][b] adds
 //   A[a][b] * v[b]        to the row sum of a   (warp-shuffle reduction), and
 //   conj(A[a][b]) * v[a]  to a per-lane accumulator of column b,
-// so each element is read once per iteration (half the traffic of a full
-// mat-vec).  Columns are processed in chunks of 512 (lane <-> fixed columns).
-template <int THREADS>
+// so each element is read once per Lanczos step (half the traffic of a full
+// mat-vec).  TMA = true (ld <= 512): every row segment is fetched with one
+// cp.async.bulk into a per-warp ring of NST 4 KB shared-memory stages
+// (mbarrier complete_tx), so ~NST row fetches per warp are in flight while the
+// warp does FMAs.  TMA = false: direct 16-byte loads, any ld, columns in
+// chunks of 512.
+template <int THREADS, bool TMA>
 __global__ void __launch_bounds__(THREADS)
 thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
                 const int* __restrict__ nred, int eta0,
                 double* __restrict__ eigs, int* __restrict__ status,
                 int* __restrict__ iters, double tol, double etol, int max_iter) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NW = THREADS / 32;
+    constexpr int NST = 3;
     LanczosShared& S = *reinterpret_cast<LanczosShared*>(smem_raw);
     float2* v = reinterpret_cast<float2*>(smem_raw + sizeof(LanczosShared));
     float2* vp = v + ld;
     float2* w = vp + ld;          // row sums, then the new Lanczos vector
     float2* u = w + ld;           // column sums
-    float2* part = u + ld;        // [NW][512] per-warp column partials
+    // TMA: [NW][NST][256] float4 stages, re-used as the column-partial scratch
+    float4* stages = reinterpret_cast<float4*>(u + ld);
+    float2* part = reinterpret_cast<float2*>(stages);   // [NW][512]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(
+        reinterpret_cast<unsigned char*>(stages) +
+        (TMA ? (size_t)NW * NST * 4096 : (size_t)NW * 4096));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int e = blockIdx.x;
     const int n = nred[eta0 + e];
@@ -255,6 +313,12 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
         }
         return;
     }
+    if (TMA) {
+        if (tid == 0) {
+            for (int i = 0; i < NW * NST; ++i) mbar_init(mbar + i, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
     // v0 = row n//2 of the Hermitian matrix (ththmod.py:398-399)
     const int h = n / 2;
     double part0 = 0.0;
@@ -268,7 +332,7 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
     }
     part0 = warp_sum(part0);
     if (lane == 0) S.red[0][warp] = part0;
-    if (tid == 0) { S.done = 0; S.lo = 0.0; S.theta = 0.0; }
+    if (tid == 0) { S.done = 0; S.lo = 0.0; S.theta = 0.0; S.next_check = 1; S.beta2[0] = 0.0; }
     __syncthreads();
     double nrm2 = 0.0;
     for (int k = 0; k < NW; ++k) nrm2 += S.red[0][k];
@@ -286,7 +350,10 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
     __syncthreads();
 
     const int ncol4 = (n + 1) >> 1;      // float4 = two complex columns
-    const int nchunk = (n + 511) / 512;  // column chunks of 512
+    const int nchunk = (n + 511) / 512;  // column chunks of 512 (1 when TMA)
+    unsigned gi = 0, gc = 0;             // ring producer / consumer counters
+    float4* mystage = stages + (size_t)warp * NST * 256;
+    unsigned long long* mybar = mbar + warp * NST;
     float beta_prev = 0.f;
     int m = 0;
     for (int it = 0; it < max_iter; ++it) {
@@ -294,42 +361,86 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
         __syncthreads();
         for (int cb = 0; cb < nchunk; ++cb) {
             float4 yc[8];
-            float4 xv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                yc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int c4 = cb * 256 + lane + 32 * j;
-                xv[j] = (2 * c4 < ld) ? *reinterpret_cast<const float4*>(v + 2 * c4)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int j = 0; j < 8; ++j) yc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             const int chunk_end = min(n, (cb + 1) * 512);
-            for (int a = warp; a + 1 < chunk_end; a += NW) {
-                const float4* row = reinterpret_cast<const float4*>(M + (size_t)a * ld);
+            // rows a = warp + NW*k with a + 1 < chunk_end
+            const int K = (chunk_end - 2 >= warp) ? (chunk_end - 2 - warp) / NW + 1 : 0;
+            if (TMA) {
+                // prologue: fill the ring
+                for (int k = 0; k < NST && k < K; ++k) {
+                    const int st = gi % NST;
+                    ++gi;
+                    if (lane == 0) {
+                        const int a = warp + NW * k;
+                        const int c_lo = (a + 1) & ~1;
+                        const unsigned bytes = (unsigned)(2 * ncol4 - c_lo) * 8u;
+                        mbar_expect_tx(mybar + st, bytes);
+                        bulk_g2s(reinterpret_cast<float2*>(mystage + st * 256) + c_lo,
+                                 M + (size_t)a * ld + c_lo, bytes, mybar + st);
+                    }
+                }
+            }
+            for (int k = 0; k < K; ++k) {
+                const int a = warp + NW * k;
                 const int first4 = (a + 1) >> 1;
                 const float2 xa = v[a];
                 float4 mm[8];
+                if (TMA) {
+                    const int st = gc % NST;
+                    const unsigned par = (gc / NST) & 1u;
+                    ++gc;
+                    while (!mbar_try_wait(mybar + st, par)) {}
+                    const float4* sg = mystage + st * 256;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c4 = cb * 256 + lane + 32 * j;
-                    mm[j] = (c4 >= first4 && c4 < ncol4) ? __ldg(row + c4)
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int j = 0; j < 8; ++j) {
+                        const int c4 = lane + 32 * j;
+                        mm[j] = (c4 >= first4 && c4 < ncol4) ? sg[c4]
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                } else {
+                    const float4* row = reinterpret_cast<const float4*>(M + (size_t)a * ld);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int c4 = cb * 256 + lane + 32 * j;
+                        mm[j] = (c4 >= first4 && c4 < ncol4) ? __ldg(row + c4)
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
                 float rx = 0.f, ry = 0.f;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
+                    const int c4 = cb * 256 + lane + 32 * j;
                     const float4 q = mm[j];
-                    rx += q.x * xv[j].x - q.y * xv[j].y + q.z * xv[j].z - q.w * xv[j].w;
-                    ry += q.x * xv[j].y + q.y * xv[j].x + q.z * xv[j].w + q.w * xv[j].z;
+                    const float4 x = (2 * c4 < ld) ? *reinterpret_cast<const float4*>(v + 2 * c4)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                    rx += q.x * x.x - q.y * x.y + q.z * x.z - q.w * x.w;
+                    ry += q.x * x.y + q.y * x.x + q.z * x.w + q.w * x.z;
                     // conj(A) * v[a]
                     yc[j].x += q.x * xa.x + q.y * xa.y;
                     yc[j].y += q.x * xa.y - q.y * xa.x;
                     yc[j].z += q.z * xa.x + q.w * xa.y;
                     yc[j].w += q.z * xa.y - q.w * xa.x;
                 }
+                if (TMA) {
+                    __syncwarp();
+                    const bool more = k + NST < K;
+                    const int st = gi % NST;   // == the stage just consumed
+                    if (more) ++gi;
+                    if (lane == 0 && more) {
+                        const int a2 = warp + NW * (k + NST);
+                        const int c_lo = (a2 + 1) & ~1;
+                        const unsigned bytes = (unsigned)(2 * ncol4 - c_lo) * 8u;
+                        mbar_expect_tx(mybar + st, bytes);
+                        bulk_g2s(reinterpret_cast<float2*>(mystage + st * 256) + c_lo,
+                                 M + (size_t)a2 * ld + c_lo, bytes, mybar + st);
+                    }
+                }
                 rx = warp_sum(rx);
                 ry = warp_sum(ry);
                 if (lane == 0) { w[a].x += rx; w[a].y += ry; }
             }
+            if (TMA) __syncthreads();   // every warp is done with its stages
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(part + warp * 512 + 2 * (lane + 32 * j)) = yc[j];
@@ -340,6 +451,7 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
                 for (int k = 0; k < NW; ++k) { sx += part[k * 512 + c].x; sy += part[k * 512 + c].y; }
                 if (cb * 512 + c < ld) u[cb * 512 + c] = make_float2(sx, sy);
             }
+            if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
         }
         // ---- alpha = Re <v, A v>
@@ -373,9 +485,10 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
         for (int k = 0; k < NW; ++k) b2 += S.red[1][k];
         const double beta = sqrt(b2);
         m = it + 1;
-        if (tid == 0) { S.alpha[it] = alpha; S.beta[m] = beta; }
+        if (tid == 0) { S.alpha[it] = alpha; S.beta[m] = beta; S.beta2[m] = b2; }
         __syncthreads();
-        if (warp == 0) lanczos_check(S, m, tol, etol);
+        const bool last = (it + 1 == max_iter);
+        if (warp == 0 && (m >= S.next_check || last || !(beta > 0.0))) lanczos_check(S, m, tol, etol);
         __syncthreads();
         if (S.done || !isfinite(alpha)) break;
         // ---- rotate: vp = v, v = w / beta
@@ -480,11 +593,16 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
     const int T = ld / 32;
     const int npairs = T * (T + 1) / 2;
     constexpr int EIG_THREADS = 512;
+    const bool use_tma = (ld <= 512) && !getenv("SB_EIG_NO_TMA");
     const size_t smem = sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2) +
-                        (size_t)(EIG_THREADS / 32) * 512 * sizeof(float2);
-    SB_CUDA(cudaFuncSetAttribute(thth_eig_kernel<EIG_THREADS>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
+                        (use_tma ? (size_t)(EIG_THREADS / 32) * 3 * 4096 + 512
+                                 : (size_t)(EIG_THREADS / 32) * 4096 + 512);
+    if (use_tma)
+        SB_CUDA(cudaFuncSetAttribute(thth_eig_kernel<EIG_THREADS, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+        SB_CUDA(cudaFuncSetAttribute(thth_eig_kernel<EIG_THREADS, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int e0 = 0; e0 < neta; e0 += batch) {
         int nb = neta - e0 < batch ? neta - e0 : batch;
         dim3 grid(npairs, nb), block(32, 8);
@@ -493,8 +611,12 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
         prof_end(PROF_THTH_BUILD, st);
         SB_LAUNCH_CHECK();
         prof_begin(PROF_THTH_EIG, st);
-        thth_eig_kernel<EIG_THREADS><<<nb, EIG_THREADS, smem, st>>>(
-            d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter);
+        if (use_tma)
+            thth_eig_kernel<EIG_THREADS, true><<<nb, EIG_THREADS, smem, st>>>(
+                d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter);
+        else
+            thth_eig_kernel<EIG_THREADS, false><<<nb, EIG_THREADS, smem, st>>>(
+                d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter);
         prof_end(PROF_THTH_EIG, st);
         SB_LAUNCH_CHECK();
     }
