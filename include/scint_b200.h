@@ -66,14 +66,21 @@ int sb_profile_collect(double* ms_host, int32_t* count_host, int32_t n);
  *   th_cents = recentred bin centres of `edges` (device, float64, n of them)
  */
 typedef struct sb_thth_geom {
-    const void* cs;        /* float2 [ntau][nfd], fftshifted conjugate spectrum */
-    int64_t ntau, nfd;
+    const void* cs;        /* float2 conjugate spectrum, rows fftshifted (see cs_half) */
+    int64_t ntau, nfd;     /* logical size: len(tau), len(fd) */
     double tau0, dtau, tau_absmax;
     double fd0, dfd, fd_half;
     const double* th_cents;      /* device */
     const double* th_cents_host; /* same values on the host */
     int32_t n_th;
     int32_t coherent;      /* 1: complex CS; 0: |CS| (ththmod.py:801) */
+    int64_t cs_pitch;      /* elements per stored row (nfd for a plain full array) */
+    int32_t cs_half;       /* 0: full fftshifted [ntau][nfd].  1: Hermitian half as
+                              written by sb_cs_f32(half_plane=1): [ntau][cs_pitch],
+                              columns k = 0..nfd/2 are the NON-shifted fd >= 0 bins;
+                              the rest follows from CS[-tau,-fd] = conj(CS[tau,fd])
+                              (valid for the CS of a real dynamic spectrum) */
+    int32_t reserved;
 } sb_thth_geom;
 
 /* Replaces the eta loop of ththmod.single_search (ththmod.py:789-811) /
@@ -130,10 +137,14 @@ int sb_acf_f32(const float* dyn, int32_t nf, int32_t nt, int32_t subtract_mean,
  *   CS = fftshift(fft2(pad(dspec, npad copies, constant pad_value)));
  *   CS[tau_rowmask] = 0
  * dspec float32 [nf][nt]; cs: float2 [(npad+1)nf][(npad+1)nt]; tau_rowmask:
- * uint8 [(npad+1)nf] (1 = zero that fftshifted row) or NULL.  Padded sizes must
- * be powers of two in this version. */
+ * uint8 [(npad+1)nf] (1 = zero that fftshifted row) or NULL.  half_plane=1
+ * writes only the fd >= 0 half, [(npad+1)nf][cs_pitch] with cs_pitch >=
+ * (npad+1)nt/2 + 1 (see sb_thth_geom.cs_half): half the HBM traffic, and all
+ * the theta-theta sweep needs.  half_plane=0: full array, cs_pitch ignored.
+ * Padded sizes must be powers of two in this version. */
 int sb_cs_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad,
-              float pad_value, const uint8_t* tau_rowmask, void* cs, void* stream);
+              float pad_value, const uint8_t* tau_rowmask, int32_t half_plane,
+              int64_t cs_pitch, void* cs, void* stream);
 
 /* ---- scint_sim.Simulation ------------------------------------------------ */
 

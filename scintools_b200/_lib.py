@@ -37,6 +37,7 @@ class ThthGeom(ctypes.Structure):
         ("fd0", c_dbl), ("dfd", c_dbl), ("fd_half", c_dbl),
         ("th_cents", vp), ("th_cents_host", vp),
         ("n_th", c_int), ("coherent", c_int),
+        ("cs_pitch", c_i64), ("cs_half", c_int), ("reserved", c_int),
     ]
 
 
@@ -62,7 +63,7 @@ _SIGS = {
     "sb_sspec_f32": (c_int, [vp, c_int, c_int, vp, vp, c_dbl, c_dbl, c_int,
                              c_int, c_int, vp, vp, vp, vp]),
     "sb_acf_f32": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp]),
-    "sb_cs_f32": (c_int, [vp, c_int, c_int, c_int, c_flt, vp, vp, vp]),
+    "sb_cs_f32": (c_int, [vp, c_int, c_int, c_int, c_flt, vp, c_int, c_i64, vp, vp]),
     "sb_sim_weights": (c_int, [ctypes.POINTER(SimParams), vp, vp]),
     "sb_sim_screen": (c_int, [c_int, c_int, vp, vp, vp, ctypes.c_uint64, vp, vp]),
     "sb_sim_intensity": (c_int, [c_int, c_int, c_int, vp, vp, c_dbl, c_dbl, vp,

@@ -99,7 +99,8 @@ int sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
           double swt, double swf, int prewhite, int halve, int db,
           const float* pd1, const float* pd2, float* sec, cudaStream_t st);
 int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
-                  const unsigned char* rowmask, float2* CS, cudaStream_t st);
+                  const unsigned char* rowmask, int half, long pitch, float2* CS,
+                  cudaStream_t st);
 int acf(const float* dyn, int nf, int nt, int subtract_mean, int normalise,
         float* out, cudaStream_t st);
 void twiddle_release();
@@ -142,6 +143,9 @@ static int to_geom(const sb_thth_geom* in, ThthGeom* g) {
     g->th = in->th_cents;
     g->n = in->n_th;
     g->coherent = in->coherent;
+    g->cs_half = in->cs_half;
+    g->cs_pitch = in->cs_half ? in->cs_pitch : (in->cs_pitch > 0 ? in->cs_pitch : in->nfd);
+    SB_ARG(!in->cs_half || (in->cs_pitch >= in->nfd / 2 + 1 && in->nfd % 2 == 0));
     return SB_OK;
 }
 
@@ -238,10 +242,13 @@ int sb_acf_f32(const float* dyn, int32_t nf, int32_t nt, int32_t subtract_mean,
 }
 
 int sb_cs_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad,
-              float pad_value, const uint8_t* tau_rowmask, void* cs, void* stream) {
+              float pad_value, const uint8_t* tau_rowmask, int32_t half_plane,
+              int64_t cs_pitch, void* cs, void* stream) {
     SB_ARG(dspec && cs && nf >= 1 && nt >= 1 && npad >= 0);
+    SB_ARG(!half_plane || cs_pitch >= (int64_t)(npad + 1) * nt / 2 + 1);
     return sb::conj_spectrum(dspec, nf, nt, npad, pad_value, tau_rowmask,
-                             (float2*)cs, (cudaStream_t)stream);
+                             half_plane, (long)cs_pitch, (float2*)cs,
+                             (cudaStream_t)stream);
 }
 
 int sb_sim_weights(const sb_sim_params* p, double* w, void* stream) {

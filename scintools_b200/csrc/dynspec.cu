@@ -163,10 +163,17 @@ struct CsStore {
     int NF, NT, R1;
     const unsigned char* rowmask;   // [NF] in fftshifted row order, or null
     float dc;
+    int half;       // 1: write only the fd >= 0 half, [NF][pitch], column = c
+    long pitch;
     __device__ __forceinline__ void operator()(int y, int k, int c, float2 v) const {
         const int kf = y + R1 * k;
         if (kf == 0 && c == 0) v.x += dc;
         const int rs = (kf + NF / 2) & (NF - 1);
+        if (half) {
+            const bool mh = rowmask && rowmask[rs];
+            CS[(size_t)rs * pitch + c] = mh ? make_float2(0.f, 0.f) : v;
+            return;
+        }
         const int cs = (c + NT / 2) & (NT - 1);
         const bool m0 = rowmask && rowmask[rs];
         CS[(size_t)rs * NT + cs] = m0 ? make_float2(0.f, 0.f) : v;
@@ -382,7 +389,8 @@ int sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
 // conjugate spectrum of a zero(/constant)-padded chunk
 // (ththmod.py:777-787, dynspec.py:1572-1579)
 int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
-                  const unsigned char* rowmask, float2* CS, cudaStream_t st) {
+                  const unsigned char* rowmask, int half, long cs_pitch, float2* CS,
+                  cudaStream_t st) {
     const long NFl = (long)(npad + 1) * nf, NTl = (long)(npad + 1) * nt;
     if (!is_pow2(NFl) || !is_pow2(NTl) || NTl / 2 < 8 || NTl / 2 > 16384 ||
         NFl > 65536 || NFl < 4) {
@@ -402,7 +410,7 @@ int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
     if (rc) return rc;
     int R1, R2;
     split_len(NF, &R1, &R2);
-    CsStore cs{CS, NF, NT, R1, rowmask, pad_value * (float)NF * (float)NT};
+    CsStore cs{CS, NF, NT, R1, rowmask, pad_value * (float)NF * (float)NT, half, cs_pitch};
     return cols_forward(H, A, pitch, NF, nf, NT / 2 + 1, cs, st, PROF_CS_COLA, PROF_CS_COLB);
 }
 

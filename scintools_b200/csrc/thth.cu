@@ -276,7 +276,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
 // (mbarrier complete_tx), so ~NST row fetches per warp are in flight while the
 // warp does FMAs.  TMA = false: direct 16-byte loads, any ld, columns in
 // chunks of 512.
-template <int THREADS, bool TMA>
+template <int THREADS, bool TMA, int NST>
 __global__ void __launch_bounds__(THREADS)
 thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
                 const int* __restrict__ nred, int eta0,
@@ -284,7 +284,6 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
                 int* __restrict__ iters, double tol, double etol, int max_iter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NW = THREADS / 32;
-    constexpr int NST = 3;
     LanczosShared& S = *reinterpret_cast<LanczosShared*>(smem_raw);
     float2* v = reinterpret_cast<float2*>(smem_raw + sizeof(LanczosShared));
     float2* vp = v + ld;
@@ -408,8 +407,10 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
                     }
                 }
                 float rx = 0.f, ry = 0.f;
+                const int jskip = (first4 - cb * 256) >> 5;   // groups entirely left of the diagonal
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
+                    if (j < jskip) continue;
                     const int c4 = cb * 256 + lane + 32 * j;
                     const float4 q = mm[j];
                     const float4 x = (2 * c4 < ld) ? *reinterpret_cast<const float4*>(v + 2 * c4)
@@ -592,16 +593,19 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
     if (!d_M) return SB_ERR_NOMEM;
     const int T = ld / 32;
     const int npairs = T * (T + 1) / 2;
-    constexpr int EIG_THREADS = 512;
+    // TMA ring variant (ld <= 512): 256 threads, 2 stages -> 2 CTAs per SM so
+    // one CTA streams while the other is in its serial Lanczos bookkeeping
+    constexpr int TT = 256, TS = 2;      // TMA: threads, stages
+    constexpr int DT = 512;              // direct-load variant
     const bool use_tma = (ld <= 512) && !getenv("SB_EIG_NO_TMA");
     const size_t smem = sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2) +
-                        (use_tma ? (size_t)(EIG_THREADS / 32) * 3 * 4096 + 512
-                                 : (size_t)(EIG_THREADS / 32) * 4096 + 512);
+                        (use_tma ? (size_t)(TT / 32) * TS * 4096 + 512
+                                 : (size_t)(DT / 32) * 4096 + 512);
     if (use_tma)
-        SB_CUDA(cudaFuncSetAttribute(thth_eig_kernel<EIG_THREADS, true>,
+        SB_CUDA(cudaFuncSetAttribute(thth_eig_kernel<TT, true, TS>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else
-        SB_CUDA(cudaFuncSetAttribute(thth_eig_kernel<EIG_THREADS, false>,
+        SB_CUDA(cudaFuncSetAttribute(thth_eig_kernel<DT, false, 1>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int e0 = 0; e0 < neta; e0 += batch) {
         int nb = neta - e0 < batch ? neta - e0 : batch;
@@ -612,10 +616,10 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
         SB_LAUNCH_CHECK();
         prof_begin(PROF_THTH_EIG, st);
         if (use_tma)
-            thth_eig_kernel<EIG_THREADS, true><<<nb, EIG_THREADS, smem, st>>>(
+            thth_eig_kernel<TT, true, TS><<<nb, TT, smem, st>>>(
                 d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter);
         else
-            thth_eig_kernel<EIG_THREADS, false><<<nb, EIG_THREADS, smem, st>>>(
+            thth_eig_kernel<DT, false, 1><<<nb, DT, smem, st>>>(
                 d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter);
         prof_end(PROF_THTH_EIG, st);
         SB_LAUNCH_CHECK();

@@ -8,8 +8,11 @@ namespace sb {
 // (reference: scintools/ththmod.py:83-107).  Scalars are computed on the
 // host with the reference's own numpy expressions so they are bit-identical.
 struct ThthGeom {
-    const float2* cs;      // conjugate spectrum [ntau][nfd], fftshifted
-    long long ntau, nfd;
+    const float2* cs;      // conjugate spectrum, fftshifted rows
+    long long ntau, nfd;   // logical size
+    long long cs_pitch;    // elements per stored row
+    int cs_half;           // 0: full [ntau][nfd]; 1: Hermitian half [ntau][nfd/2+1]
+                           //    holding the UNSHIFTED columns k = 0..nfd/2 (fd >= 0)
     double tau0, dtau, half_dtau, tau_absmax;  // tau[0], mean diff, /2, |tau.max()|
     double fd0, dfd, half_dfd, fd_half;        // fd[0], mean diff, /2, |fd.max()|/2
     double inv_dtau, inv_dfd;                  // reciprocals for the fast exact floor
@@ -49,7 +52,19 @@ __device__ __forceinline__ float2 thth_value(const ThthGeom& g, double eta,
     float2 v = make_float2(0.f, 0.f);
     if (p.pnt && !p.index_error) {
         long long fi = p.fq < 0 ? p.fq + g.nfd : p.fq;
-        v = __ldg(g.cs + (size_t)p.tq * (size_t)g.nfd + (size_t)fi);
+        if (!g.cs_half) {
+            v = __ldg(g.cs + (size_t)p.tq * (size_t)g.cs_pitch + (size_t)fi);
+        } else {
+            // CS of a real dynamic spectrum: CS[-tau, -fd] = conj(CS[tau, fd])
+            const long long h = g.nfd / 2;
+            long long r = p.tq, c;
+            bool cj = false;
+            if (fi >= h) c = fi - h;
+            else if (fi == 0) c = h;
+            else { c = h - fi; r = (g.ntau - p.tq) % g.ntau; cj = true; }
+            v = __ldg(g.cs + (size_t)r * (size_t)g.cs_pitch + (size_t)c);
+            if (cj) v.y = -v.y;
+        }
         if (!g.coherent) v = make_float2(hypotf(v.x, v.y), 0.f);
     }
     // Jacobian sqrt|2 eta (th2 - th1)| (ththmod.py:107); fp32 sqrt is ample

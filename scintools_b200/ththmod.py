@@ -56,12 +56,19 @@ def fft_axis(x, unit, pad=0):
 
 
 class DeviceCS:
-    """A conjugate spectrum resident in HBM: float32 tensor [ntau][nfd][2]."""
+    """A conjugate spectrum resident in HBM.
 
-    def __init__(self, tensor):
+    full: float32 tensor [ntau][nfd][2] (fftshifted, like the reference's CS).
+    half (``nfd`` given): [ntau][pitch][2] holding only the fd >= 0 columns
+    (unshifted k = 0..nfd/2) of the CS of a REAL dynamic spectrum; the other
+    half is its Hermitian mirror and is never materialised."""
+
+    def __init__(self, tensor, nfd=None):
         assert tensor.dim() == 3 and tensor.shape[2] == 2
         self.t = tensor
-        self.shape = (int(tensor.shape[0]), int(tensor.shape[1]))
+        self.half = nfd is not None
+        self.pitch = int(tensor.shape[1])
+        self.shape = (int(tensor.shape[0]), int(nfd) if self.half else self.pitch)
 
     @classmethod
     def from_numpy(cls, CS):
@@ -71,8 +78,20 @@ class DeviceCS:
         return cls(D.upload_f32(CS))
 
     def numpy(self):
+        """The full fftshifted complex128 array (expands a half-plane CS)."""
         a = self.t.cpu().numpy()
-        return (a[..., 0] + 1j * a[..., 1]).astype(np.complex128)
+        z = (a[..., 0] + 1j * a[..., 1]).astype(np.complex128)
+        if not self.half:
+            return z
+        ntau, nfd = self.shape
+        h = nfd // 2
+        pos = z[:, :h + 1]                       # unshifted columns 0..h
+        full = np.empty((ntau, nfd), dtype=np.complex128)
+        full[:, h:] = pos[:, :h]                 # shifted columns h..nfd-1
+        full[:, 0] = pos[:, h]                   # Nyquist column
+        rows = (ntau - np.arange(ntau)) % ntau   # mirrored (shifted) row index
+        full[:, 1:h] = np.conj(pos[rows][:, h - 1:0:-1])
+        return full
 
 
 def _as_device_cs(CS):
@@ -114,6 +133,8 @@ class _Geom:
         g.th_cents_host = self.th.ctypes.data
         g.n_th = self.th.shape[0]
         g.coherent = 1 if coherent else 0
+        g.cs_half = 1 if (cs is not None and cs.half) else 0
+        g.cs_pitch = cs.pitch if cs is not None else fd.shape[0]
         self.g = g
 
     @property
@@ -237,11 +258,14 @@ def thth_redmap(CS, tau, fd, eta, edges, hermetian=True):
     return red, U.wrap(edges_red, "mHz", like=edges)
 
 
-def conjugate_spectrum(dspec2, npad, pad_value=None, tau=None, tau_mask=0.0):
+def conjugate_spectrum(dspec2, npad, pad_value=None, tau=None, tau_mask=0.0,
+                       half=True):
     """CS stage of single_search (ththmod.py:777-787): pad, fft2, fftshift,
     zero |tau| < tau_mask.  Returns a DeviceCS.  ``pad_value=None`` pads with
     dspec2.mean() like single_search; 0.0 reproduces
-    Dynspec.thetatheta_single (dynspec.py:1575-1579)."""
+    Dynspec.thetatheta_single (dynspec.py:1575-1579).  ``half=True`` keeps only
+    the fd >= 0 half on the device (the spectrum of a real array is Hermitian;
+    ``.numpy()`` still returns the full array)."""
     import torch
     d = np.asarray(dspec2)
     nf, nt = d.shape
@@ -249,15 +273,17 @@ def conjugate_spectrum(dspec2, npad, pad_value=None, tau=None, tau_mask=0.0):
         pad_value = float(d.mean())
     dd = D.upload_f32(d)
     NF, NT = (npad + 1) * nf, (npad + 1) * nt
-    cs = D.empty((NF, NT, 2), torch.float32)
+    pitch = NT // 2 + 16 if half else NT
+    cs = D.empty((NF, pitch, 2), torch.float32)
     mask = None
     if tau is not None and tau_mask is not None:
         m = np.abs(U.value(tau, "us")) < float(U.value(tau_mask, "us"))
         if m.any():
             mask = D.upload(m.astype(np.uint8))
     _lib.check(_lib.lib.sb_cs_f32(dd.data_ptr(), nf, nt, npad, float(pad_value),
-                                  D.ptr(mask), cs.data_ptr(), D.stream_ptr()))
-    return DeviceCS(cs)
+                                  D.ptr(mask), 1 if half else 0, pitch,
+                                  cs.data_ptr(), D.stream_ptr()))
+    return DeviceCS(cs, nfd=NT if half else None)
 
 
 def peak_fit(etas, eigs, fw):

@@ -176,11 +176,44 @@ def test_conjugate_spectrum(sb, shape, npad):
     tau = TO.fft_axis(f, "us", npad)
     for pad_value, mask in ((0.0, 0.0), (0.37, 0.0), (None, 2.0)):
         ref = TO.conjugate_spectrum(d, npad, pad_value, tau, mask)
-        got = sb.ththmod.conjugate_spectrum(d, npad, pad_value, tau, mask).numpy()
-        assert got.shape == ref.shape
-        assert maxrel(got, ref) < RTOL
-        if mask:
-            assert np.array_equal(got == 0, ref == 0)
+        for half in (False, True):
+            got = sb.ththmod.conjugate_spectrum(d, npad, pad_value, tau, mask,
+                                                half=half).numpy()
+            assert got.shape == ref.shape
+            assert maxrel(got, ref) < RTOL
+            if mask:
+                assert np.array_equal(got == 0, ref == 0)
+
+
+def test_half_plane_sweep_matches_full(sb):
+    """The sweep on the Hermitian half-plane CS equals the sweep on the full
+    array, including gathers that land on negative fd (edges wider than fd)."""
+    rng = np.random.default_rng(9)
+    nf, nt, npad = 32, 64, 1
+    d = rng.normal(size=(nf, nt))
+    d -= d.mean()
+    t = np.arange(nt) * 10.0
+    f = 1400 + 0.1 * np.arange(nf)
+    fd = TO.fft_axis(t, "mHz", npad)
+    tau = TO.fft_axis(f, "us", npad)
+    thth = sb.ththmod
+    full = thth.conjugate_spectrum(d, npad, 0.0, half=False)
+    half = thth.conjugate_spectrum(d, npad, 0.0, half=True)
+    for lim in (20.0, 60.0, 110.0):      # 110 > fd range: wraps to negative fd
+        edges = np.linspace(-lim, lim, 64)
+        etas = np.linspace(0.0005, 0.004, 12)
+        a, ia = thth.eta_sweep(full, tau, fd, etas, edges, return_info=True)
+        b, ib = thth.eta_sweep(half, tau, fd, etas, edges, return_info=True)
+        ref = TO.eta_sweep(full.numpy(), tau, fd, etas, edges)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.array_equal(np.isnan(a), np.isnan(ref))
+        ok = ~np.isnan(a)
+        assert np.allclose(a[ok], b[ok], rtol=1e-6)
+        assert (np.abs(a[ok] - ref[ok]) / np.abs(ref[ok])).max() < RTOL
+        m1 = thth.thth_map(full, tau, fd, etas[3], edges) if not np.isnan(a[3]) else None
+        if m1 is not None:
+            m2 = thth.thth_map(half, tau, fd, etas[3], edges)
+            assert maxrel(m2, m1) < 1e-6
 
 
 def test_single_search_end_to_end(sb, golden_dir):
