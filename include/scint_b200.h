@@ -136,6 +136,8 @@ int sb_acf_f32(const float* dyn, int32_t nf, int32_t nt, int32_t subtract_mean,
  * and Dynspec.thetatheta_single (scintools/dynspec.py:1572-1579):
  *   CS = fftshift(fft2(pad(dspec, npad copies, constant pad_value)));
  *   CS[tau_rowmask] = 0
+ * pad_value = NaN pads with the mean of dspec computed on the device
+ * (constant_values=dspec2.mean(), ththmod.py:781) without a host pass.
  * dspec float32 [nf][nt]; cs: float2 [(npad+1)nf][(npad+1)nt]; tau_rowmask:
  * uint8 [(npad+1)nf] (1 = zero that fftshifted row) or NULL.  half_plane=1
  * writes only the fd >= 0 half, [(npad+1)nf][cs_pitch] with cs_pitch >=

@@ -113,6 +113,7 @@ struct DynRowLoad {
         float m1, m2 = 0.f;
         if (mode == 0) { m1 = (float)stats[4]; m2 = (float)stats[5]; }
         else if (mode == 1) { m1 = (float)stats[6]; }
+        else if (mode == 3) { m1 = (float)stats[4]; }     // minus the device-side mean
         else { m1 = sub; }
         const int f = (int)row, t = 2 * n;
         return make_float2(get(f, t, m1, m2), get(f, t + 1, m1, m2));
@@ -165,9 +166,11 @@ struct CsStore {
     float dc;
     int half;       // 1: write only the fd >= 0 half, [NF][pitch], column = c
     long pitch;
+    const double* dc_stats;   // non-null: dc = stats[4] * NF * NT (device-side mean)
     __device__ __forceinline__ void operator()(int y, int k, int c, float2 v) const {
         const int kf = y + R1 * k;
-        if (kf == 0 && c == 0) v.x += dc;
+        if (kf == 0 && c == 0)
+            v.x += dc_stats ? (float)(dc_stats[4] * (double)NF * (double)NT) : dc;
         const int rs = (kf + NF / 2) & (NF - 1);
         if (half) {
             const bool mh = rowmask && rowmask[rs];
@@ -310,6 +313,8 @@ struct AcfRowStore {
 };
 
 // ------------------------------------------------------------ host drivers
+int stats_pass(const float* dyn, int nf, int nt, const float* wt, const float* wf,
+               double swt, double swf, double* stats, cudaStream_t st);
 static long half_pitch(long NT) { return ((NT / 2 + 1) + 15) & ~15L; }
 
 static int next_pow2(long v) {
@@ -403,14 +408,26 @@ int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
     float2* H = (float2*)workspace(3, (size_t)nf * pitch * sizeof(float2));
     float2* A = (float2*)workspace(4, (size_t)NF * pitch * sizeof(float2));
     if (!H || !A) return SB_ERR_NOMEM;
-    DynRowLoad ld{dyn, nf, nt, nullptr, nullptr, nullptr, 2, 0, pad_value};
+    // pad_value = NaN: pad with the mean of the chunk (ththmod.py:781), which
+    // is then computed on the device instead of a host pass over the data
+    const bool dev_mean = pad_value != pad_value;
+    double* stats = nullptr;
+    if (dev_mean) {
+        stats = (double*)workspace(0, 64 * sizeof(double));
+        if (!stats) return SB_ERR_NOMEM;
+        int rc0 = stats_pass(dyn, nf, nt, nullptr, nullptr, 0, 0, stats, st);
+        if (rc0) return rc0;
+        pad_value = 0.f;
+    }
+    DynRowLoad ld{dyn, nf, nt, nullptr, nullptr, stats, dev_mean ? 3 : 2, 0, pad_value};
     prof_begin(PROF_CS_ROWS, st);
     int rc = rows_r2c(ld, H, pitch, NT, nf, st);
     prof_end(PROF_CS_ROWS, st);
     if (rc) return rc;
     int R1, R2;
     split_len(NF, &R1, &R2);
-    CsStore cs{CS, NF, NT, R1, rowmask, pad_value * (float)NF * (float)NT, half, cs_pitch};
+    CsStore cs{CS, NF, NT, R1, rowmask, pad_value * (float)NF * (float)NT, half, cs_pitch,
+               dev_mean ? stats : nullptr};
     return cols_forward(H, A, pitch, NF, nf, NT / 2 + 1, cs, st, PROF_CS_COLA, PROF_CS_COLB);
 }
 

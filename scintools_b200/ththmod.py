@@ -270,7 +270,7 @@ def conjugate_spectrum(dspec2, npad, pad_value=None, tau=None, tau_mask=0.0,
     d = np.asarray(dspec2)
     nf, nt = d.shape
     if pad_value is None:
-        pad_value = float(d.mean())
+        pad_value = float("nan")     # = dspec2.mean(), evaluated on the device
     dd = D.upload_f32(d)
     NF, NT = (npad + 1) * nf, (npad + 1) * nt
     pitch = NT // 2 + 16 if half else NT

@@ -209,7 +209,8 @@ def test_half_plane_sweep_matches_full(sb):
         assert np.array_equal(np.isnan(a), np.isnan(ref))
         ok = ~np.isnan(a)
         assert np.allclose(a[ok], b[ok], rtol=1e-6)
-        assert (np.abs(a[ok] - ref[ok]) / np.abs(ref[ok])).max() < RTOL
+        if ok.any():
+            assert (np.abs(a[ok] - ref[ok]) / np.abs(ref[ok])).max() < RTOL
         m1 = thth.thth_map(full, tau, fd, etas[3], edges) if not np.isnan(a[3]) else None
         if m1 is not None:
             m2 = thth.thth_map(half, tau, fd, etas[3], edges)
