@@ -132,6 +132,13 @@ int sb_sspec_f32(const float* dyn, int32_t nf, int32_t nt, const float* win_t,
 int sb_acf_f32(const float* dyn, int32_t nf, int32_t nt, int32_t subtract_mean,
                int32_t normalise, float* acf, void* stream);
 
+/* Replaces Dynspec.calc_acf(method='sspec') (scintools/dynspec.py:3798-3807):
+ * real(fftshift(fft2(linear un-halved secondary spectrum))) [/ max], with the
+ * window arguments of sb_sspec_f32.  acf: float32 [nrfft][ncfft]. */
+int sb_acf_sspec_f32(const float* dyn, int32_t nf, int32_t nt, const float* win_t,
+                     const float* win_f, double sum_win_t, double sum_win_f,
+                     int32_t normalise, float* acf, void* stream);
+
 /* Replaces the CS stage of ththmod.single_search (scintools/ththmod.py:777-787)
  * and Dynspec.thetatheta_single (scintools/dynspec.py:1572-1579):
  *   CS = fftshift(fft2(pad(dspec, npad copies, constant pad_value)));
@@ -143,7 +150,9 @@ int sb_acf_f32(const float* dyn, int32_t nf, int32_t nt, int32_t subtract_mean,
  * writes only the fd >= 0 half, [(npad+1)nf][cs_pitch] with cs_pitch >=
  * (npad+1)nt/2 + 1 (see sb_thth_geom.cs_half): half the HBM traffic, and all
  * the theta-theta sweep needs.  half_plane=0: full array, cs_pitch ignored.
- * Padded sizes must be powers of two in this version. */
+ * Power-of-two padded sizes take the direct radix-16 path (rows <= 65536, cols
+ * <= 32768); any other size runs a chirp-z (Bluestein) transform on both axes
+ * (rows <= 32768, cols <= 8192, half_plane must be 0). */
 int sb_cs_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad,
               float pad_value, const uint8_t* tau_rowmask, int32_t half_plane,
               int64_t cs_pitch, void* cs, void* stream);

@@ -97,12 +97,15 @@ int thth_map(const ThthGeom& g, double eta, int hermitian, float2* d_out,
 
 int sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
           double swt, double swf, int prewhite, int halve, int db,
-          const float* pd1, const float* pd2, float* sec, cudaStream_t st);
+          const float* pd1, const float* pd2, float* sec, cudaStream_t st,
+          int noshift = 0);
 int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
                   const unsigned char* rowmask, int half, long pitch, float2* CS,
                   cudaStream_t st);
 int acf(const float* dyn, int nf, int nt, int subtract_mean, int normalise,
         float* out, cudaStream_t st);
+int acf_sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
+              double swt, double swf, int normalise, float* out, cudaStream_t st);
 void twiddle_release();
 struct SimParams {
     int nx, ny;
@@ -239,6 +242,15 @@ int sb_acf_f32(const float* dyn, int32_t nf, int32_t nt, int32_t subtract_mean,
                int32_t normalise, float* acf, void* stream) {
     SB_ARG(dyn && acf && nf >= 1 && nt >= 1);
     return sb::acf(dyn, nf, nt, subtract_mean, normalise, acf, (cudaStream_t)stream);
+}
+
+int sb_acf_sspec_f32(const float* dyn, int32_t nf, int32_t nt, const float* win_t,
+                     const float* win_f, double sum_win_t, double sum_win_f,
+                     int32_t normalise, float* acf, void* stream) {
+    SB_ARG(dyn && acf && nf >= 2 && nt >= 2);
+    SB_ARG((win_t == nullptr) == (win_f == nullptr));
+    return sb::acf_sspec(dyn, nf, nt, win_t, win_f, sum_win_t, sum_win_f, normalise,
+                         acf, (cudaStream_t)stream);
 }
 
 int sb_cs_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad,

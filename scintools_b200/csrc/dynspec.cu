@@ -196,9 +196,13 @@ struct SspecStore {
     int halve, db;
     const float* pd1;   // [NT] sin^2 over the shifted fd axis, or null
     const float* pd2;   // [NF/2] sin^2 over td
+    int noshift;        // 1: natural (un-fftshifted) order, full frame only
     __device__ __forceinline__ void put(int kf, int cs, float p) const {
         int row;
-        if (halve) {
+        if (noshift) {
+            row = kf;
+            cs = (cs + NT / 2) & (NT - 1);     // undo the column shift
+        } else if (halve) {
             if (kf >= NF / 2) return;
             row = kf;
         } else {
@@ -367,7 +371,8 @@ int stats_pass(const float* dyn, int nf, int nt, const float* wt, const float* w
 // Dynspec.calc_sspec (dynspec.py:3664-3721)
 int sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
           double swt, double swf, int prewhite, int halve, int db,
-          const float* pd1, const float* pd2, float* sec, cudaStream_t st) {
+          const float* pd1, const float* pd2, float* sec, cudaStream_t st,
+          int noshift = 0) {
     ProfScope prof(PROF_SSPEC, st);
     const int NF = 2 * next_pow2(nf), NT = 2 * next_pow2(nt);  // 2^(ceil(log2 n)+1)
     if (NT / 2 < 8 || NT / 2 > 16384 || NF > 65536 || NF < 4) {
@@ -387,9 +392,14 @@ int sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
     if (rc) return rc;
     int R1, R2;
     split_len(NF, &R1, &R2);
-    SspecStore ss{sec, NF, NT, R1, halve, db, prewhite ? pd1 : nullptr, pd2};
+    SspecStore ss{sec, NF, NT, R1, halve, db, prewhite ? pd1 : nullptr, pd2, noshift};
     return cols_forward(H, A, pitch, NF, live, NT / 2 + 1, ss, st);
 }
+
+static int conj_spectrum_bluestein(const float* dyn, int nf, int nt, int NF, int NT,
+                                   float pad_value, const double* stats,
+                                   const unsigned char* rowmask, float2* CS,
+                                   cudaStream_t st);
 
 // conjugate spectrum of a zero(/constant)-padded chunk
 // (ththmod.py:777-787, dynspec.py:1572-1579)
@@ -397,10 +407,27 @@ int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
                   const unsigned char* rowmask, int half, long cs_pitch, float2* CS,
                   cudaStream_t st) {
     const long NFl = (long)(npad + 1) * nf, NTl = (long)(npad + 1) * nt;
-    if (!is_pow2(NFl) || !is_pow2(NTl) || NTl / 2 < 8 || NTl / 2 > 16384 ||
-        NFl > 65536 || NFl < 4) {
-        set_error("conjugate spectrum: padded size %ldx%ld must be powers of two "
-                  "(rows 4..65536, cols 16..32768)", NFl, NTl);
+    if (!is_pow2(NFl) || !is_pow2(NTl) || NTl / 2 < 8 || NFl < 4) {
+        // arbitrary lengths: chirp-z on both axes, full plane only
+        if (half) {
+            set_error("conjugate spectrum: half-plane output needs power-of-two "
+                      "padded sizes (got %ldx%ld)", NFl, NTl);
+            return SB_ERR_ARG;
+        }
+        double* bstats = nullptr;
+        if (pad_value != pad_value) {
+            bstats = (double*)workspace(0, 64 * sizeof(double));
+            if (!bstats) return SB_ERR_NOMEM;
+            int rc0 = stats_pass(dyn, nf, nt, nullptr, nullptr, 0, 0, bstats, st);
+            if (rc0) return rc0;
+            pad_value = 0.f;
+        }
+        return conj_spectrum_bluestein(dyn, nf, nt, (int)NFl, (int)NTl, pad_value,
+                                       bstats, rowmask, CS, st);
+    }
+    if (NTl / 2 > 16384 || NFl > 65536) {
+        set_error("conjugate spectrum: padded size %ldx%ld too large "
+                  "(rows <= 65536, cols <= 32768)", NFl, NTl);
         return SB_ERR_UNSUPPORTED;
     }
     const int NF = (int)NFl, NT = (int)NTl;
@@ -429,6 +456,228 @@ int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
     CsStore cs{CS, NF, NT, R1, rowmask, pad_value * (float)NF * (float)NT, half, cs_pitch,
                dev_mean ? stats : nullptr};
     return cols_forward(H, A, pitch, NF, nf, NT / 2 + 1, cs, st, PROF_CS_COLA, PROF_CS_COLB);
+}
+
+
+// ------------------------------------------------------------------------
+// Conjugate spectrum for padded sizes that are NOT powers of two (e.g. the
+// reference tutorial's 64 x 150 chunk -> 256 x 600): Bluestein / chirp-z on
+// both axes on top of the power-of-two engine.
+//   X[k] = w[k] * sum_n (x[n] w[n]) conj(w)[k - n],  w[n] = exp(-i pi n^2 / N)
+// = w[k] * IFFT_M( FFT_M(x w) * FFT_M(b) )[k],  M = 2^p >= 2N - 1.
+// Full plane output (no Hermitian shortcut), generic fftshift (odd N too).
+// ------------------------------------------------------------------------
+__global__ void chirp_fill_kernel(float2* w, float2* b, int N, int M) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= M) return;
+    // b[m] = conj(w[|m|]) for -N < m < N (wrapped mod M), else 0
+    const int m = n < N ? n : (M - n < N ? M - n : -1);
+    float2 bv = make_float2(0.f, 0.f);
+    if (m >= 0) {
+        const long long q = ((long long)m * m) % (2LL * N);
+        double s, c;
+        sincospi((double)q / (double)N, &s, &c);
+        bv = make_float2((float)c, (float)s);            // conj(w) = exp(+i pi m^2/N)
+        if (n < N) w[n] = make_float2((float)c, (float)-s);
+    }
+    b[n] = bv;
+}
+
+struct VecLoad {     // single row / column loader
+    const float2* v;
+    __device__ __forceinline__ float2 operator()(long, int n) const { return v[n]; }
+};
+struct VecStore {
+    float2* v;
+    __device__ __forceinline__ void operator()(long, int k, float2 x) const { v[k] = x; }
+};
+struct ColVecLoad {  // y = r2, i = r1 over a [M][1] array
+    const float2* v;
+    int R2;
+    __device__ __forceinline__ float2 operator()(int y, int i, int) const { return v[i * R2 + y]; }
+};
+struct ColVecStore {
+    float2* v;
+    int R1;
+    __device__ __forceinline__ void operator()(int y, int k, int, float2 x) const { v[y + R1 * k] = x; }
+};
+
+struct ChirpRowLoad {    // a[n] = (x[f][n] - sub) * w[n], zero beyond the live samples
+    const float* dyn;
+    int nt;
+    const float2* w;
+    const double* stats;  // non-null: subtract stats[4] (device mean)
+    float sub;
+    __device__ __forceinline__ float2 operator()(long row, int n) const {
+        if (n >= nt) return make_float2(0.f, 0.f);
+        const float x = dyn[(size_t)row * nt + n] - (stats ? (float)stats[4] : sub);
+        const float2 c = w[n];
+        return make_float2(x * c.x, x * c.y);
+    }
+};
+struct MulVecRowStore {  // out[row][k] = v * B[k]
+    float2* out;
+    long pitch;
+    const float2* B;
+    __device__ __forceinline__ void operator()(long row, int k, float2 v) const {
+        out[row * pitch + k] = cmul(v, B[k]);
+    }
+};
+struct PitchRowLoad {
+    const float2* in;
+    long pitch;
+    __device__ __forceinline__ float2 operator()(long row, int n) const { return in[row * pitch + n]; }
+};
+struct ChirpOutRowStore {  // Y[row][k] = v * w[k] / M, k < N
+    float2* out;
+    long pitch;
+    const float2* w;
+    int N;
+    float scale;
+    __device__ __forceinline__ void operator()(long row, int k, float2 v) const {
+        if (k < N) {
+            const float2 r = cmul(v, w[k]);
+            out[row * pitch + k] = make_float2(r.x * scale, r.y * scale);
+        }
+    }
+};
+struct ChirpColALoad {   // y = r2, i = r1 : Y[row][c] * wF[row], zero beyond live rows
+    const float2* Y;
+    long pitch;
+    int R2, live;
+    const float2* w;
+    __device__ __forceinline__ float2 operator()(int y, int i, int c) const {
+        const int row = i * R2 + y;
+        return row < live ? cmul(Y[(size_t)row * pitch + c], w[row]) : make_float2(0.f, 0.f);
+    }
+};
+struct MulVecColStore {  // out[k][c] = v * B[k], k = k1 + R1 k2
+    float2* out;
+    long pitch;
+    int R1;
+    const float2* B;
+    __device__ __forceinline__ void operator()(int y, int k, int c, float2 v) const {
+        const int kk = y + R1 * k;
+        out[(size_t)kk * pitch + c] = cmul(v, B[kk]);
+    }
+};
+struct PlainColALoad {
+    const float2* in;
+    long pitch;
+    int R2;
+    __device__ __forceinline__ float2 operator()(int y, int i, int c) const {
+        return in[(size_t)(i * R2 + y) * pitch + c];
+    }
+};
+struct ChirpCsStore {    // CS[(k + N/2) % N][(c + NT/2) % NT] = v * wF[k] / M (+dc), masks
+    float2* CS;
+    int NF, NT, R1;
+    const float2* w;
+    float scale;
+    const unsigned char* rowmask;
+    float dc;
+    const double* dc_stats;
+    __device__ __forceinline__ void operator()(int y, int k, int c, float2 v) const {
+        const int kf = y + R1 * k;
+        if (kf >= NF) return;
+        float2 r = cmul(v, w[kf]);
+        r.x *= scale;
+        r.y *= scale;
+        if (kf == 0 && c == 0)
+            r.x += dc_stats ? (float)(dc_stats[4] * (double)NF * (double)NT) : dc;
+        const int rs = (kf + NF / 2) % NF, cs = (c + NT / 2) % NT;
+        if (rowmask && rowmask[rs]) r = make_float2(0.f, 0.f);
+        CS[(size_t)rs * NT + cs] = r;
+    }
+};
+
+template <int DIR, class LoadA, class StoreB>
+static int cols_generic_f(LoadA la, float2* tmp, long pitch, int R, int ncols,
+                          StoreB sb, cudaStream_t st) {
+    int R1, R2;
+    split_len(R, &R1, &R2);
+    const float2* wR = twiddle_table<float>(R, DIR, st);
+    if (!wR) return SB_ERR_NOMEM;
+    ColAStore sa{tmp, pitch, R2, R, wR};
+    int rc = SB_OK;
+    SB_TILE_DISPATCH(R1, rc = (launch_tile_fft<float, LL, 32, DIR>(la, sa, ncols, R2, st)));
+    if (rc) return rc;
+    ColBLoad lb{tmp, pitch, R2};
+    SB_TILE_DISPATCH(R2, rc = (launch_tile_fft<float, LL, 32, DIR>(lb, sb, ncols, R1, st)));
+    return rc;
+}
+
+// chirp w[N] and the transformed kernel B = FFT_M(b)
+static int bluestein_tables(int N, int M, float2* w, float2* B, float2* scratch,
+                            cudaStream_t st) {
+    chirp_fill_kernel<<<(M + 255) / 256, 256, 0, st>>>(w, B, N, M);
+    SB_LAUNCH_CHECK();
+    if (M <= 16384) {
+        SB_CUDA(cudaMemcpyAsync(scratch, B, (size_t)M * sizeof(float2),
+                                cudaMemcpyDeviceToDevice, st));
+        VecLoad ld{scratch};
+        VecStore vs{B};
+        int rc = SB_OK;
+        SB_ROW_DISPATCH(M, rc = (launch_row_c2c<float, N1, N2, -1>(ld, vs, 1, st)));
+        return rc;
+    }
+    int R1, R2;
+    split_len(M, &R1, &R2);
+    SB_CUDA(cudaMemcpyAsync(scratch, B, (size_t)M * sizeof(float2),
+                            cudaMemcpyDeviceToDevice, st));
+    ColVecLoad la{scratch, R2};
+    ColVecStore sb_{B, R1};
+    return cols_generic_f<-1>(la, scratch + M, 1, M, 1, sb_, st);
+}
+
+static int conj_spectrum_bluestein(const float* dyn, int nf, int nt, int NF, int NT,
+                                   float pad_value, const double* stats,
+                                   const unsigned char* rowmask, float2* CS,
+                                   cudaStream_t st) {
+    const int MT = next_pow2(2L * NT - 1), MF = next_pow2(2L * NF - 1);
+    if (MT < 8 || MT > 16384 || MF < 4 || MF > 65536) {
+        set_error("conjugate spectrum (Bluestein): padded size %dx%d too large "
+                  "(rows <= 32768, cols <= 8192 for non power-of-two sizes)", NF, NT);
+        return SB_ERR_UNSUPPORTED;
+    }
+    const long pt = ((long)NT + 15) & ~15L;
+    float2* tabs = (float2*)workspace(6, (size_t)(NT + 3L * MT + NF + 3L * MF + 64) * sizeof(float2));
+    float2* R1buf = (float2*)workspace(3, (size_t)nf * MT * sizeof(float2));
+    float2* Ybuf = (float2*)workspace(4, (size_t)nf * pt * sizeof(float2));
+    float2* C0 = (float2*)workspace(5, (size_t)MF * pt * sizeof(float2));
+    float2* C1 = (float2*)workspace(7, (size_t)MF * pt * sizeof(float2));
+    if (!tabs || !R1buf || !Ybuf || !C0 || !C1) return SB_ERR_NOMEM;
+    float2* wT = tabs;
+    float2* BT = wT + NT;
+    float2* wF = BT + MT;
+    float2* BF = wF + NF;
+    float2* scratch = BF + MF;      // 2*max(MT, MF)
+    int rc = bluestein_tables(NT, MT, wT, BT, scratch, st);
+    if (rc) return rc;
+    rc = bluestein_tables(NF, MF, wF, BF, scratch, st);
+    if (rc) return rc;
+    // rows: chirp, FFT, multiply, inverse FFT, chirp
+    {
+        ChirpRowLoad ld{dyn, nt, wT, stats, pad_value};
+        MulVecRowStore ms{R1buf, MT, BT};
+        SB_ROW_DISPATCH(MT, rc = (launch_row_c2c<float, N1, N2, -1>(ld, ms, nf, st)));
+        if (rc) return rc;
+        PitchRowLoad pl{R1buf, MT};
+        ChirpOutRowStore os{Ybuf, pt, wT, NT, 1.0f / (float)MT};
+        SB_ROW_DISPATCH(MT, rc = (launch_row_c2c<float, N1, N2, +1>(pl, os, nf, st)));
+        if (rc) return rc;
+    }
+    // columns
+    int R1, R2;
+    split_len(MF, &R1, &R2);
+    ChirpColALoad la{Ybuf, pt, R2, nf, wF};
+    MulVecColStore mc{C1, pt, R1, BF};
+    rc = cols_generic_f<-1>(la, C0, pt, MF, NT, mc, st);
+    if (rc) return rc;
+    PlainColALoad pa{C1, pt, R2};
+    ChirpCsStore cs{CS, NF, NT, R1, wF, 1.0f / (float)MF, rowmask,
+                    pad_value * (float)NF * (float)NT, stats};
+    return cols_generic_f<+1>(pa, C0, pt, MF, NT, cs, st);
 }
 
 // Dynspec.calc_acf(method='direct') (dynspec.py:3780-3797)
@@ -491,6 +740,52 @@ int acf(const float* dyn, int nf, int nt, int subtract_mean, int normalise,
     const int N = PT / 2;
     SB_ROW_DISPATCH(N, return (launch_row_c2r<float, N1, N2>(rl, rs, 2L * nf, st)));
     return SB_OK;
+}
+
+// real part of FFT2 of a real array with fftshift, scaled by 1/sum (ACF through
+// the secondary spectrum, dynspec.py:3798-3807)
+struct RealShiftStore {
+    float* out;
+    int NF, NT, R1;
+    const double* stats;   // [0] = sum of the input (the zero-frequency bin)
+    int normalise;
+    __device__ __forceinline__ void operator()(int y, int k, int c, float2 v) const {
+        const int kf = y + R1 * k;
+        const float val = normalise ? (float)((double)v.x / stats[0]) : v.x;
+        out[(size_t)((kf + NF / 2) & (NF - 1)) * NT + ((c + NT / 2) & (NT - 1))] = val;
+        if (c != 0 && c != NT / 2)
+            out[(size_t)(((NF - kf) + NF / 2) & (NF - 1)) * NT + (((NT - c) + NT / 2) & (NT - 1))] = val;
+    }
+};
+
+// Dynspec.calc_acf(method='sspec'): FFT2 of the un-halved, un-shifted linear
+// secondary spectrum (dynspec.py:3798-3807)
+int acf_sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
+              double swt, double swf, int normalise, float* out, cudaStream_t st) {
+    const int NF = 2 * next_pow2(nf), NT = 2 * next_pow2(nt);
+    float* P = (float*)workspace(5, (size_t)NF * NT * sizeof(float));
+    if (!P) return SB_ERR_NOMEM;
+    int rc = sspec(dyn, nf, nt, wt, wf, swt, swf, 0, 0, 0, nullptr, nullptr, P, st, 1);
+    if (rc) return rc;
+    ProfScope prof(PROF_ACF, st);
+    if (NT / 2 < 8 || NT / 2 > 16384) {
+        set_error("calc_acf(sspec): size outside supported FFT sizes");
+        return SB_ERR_UNSUPPORTED;
+    }
+    const long pitch = half_pitch(NT);
+    double* stats = (double*)workspace(0, 64 * sizeof(double));
+    float2* H = (float2*)workspace(3, (size_t)NF * pitch * sizeof(float2));
+    float2* A = (float2*)workspace(4, (size_t)NF * pitch * sizeof(float2));
+    if (!stats || !H || !A) return SB_ERR_NOMEM;
+    rc = stats_pass(P, NF, NT, nullptr, nullptr, 0, 0, stats, st);
+    if (rc) return rc;
+    DynRowLoad ld{P, NF, NT, nullptr, nullptr, nullptr, 2, 0, 0.f};
+    rc = rows_r2c(ld, H, pitch, NT, NF, st);
+    if (rc) return rc;
+    int R1, R2;
+    split_len(NF, &R1, &R2);
+    RealShiftStore rs{out, NF, NT, R1, stats, normalise};
+    return cols_forward(H, A, pitch, NF, NF, NT / 2 + 1, rs, st);
 }
 
 }  // namespace sb

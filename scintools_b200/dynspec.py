@@ -218,10 +218,21 @@ class Dynspec:
                 d.data_ptr(), nf, nt, 1 if input_dyn is None else 0,
                 1 if normalise else 0, out.data_ptr(), D.stream_ptr()))
             arr = D.download(out, dtype)
-        elif method == 'sspec':
-            raise NotImplementedError(
-                "calc_acf(method='sspec') is not on the B200 path yet; "
-                "method='direct' gives the same function")
+        elif method == 'sspec':     # FFT of the secondary spectrum, :3798-3807
+            src = np.asarray(self.dyn)
+            nf, nt = src.shape
+            nrfft = int(2 ** (np.ceil(np.log2(nf)) + 1))
+            ncfft = int(2 ** (np.ceil(np.log2(nt)) + 1))
+            cw, sw = get_window(nt, nf, window='hanning', frac=window_frac)
+            d = D.upload_f32(src)
+            wt = D.upload(cw.astype(np.float32))
+            wf = D.upload(sw.astype(np.float32))
+            out = D.empty((nrfft, ncfft), torch.float32)
+            _lib.check(_lib.lib.sb_acf_sspec_f32(
+                d.data_ptr(), nf, nt, wt.data_ptr(), wf.data_ptr(),
+                float(cw.sum()), float(sw.sum()), 1 if normalise else 0,
+                out.data_ptr(), D.stream_ptr()))
+            arr = D.download(out, dtype)
         else:
             print('Method not understood. Choose "direct" or "sspec"')
             return

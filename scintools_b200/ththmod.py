@@ -273,6 +273,8 @@ def conjugate_spectrum(dspec2, npad, pad_value=None, tau=None, tau_mask=0.0,
         pad_value = float("nan")     # = dspec2.mean(), evaluated on the device
     dd = D.upload_f32(d)
     NF, NT = (npad + 1) * nf, (npad + 1) * nt
+    if (NF & (NF - 1)) or (NT & (NT - 1)) or NT < 16 or NF < 4:
+        half = False        # chirp-z path for arbitrary lengths: full plane
     pitch = NT // 2 + 16 if half else NT
     cs = D.empty((NF, pitch, 2), torch.float32)
     mask = None

@@ -149,6 +149,14 @@ def test_sspec_acf_golden(sb, golden_dir, name):
     assert maxrel(raw, DO.calc_acf(g["dyn"], normalise=False)) < RTOL
 
 
+def test_acf_sspec_method(sb, golden_dir):
+    g = _dyn(golden_dir, "sspec_acf_48x80.npz")
+    ds = _ds(sb, g["dyn"], float(g["dt"]), float(g["df"]))
+    ds.calc_acf(method="sspec")
+    assert ds.acf.shape == g["acf_sspec"].shape
+    assert maxrel(ds.acf, g["acf_sspec"]) < RTOL
+
+
 def test_sspec_variants(sb, golden_dir):
     g = _dyn(golden_dir, "sspec_acf_48x80.npz")
     ds = _ds(sb, g["dyn"], float(g["dt"]), float(g["df"]))
@@ -183,6 +191,39 @@ def test_conjugate_spectrum(sb, shape, npad):
             assert maxrel(got, ref) < RTOL
             if mask:
                 assert np.array_equal(got == 0, ref == 0)
+
+
+@pytest.mark.parametrize("shape,npad", [((64, 150), 3), ((10, 7), 1), ((33, 100), 2),
+                                        ((128, 75), 3), ((50, 64), 0)])
+def test_conjugate_spectrum_any_size(sb, shape, npad):
+    """Non power-of-two padded sizes (chirp-z path), incl. odd lengths."""
+    rng = np.random.default_rng(6)
+    d = rng.normal(size=shape)
+    d -= d.mean()
+    f = 1400 + 0.05 * np.arange(shape[0])
+    tau = TO.fft_axis(f, "us", npad)
+    for pad_value, mask in ((0.0, 0.0), (None, 0.0), (0.21, 1.5)):
+        ref = TO.conjugate_spectrum(d, npad, pad_value, tau, mask)
+        got = sb.ththmod.conjugate_spectrum(d, npad, pad_value, tau, mask).numpy()
+        assert got.shape == ref.shape
+        assert maxrel(got, ref) < RTOL
+        if mask:
+            assert np.array_equal(got == 0, ref == 0)
+
+
+def test_single_search_tutorial_chunk(sb, golden_dir):
+    """The reference's own tutorial chunk (64 x 150, npad=3 -> 256 x 600 CS)
+    end to end on the GPU against the reference's single_search output."""
+    g = np.load(os.path.join(golden_dir, "thth_sample_64x150.npz"))
+    d0 = g["dspec2"] - g["dspec2"].mean()
+    res = sb.ththmod.single_search([d0, g["freq"], g["time"], g["etas"], g["edges"],
+                                    None, False, 0.1, int(g["npad"]), True, 0.0, False])
+    assert (np.abs(res[4] - g["ss_eigs"]) / g["ss_eigs"]).max() < RTOL
+    assert res[0] == pytest.approx(float(g["ss_eta_fit"]), rel=1e-4)
+    assert abs(res[0] - 44.0) < 2.0
+    inc = sb.ththmod.single_search([d0, g["freq"], g["time"], g["inc_etas"], g["edges"],
+                                    None, False, 0.1, int(g["npad"]), False, 0.5, False])
+    assert (np.abs(inc[4] - g["inc_eigs"]) / g["inc_eigs"]).max() < RTOL
 
 
 def test_half_plane_sweep_matches_full(sb):
