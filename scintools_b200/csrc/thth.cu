@@ -80,10 +80,13 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0,
                   const int* __restrict__ nred, float2* __restrict__ M) {
     __shared__ int ia[32], ib[32];
     __shared__ double ta_[32], tb_[32];
-    const int e = blockIdx.y;
+    // eta is the FAST grid index: CTAs resident at the same time work on the
+    // same 32x32 tile for ~900 neighbouring curvatures, whose gathers fall on
+    // the same / adjacent CS rows for small |theta1^2 - theta2^2| (L2 reuse)
+    const int e = blockIdx.x;
     const int n = nred[eta0 + e];
     // pair index -> (ta <= tb)
-    int p = blockIdx.x, ta = 0;
+    int p = blockIdx.y, ta = 0;
     const int T = ld / 32;
     while (p >= T - ta) { p -= T - ta; ++ta; }
     const int tb = ta + p;
@@ -609,7 +612,7 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int e0 = 0; e0 < neta; e0 += batch) {
         int nb = neta - e0 < batch ? neta - e0 : batch;
-        dim3 grid(npairs, nb), block(32, 8);
+        dim3 grid(nb, npairs), block(32, 8);
         prof_begin(PROF_THTH_BUILD, st);
         thth_build_kernel<<<grid, block, 0, st>>>(g, d_etas, e0, ld, d_idx, d_nred, d_M);
         prof_end(PROF_THTH_BUILD, st);
