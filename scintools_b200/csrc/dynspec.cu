@@ -353,7 +353,7 @@ static int cols_forward(const float2* H, float2* A, long pitch, int NF, int live
     if (rc) return rc;
     ColBLoad lb{A, pitch, R2};
     if (profB >= 0) prof_begin(profB, st);
-    SB_TILE_DISPATCH(R2, rc = (launch_tile_fft<float, LL, 32, -1>(lb, stb, ncols, R1, st)));
+    SB_TILE_DISPATCH(R2, rc = (launch_tile_fft<float, LL, 64, -1>(lb, stb, ncols, R1, st)));
     if (profB >= 0) prof_end(profB, st);
     return rc;
 }

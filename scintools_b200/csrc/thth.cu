@@ -74,8 +74,9 @@ __global__ void thth_indexerr_kernel(ThthGeom g, const double* __restrict__ etas
 // block = 32 x 8.  M[e] is [ld][ld] float2; inside the active 32x32 tiles
 // columns >= nred and the diagonal are zero, the lower triangle is not touched.
 // --------------------------------------------------------------------------
+#define SB_BUILD_EB 4
 __global__ void __launch_bounds__(256)
-thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0,
+thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nbatch,
                   int ld, const int* __restrict__ idx,
                   const int* __restrict__ nred, float2* __restrict__ M) {
     __shared__ int ia[32], ib[32];
@@ -83,17 +84,20 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0,
     // eta is the FAST grid index: CTAs resident at the same time work on the
     // same 32x32 tile for ~900 neighbouring curvatures, whose gathers fall on
     // the same / adjacent CS rows for small |theta1^2 - theta2^2| (L2 reuse)
-    const int e = blockIdx.x;
-    const int n = nred[eta0 + e];
     // pair index -> (ta <= tb)
     int p = blockIdx.y, ta = 0;
     const int T = ld / 32;
     while (p >= T - ta) { p -= T - ta; ++ta; }
     const int tb = ta + p;
-    if (tb * 32 >= n) return;  // never read by the eigen kernel
+    const int tx = threadIdx.x, ty = threadIdx.y;
+  // EB consecutive curvatures per CTA, back to back: their gathers hit the
+  // same or neighbouring CS rows
+  for (int e = blockIdx.x * SB_BUILD_EB; e < min(nbatch, (int)(blockIdx.x + 1) * SB_BUILD_EB); ++e) {
+    const int n = nred[eta0 + e];
+    if (tb * 32 >= n) continue;  // never read by the eigen kernel
     const double eta = etas[eta0 + e];
     const int* id = idx + (size_t)(eta0 + e) * ld;
-    const int tx = threadIdx.x, ty = threadIdx.y;
+    __syncthreads();
     if (ty == 0) {
         int a = ta * 32 + tx;
         ia[tx] = a < n ? id[a] : -1;
@@ -119,6 +123,7 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0,
         }
         Me[(size_t)(ta * 32 + la) * ld + tb * 32 + lb] = v;
     }
+  }
 }
 
 // --------------------------------------------------------------------------
@@ -612,9 +617,9 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int e0 = 0; e0 < neta; e0 += batch) {
         int nb = neta - e0 < batch ? neta - e0 : batch;
-        dim3 grid(nb, npairs), block(32, 8);
+        dim3 grid((nb + SB_BUILD_EB - 1) / SB_BUILD_EB, npairs), block(32, 8);
         prof_begin(PROF_THTH_BUILD, st);
-        thth_build_kernel<<<grid, block, 0, st>>>(g, d_etas, e0, ld, d_idx, d_nred, d_M);
+        thth_build_kernel<<<grid, block, 0, st>>>(g, d_etas, e0, nb, ld, d_idx, d_nred, d_M);
         prof_end(PROF_THTH_BUILD, st);
         SB_LAUNCH_CHECK();
         prof_begin(PROF_THTH_EIG, st);
