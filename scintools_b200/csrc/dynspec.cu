@@ -368,6 +368,121 @@ int stats_pass(const float* dyn, int nf, int nt, const float* wt, const float* w
     return SB_OK;
 }
 
+
+// ------------------------------------------------------------------------
+// calc_sspec(prewhite=True) in float64.  Post-darkening divides by
+// sin^2*sin^2 (~1e-8 at the lowest bins), which amplifies any rounding made
+// AFTER the first difference; an fp32 transform loses ~1e-4 there.  The
+// prewhite variant therefore differences, transforms and post-darkens in
+// double (dynspec.py:3680-3717); only the dB result is narrowed to float.
+// ------------------------------------------------------------------------
+struct DynRowLoadD {
+    const float* dyn;
+    int nf, nt;
+    const float* wt;
+    const float* wf;
+    const double* stats;   // [4]=mu1 [5]=mu2
+    __device__ __forceinline__ double val(int f, int t) const {
+        double v = (double)dyn[(size_t)f * nt + t] - stats[4];
+        if (wt) v *= (double)wt[t] * (double)wf[f];
+        return v - stats[5];
+    }
+    __device__ __forceinline__ double get(int f, int t) const {
+        if (t >= nt - 1) return 0.0;
+        return val(f + 1, t + 1) - val(f + 1, t) - val(f, t + 1) + val(f, t);
+    }
+    __device__ __forceinline__ double2 operator()(long row, int n) const {
+        return make_double2(get((int)row, 2 * n), get((int)row, 2 * n + 1));
+    }
+};
+struct HalfStoreD {
+    double2* H;
+    long pitch;
+    __device__ __forceinline__ void operator()(long row, int k, double2 v) const {
+        H[row * pitch + k] = v;
+    }
+};
+struct ColALoadD {
+    const double2* H;
+    long pitch;
+    int R2, live;
+    __device__ __forceinline__ double2 operator()(int y, int i, int c) const {
+        const int row = i * R2 + y;
+        return row < live ? H[(size_t)row * pitch + c] : make_double2(0.0, 0.0);
+    }
+};
+struct ColAStoreD {
+    double2* A;
+    long pitch;
+    int R2, R;
+    const double2* wR;
+    __device__ __forceinline__ void operator()(int y, int k, int c, double2 v) const {
+        A[(size_t)(k * R2 + y) * pitch + c] = cmul(v, wR[(y * k) & (R - 1)]);
+    }
+};
+struct ColBLoadD {
+    const double2* A;
+    long pitch;
+    int R2;
+    __device__ __forceinline__ double2 operator()(int y, int i, int c) const {
+        return A[(size_t)(y * R2 + i) * pitch + c];
+    }
+};
+struct SspecStoreD {     // halved frame only (prewhite requires halve)
+    float* sec;
+    int NF, NT, R1, db;
+    __device__ __forceinline__ void put(int kf, int cs, double p) const {
+        if (kf >= NF / 2) return;
+        const double pi = 3.14159265358979323846;
+        if (!(cs == NT / 2 || kf == 0)) {
+            const double s1 = sin(pi / NT * (double)(cs - NT / 2));   // fd = cs - NT/2
+            const double s2 = sin(pi / NF * (double)kf);
+            p = p / ((s1 * s1) * (s2 * s2));
+        }
+        sec[(size_t)kf * NT + cs] = db ? (float)(10.0 * log10(p)) : (float)p;
+    }
+    __device__ __forceinline__ void operator()(int y, int k, int c, double2 v) const {
+        const int kf = y + R1 * k;
+        const double p = v.x * v.x + v.y * v.y;
+        put(kf, (c + NT / 2) & (NT - 1), p);
+        if (c != 0 && c != NT / 2)
+            put((NF - kf) & (NF - 1), ((NT - c) + NT / 2) & (NT - 1), p);
+    }
+};
+
+static int sspec_prewhite_f64(const float* dyn, int nf, int nt, const float* wt,
+                              const float* wf, const double* stats, int db, float* sec,
+                              int NF, int NT, cudaStream_t st) {
+    if (NT / 2 > 8192) {
+        set_error("calc_sspec(prewhite=True): float64 path supports nt <= 8192");
+        return SB_ERR_UNSUPPORTED;
+    }
+    const long pitch = half_pitch(NT);
+    const int live = nf - 1;
+    double2* H = (double2*)workspace(3, (size_t)live * pitch * sizeof(double2));
+    double2* A = (double2*)workspace(4, (size_t)NF * pitch * sizeof(double2));
+    if (!H || !A) return SB_ERR_NOMEM;
+    DynRowLoadD ld{dyn, nf, nt, wt, wf, stats};
+    HalfStoreD hs{H, pitch};
+    int rc = SB_OK;
+    const int N = NT / 2;
+    SB_ROW_DISPATCH(N, rc = (launch_row_r2c<double, N1, N2>(ld, hs, live, st)));
+    if (rc) return rc;
+    int R1, R2;
+    split_len(NF, &R1, &R2);
+    const double2* wR = twiddle_table<double>(NF, -1, st);
+    if (!wR) return SB_ERR_NOMEM;
+    ColALoadD la{H, pitch, R2, live};
+    ColAStoreD sa{A, pitch, R2, NF, wR};
+    const int ncols = NT / 2 + 1;
+    SB_TILE_DISPATCH(R1, rc = (launch_tile_fft<double, LL, 16, -1>(la, sa, ncols, R2, st)));
+    if (rc) return rc;
+    ColBLoadD lb{A, pitch, R2};
+    SspecStoreD ss{sec, NF, NT, R1, db};
+    SB_TILE_DISPATCH(R2, rc = (launch_tile_fft<double, LL, 16, -1>(lb, ss, ncols, R1, st)));
+    return rc;
+}
+
 // Dynspec.calc_sspec (dynspec.py:3664-3721)
 int sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
           double swt, double swf, int prewhite, int halve, int db,
@@ -387,6 +502,7 @@ int sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
     if (!stats || !H || !A) return SB_ERR_NOMEM;
     int rc = stats_pass(dyn, nf, nt, wt, wf, swt, swf, stats, st);
     if (rc) return rc;
+    if (prewhite) return sspec_prewhite_f64(dyn, nf, nt, wt, wf, stats, db, sec, NF, NT, st);
     DynRowLoad ld{dyn, nf, nt, wt, wf, stats, 0, prewhite, 0.f};
     rc = rows_r2c(ld, H, pitch, NT, live, st);
     if (rc) return rc;
