@@ -64,6 +64,14 @@ def eta_grid(n_total):
     return np.logspace(np.log10(ETA_TRUE / 2), np.log10(2 * ETA_TRUE), n_total)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
+# `ncu --set full` capture of this same command (profiles/
+# r1_ncu_full_summary_final.csv); bench.py cannot run ncu on itself.
+NCU_TRAFFIC_BYTES = {"thth_eig": 19.33e9 + 0.004e9, "thth_build": 1.37e9 + 1.04e9,
+                     "cs_rows": 0.134e9 + 0.480e9, "cs_colA": 0.539e9 + 2.089e9,
+                     "cs_colB": 2.150e9 + 2.099e9}
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -304,7 +312,9 @@ def b200_arm(args):
     peak, peak_src = peak_hbm()
     ach = alg_bytes / (kern[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "unit": "GB/s", "frac": ach / peak,
+                "traffic": NCU_TRAFFIC_BYTES.get(dom),
+                "traffic_source": "profiles/r1_ncu_full_summary_final.csv (bytes per launch)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": kern}

@@ -126,7 +126,7 @@ __device__ __forceinline__ int row_out_pos(int k) {  // where X[k] ends up
 
 // complex -> complex
 template <typename T, int N1, int N2, int DIR, class Load, class Store>
-__global__ void __launch_bounds__(512) row_fft_c2c_kernel(Load ld, Store st, RowTables<T> tabs) {
+__global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) row_fft_c2c_kernel(Load ld, Store st, RowTables<T> tabs) {
     using C = cx<T>;
     constexpr int N = N1 * N2, RS = N2 + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(512) row_fft_c2c_kernel(Load ld, Store st, Row
 // real (length 2N, packed two per complex) -> half spectrum X[0..N], forward
 // Load(row, n) returns (x[2n], x[2n+1]); Store(row, k, X[k]) for k in [0, N].
 template <typename T, int N1, int N2, class Load, class Store>
-__global__ void __launch_bounds__(512) row_fft_r2c_kernel(Load ld, Store st, RowTables<T> tabs) {
+__global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) row_fft_r2c_kernel(Load ld, Store st, RowTables<T> tabs) {
     using C = cx<T>;
     constexpr int N = N1 * N2, RS = N2 + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(512) row_fft_r2c_kernel(Load ld, Store st, Row
 // half spectrum X[0..N] -> real length 2N, UNNORMALISED inverse.
 // Load(row, k) returns X[k]; Store(row, n, z) receives (x[2n], x[2n+1]).
 template <typename T, int N1, int N2, class Load, class Store>
-__global__ void __launch_bounds__(512) row_fft_c2r_kernel(Load ld, Store st, RowTables<T> tabs) {
+__global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) row_fft_c2r_kernel(Load ld, Store st, RowTables<T> tabs) {
     using C = cx<T>;
     constexpr int N = N1 * N2, RS = N2 + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -209,10 +209,11 @@ __global__ void __launch_bounds__(512) row_fft_c2r_kernel(Load ld, Store st, Row
     for (int n = tid; n < N; n += nt) st(row, n, s[row_out_pos<T, N1, N2>(n)]);
 }
 
-inline int row_threads(int N) {
+inline int row_threads(int N, int elem_bytes = 8) {
     int t = N / 8;
     if (t < 32) t = 32;
-    if (t > 512) t = 512;
+    const int cap = elem_bytes <= 8 ? 1024 : 512;   // fp32 rows: 32 warps hide latency
+    if (t > cap) t = cap;
     return t;
 }
 
@@ -226,7 +227,7 @@ int launch_row_c2c(Load ld, Store st, long nrows, cudaStream_t stream) {
     auto kern = row_fft_c2c_kernel<T, N1, N2, DIR, Load, Store>;
     const size_t smem = RowSmem<T, N1, N2>::bytes;
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)nrows, row_threads(N), smem, stream>>>(ld, st, tabs);
+    kern<<<(unsigned)nrows, row_threads(N, (int)sizeof(cx<T>)), smem, stream>>>(ld, st, tabs);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }
@@ -240,7 +241,7 @@ int launch_row_r2c(Load ld, Store st, long nrows, cudaStream_t stream) {
     auto kern = row_fft_r2c_kernel<T, N1, N2, Load, Store>;
     const size_t smem = RowSmem<T, N1, N2>::bytes;
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)nrows, row_threads(N), smem, stream>>>(ld, st, tabs);
+    kern<<<(unsigned)nrows, row_threads(N, (int)sizeof(cx<T>)), smem, stream>>>(ld, st, tabs);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }
@@ -254,7 +255,7 @@ int launch_row_c2r(Load ld, Store st, long nrows, cudaStream_t stream) {
     auto kern = row_fft_c2r_kernel<T, N1, N2, Load, Store>;
     const size_t smem = RowSmem<T, N1, N2>::bytes;
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)nrows, row_threads(N), smem, stream>>>(ld, st, tabs);
+    kern<<<(unsigned)nrows, row_threads(N, (int)sizeof(cx<T>)), smem, stream>>>(ld, st, tabs);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }

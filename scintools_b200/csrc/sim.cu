@@ -260,7 +260,7 @@ __global__ void sim_filter_kernel(int nx, int ny, double scale, double ffconx,
 
 // y-axis FFT of one row kx, then g[kx] = fx[kx] * sum_ky X[kx][ky] fy[ky]
 template <int N1, int N2>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 sim_row_reduce_kernel(const float2* __restrict__ in, long pitch,
                       const float2* __restrict__ fx, const float2* __restrict__ fy,
                       float2* __restrict__ g, float2* __restrict__ full,
@@ -270,7 +270,7 @@ sim_row_reduce_kernel(const float2* __restrict__ in, long pitch,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* s = reinterpret_cast<C*>(smem_raw);
     C* tw1 = s + N1 * RS; C* tw2 = tw1 + N1; C* twl = tw2 + N2;
-    __shared__ float redx[16], redy[16];
+    __shared__ float redx[32], redy[32];
     const int tid = threadIdx.x, nt = blockDim.x;
     const long row = blockIdx.x;
     row_load_tables<float, N1, N2, -1>(tw1, tw2, twl, tabs.wN, tid, nt);
