@@ -125,6 +125,10 @@ def golden_thth(pkg):
         **extra)
     print("thth: peak eta = %.3f (tutorial states ~44)" %
           etas[np.argmax(eigs)])
+    # axes of the notebook's Dynspec (THTHSample.ipynb cell 13) for the
+    # prep_thetatheta known-answer tests
+    np.savez_compressed(os.path.join(GOLD, "sample_axes.npz"),
+                        f_MHz=arch["f_MHz"], t_s=arch["t_s"])
 
 
 def golden_sim(pkg):

@@ -57,3 +57,30 @@ def test_host_axes_match_oracle():
     assert np.array_equal(thth.theta_centres(e), TO.theta_centres(e))
     fd, tau = TO.fft_axis(t, "mHz"), TO.fft_axis(f, "us")
     assert np.array_equal(thth.min_edges(0.3, fd, tau, 50.0), TO.min_edges(0.3, fd, tau, 50.0))
+
+
+def test_prep_thetatheta_notebook_kats():
+    """Known answers printed in the reference's own notebook
+    (scintools/examples/THTHSample.ipynb cells 13-20): edge counts and the
+    first curvatures of the per-chunk eta grids.  Host logic only."""
+    import numpy as np
+    from scintools_b200 import BasicDyn, Dynspec
+    ax = np.load(os.path.join(ROOT, "tests", "golden", "sample_axes.npz"))
+    f, t = ax["f_MHz"], ax["t_s"]
+    dyn = np.ones((f.shape[0], t.shape[0]))
+    ds = Dynspec(dyn=BasicDyn(dyn, times=t, freqs=f, nsub=t.shape[0], nchan=f.shape[0],
+                              dt=t[1] - t[0], df=f[1] - f[0]), verbose=False)
+    assert ds.df == 0.12511455278581707 and ds.dt == 289.8978362416107
+    # cell 20
+    ds.prep_thetatheta(cwf=64, edges_lim=.3, eta_min=30, eta_max=50)
+    assert (ds.cwf, ds.cwt, ds.ncf_fit, ds.nct_fit) == (64, 150, 16, 1)
+    assert ds.fref == 1396.0 and (ds.eta_min, ds.eta_max) == (30.0, 50.0)
+    assert ds.edges.shape[0] == 302
+    etas = ds._chunk_etas(f[:64].mean())
+    np.testing.assert_allclose(etas[:3], [32.75781486, 33.08757201, 33.42064867], rtol=2e-9)
+    # cell 18 (eta_max there came from the Hough prior: pass the printed value)
+    ds.prep_thetatheta(cwf=128, edges_lim=.3, eta_min=30, eta_max=109.11037416158051)
+    assert (ds.ncf_fit, ds.ncf_ret) == (8, 15)
+    assert ds.edges.shape[0] == 1318
+    etas = ds._chunk_etas(f[:128].mean())
+    np.testing.assert_allclose(etas[:2], [32.56235154, 32.88990503], rtol=2e-9)
