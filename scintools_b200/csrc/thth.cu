@@ -399,12 +399,13 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
                     ++gc;
                     while (!mbar_try_wait(mybar + st, par)) {}
                     const float4* sg = mystage + st * 256;
+                    // lane-local group range [jlo, jhi) that lies inside [first4, ncol4)
+                    const int jlo = max(0, (first4 - lane + 31) >> 5);
+                    const int jhi = (ncol4 - lane + 31) >> 5;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int c4 = lane + 32 * j;
-                        mm[j] = (c4 >= first4 && c4 < ncol4) ? sg[c4]
-                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        mm[j] = (j >= jlo && j < jhi) ? sg[lane + 32 * j]
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
                     const float4* row = reinterpret_cast<const float4*>(M + (size_t)a * ld);
 #pragma unroll
@@ -423,13 +424,16 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
                     const float4 q = mm[j];
                     const float4 x = (2 * c4 < ld) ? *reinterpret_cast<const float4*>(v + 2 * c4)
                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-                    rx += q.x * x.x - q.y * x.y + q.z * x.z - q.w * x.w;
-                    ry += q.x * x.y + q.y * x.x + q.z * x.w + q.w * x.z;
+                    // explicit FMA chains (16 FFMA per two complex elements)
+                    rx = fmaf(q.x, x.x, rx); rx = fmaf(-q.y, x.y, rx);
+                    rx = fmaf(q.z, x.z, rx); rx = fmaf(-q.w, x.w, rx);
+                    ry = fmaf(q.x, x.y, ry); ry = fmaf(q.y, x.x, ry);
+                    ry = fmaf(q.z, x.w, ry); ry = fmaf(q.w, x.z, ry);
                     // conj(A) * v[a]
-                    yc[j].x += q.x * xa.x + q.y * xa.y;
-                    yc[j].y += q.x * xa.y - q.y * xa.x;
-                    yc[j].z += q.z * xa.x + q.w * xa.y;
-                    yc[j].w += q.z * xa.y - q.w * xa.x;
+                    yc[j].x = fmaf(q.x, xa.x, yc[j].x); yc[j].x = fmaf(q.y, xa.y, yc[j].x);
+                    yc[j].y = fmaf(q.x, xa.y, yc[j].y); yc[j].y = fmaf(-q.y, xa.x, yc[j].y);
+                    yc[j].z = fmaf(q.z, xa.x, yc[j].z); yc[j].z = fmaf(q.w, xa.y, yc[j].z);
+                    yc[j].w = fmaf(q.z, xa.y, yc[j].w); yc[j].w = fmaf(-q.w, xa.x, yc[j].w);
                 }
                 if (TMA) {
                     __syncwarp();
