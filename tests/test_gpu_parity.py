@@ -304,3 +304,48 @@ def test_batch_arc_pipeline(sb):
     for i, d in enumerate(dyns):
         ref = TO.single_search(d - d.mean(), f, t, etas, edges, 0.1, npad, True, 0.0)
         assert fit[i] == pytest.approx(ref[0], rel=1e-3)
+
+
+def test_dynspec_thetatheta_chunks(sb):
+    """Dynspec.prep_thetatheta / thetatheta_single / fit_thetatheta on a 2x2
+    chunk grid against the oracle's single_search per chunk and the reference's
+    weighted A/f^2 combination (dynspec.py:1724-1744)."""
+    rng = np.random.default_rng(21)
+    nf, nt = 128, 256
+    t = np.arange(nt) * 20.0
+    f = 1400.0 + np.arange(nf) * 0.05
+    fdk = rng.uniform(-6, 6, 24)
+    ak = (rng.normal(size=24) + 1j * rng.normal(size=24)) * np.exp(-(fdk / 3) ** 2)
+    E = sum(a * np.exp(2j * np.pi * (k * 1e-3 * t[None, :] - 30.0 * k ** 2 * (f[:, None] - f[0])))
+            for a, k in zip(ak, fdk))
+    dyn = np.abs(E) ** 2 + rng.normal(0, 0.02, (nf, nt))
+    ds = sb.Dynspec(dyn=sb.BasicDyn(dyn, times=t, freqs=f, dt=20.0, df=0.05), verbose=False)
+    ds.prep_thetatheta(cwf=64, cwt=128, eta_min=15.0, eta_max=60.0, nedge=128,
+                       edges_lim=8.0, fw=0.2, npad=3)
+    assert (ds.ncf_fit, ds.nct_fit) == (2, 2)
+    etas, eigs, popt = ds.thetatheta_single(cf=1, ct=0)
+    fs, ts = slice(64, 128), slice(0, 128)
+    d2 = dyn[fs, ts] - dyn[fs, ts].mean()
+    e_ref = TO.eta_grid(ds.eta_min, ds.eta_max, ds.fw, ds.fref, f[fs].mean())
+    assert np.array_equal(etas, e_ref)
+    CS = TO.conjugate_spectrum(d2, 3, 0.0)
+    ref = TO.eta_sweep(CS, TO.fft_axis(f[fs], "us", 3), TO.fft_axis(t[ts], "mHz", 3), e_ref,
+                       ds.edges * (f[fs].mean() / ds.fref))
+    assert (np.abs(eigs - ref) / ref).max() < RTOL
+    ds.fit_thetatheta()
+    assert ds.eta_evo.shape == (2, 2)
+    for cf in range(2):
+        for ct in range(2):
+            fs, ts = slice(cf * 64, (cf + 1) * 64), slice(ct * 128, (ct + 1) * 128)
+            d2 = dyn[fs, ts] - dyn[fs, ts].mean()
+            r = TO.single_search(d2, f[fs], t[ts],
+                                 TO.eta_grid(ds.eta_min, ds.eta_max, ds.fw, ds.fref, f[fs].mean()),
+                                 ds.edges * (f[fs].mean() / ds.fref), ds.fw, 3, True, 0.0)
+            assert ds.eta_evo[cf, ct] == pytest.approx(r[0], rel=1e-3)
+    f0 = ds.f0s[:, None]
+    ok = np.isfinite(ds.eta_evo) * np.isfinite(ds.eta_evo_err)
+    A = (np.sum(ds.eta_evo[ok] / (f0 * ds.eta_evo_err)[ok] ** 2) /
+         np.sum(1 / ((f0 ** 2) * ds.eta_evo_err)[ok] ** 2))
+    assert ds.ththeta == pytest.approx(A / ds.fref ** 2, rel=1e-12)
+    with pytest.raises(ValueError):
+        ds.fit_thetatheta(pool=object())
