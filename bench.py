@@ -82,8 +82,12 @@ def peak_hbm():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi sampling in the background (started well before the timed
+    region so that it is already polling); `stop(t0, t1)` keeps the samples
+    whose timestamp falls inside the timed window (wall clock), falling back to
+    the samples taken under load (power above half of the maximum seen)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -91,15 +95,17 @@ class ClockSampler:
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -107,27 +113,34 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                  "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), float(parts[3]),
+                             [nm for nm, v in zip(names, parts[4:8])
+                              if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.f.name)
-        if sm:
-            hot = [v for v in sm if v > 0.5 * max(sm)] or sm
-            out = {"sm_mhz": float(np.median(hot)), "sm_max_mhz": float(max(mx)),
-                   "reasons": sorted(reasons), "samples": len(sm)}
-        return out
+        if not rows:
+            return out
+        sel = [r for r in rows if t0 is not None and t0 - 0.03 <= r[0] <= t1 + 0.03]
+        how = "timed window"
+        if not sel:
+            pmax = max(r[3] for r in rows)
+            sel = [r for r in rows if r[3] >= 0.5 * pmax]
+            how = "samples under load around the timed window"
+        reasons = sorted({x for r in sel for x in r[4]})
+        return {"sm_mhz": float(np.median([r[1] for r in sel])),
+                "sm_max_mhz": float(max(r[2] for r in sel)), "reasons": reasons,
+                "power_w_max": float(max(r[3] for r in sel)),
+                "samples": len(sel), "from": how}
 
 
 # --------------------------------------------------------------------------
@@ -233,6 +246,7 @@ def b200_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    clocks = ClockSampler(local)      # polling from the start; windowed later
     dyn, freq, t = make_dynspec()
     fd = np.asarray(thth.fft_axis(t, "mHz", NPAD))
     tau = np.asarray(thth.fft_axis(freq, "us", NPAD))
@@ -273,17 +287,18 @@ def b200_arm(args):
     for _ in range(args.warmup):
         step()
     sync_all()
-    clocks = ClockSampler(local)
     launches0 = L.sb_launch_count()
     L.sb_profile_enable(1)
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     sync_all()
+    wall0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     sync_all()
+    wall1 = time.time()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -292,7 +307,7 @@ def b200_arm(args):
     prof_ms = (np.zeros(16), np.zeros(16, dtype=np.int32))
     _lib.check(L.sb_profile_collect(prof_ms[0].ctypes.data, prof_ms[1].ctypes.data, 16))
     L.sb_profile_enable(0)
-    clk = clocks.stop()
+    clk = clocks.stop(wall0, wall1)
 
     eigs = d_eigs.cpu().numpy()
     nred = d_nred.cpu().numpy().astype(np.int64)
