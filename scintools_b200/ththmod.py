@@ -17,7 +17,6 @@ per-call semantics) or a ``DeviceCS`` that keeps the spectrum resident.
 There is no CPU fallback.
 """
 import ctypes
-import warnings
 
 import numpy as np
 from scipy.optimize import curve_fit
@@ -80,12 +79,12 @@ class DeviceCS:
     def numpy(self):
         """The full fftshifted complex128 array (expands a half-plane CS)."""
         a = self.t.cpu().numpy()
-        z = (a[..., 0] + 1j * a[..., 1]).astype(np.complex128)
         if not self.half:
-            return z
+            return (a[..., 0] + 1j * a[..., 1]).astype(np.complex128)
         ntau, nfd = self.shape
         h = nfd // 2
-        pos = z[:, :h + 1]                       # unshifted columns 0..h
+        a = a[:, :h + 1]                         # drop the pitch padding
+        pos = (a[..., 0] + 1j * a[..., 1]).astype(np.complex128)   # unshifted columns 0..h
         full = np.empty((ntau, nfd), dtype=np.complex128)
         full[:, h:] = pos[:, :h]                 # shifted columns h..nfd-1
         full[:, 0] = pos[:, h]                   # Nyquist column
@@ -355,6 +354,3 @@ def min_edges(fd_lim, fd, tau, eta, factor=2):
     return U.wrap(np.linspace(-fd_lim_v, fd_lim_v, int(npoints)), "mHz",
                   like=fd_lim)
 
-
-def _silence_unused():  # keep flake8 quiet about optional imports
-    return warnings
