@@ -68,120 +68,62 @@ __global__ void thth_indexerr_kernel(ThthGeom g, const double* __restrict__ etas
 }
 
 // --------------------------------------------------------------------------
-// eta-independent part of the gather, once per sweep: for every pair i < j of
-// theta centres
-//   d[i][j]   = th_j^2 - th_i^2            (fp64, the operand of eta * d)
-//   col[i][j] = where the fd index lands in the stored CS: column c >= 0, or
-//               -(c+1) when the point lies in the mirrored (fd < 0) half of a
-//               half-plane CS (row ntau - tau_inv, conjugate), or COL_NEVER
-//               when fd_inv >= nfd / would raise (handled by the index-error
-//               kernel)
-//   s[i][j]   = sqrt|th_i - th_j|          (Jacobian = sqrt(2 eta) * s)
-// so the per-eta kernel is left with one fp64 multiply-add chain, one exact
-// floor and the gather itself.
-// --------------------------------------------------------------------------
-#define SB_COL_NEVER 0x7fffffff
-
-__global__ void thth_pairs_kernel(ThthGeom g, double* __restrict__ td,
-                                  int* __restrict__ tcol, float* __restrict__ ts) {
-    const long long total = (long long)g.n * g.n;
-    const int nfd = (int)g.nfd;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
-         p += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(p / g.n), j = (int)(p % g.n);
-        if (j <= i) continue;
-        const double th1 = g.th[j], th2 = g.th[i];
-        td[p] = __dsub_rn(__dmul_rn(th1, th1), __dmul_rn(th2, th2));
-        ts[p] = sqrtf((float)fabs(th2 - th1));
-        const double b = __dadd_rn(__dsub_rn(__dsub_rn(th1, th2), g.fd0), g.half_dfd);
-        const double fqd = floor_div_fast(b, g.dfd, g.inv_dfd);
-        int code = SB_COL_NEVER;
-        if (!(fqd >= (double)nfd) && (fqd >= -(double)nfd)) {   // inside [-nfd, nfd)
-            int fi = (int)fqd;
-            if (fi < 0) fi += nfd;                               // python negative index
-            if (!g.cs_half) {
-                code = fi;
-            } else {
-                const int h = nfd >> 1;
-                if (fi >= h) code = fi - h;
-                else if (fi == 0) code = h;
-                else code = -((h - fi) + 1);
-            }
-        }
-        tcol[p] = code;
-    }
-}
-
-// --------------------------------------------------------------------------
 // build the cropped theta-theta matrix for a batch of etas: STRICT UPPER
 // triangle only (the matrix is Hermitian with zero diagonal; the eigen kernel
-// uses every stored element twice).  grid = (eta groups, tile pairs), block =
-// 32 x 8.  M[e] is [ld][ld] float2; inside the active 32x32 tiles columns >=
-// nred and the diagonal are zero, the lower triangle is not touched.
-// eta is the FAST grid index: CTAs resident at the same time work on the same
-// tile for ~900 neighbouring curvatures, whose gathers fall on the same /
-// adjacent CS rows (L2 reuse: DRAM read 9.96 GB -> 1.37 GB per sweep).
+// uses every stored element twice).  grid = (tile pairs, etas in batch),
+// block = 32 x 8.  M[e] is [ld][ld] float2; inside the active 32x32 tiles
+// columns >= nred and the diagonal are zero, the lower triangle is not touched.
 // --------------------------------------------------------------------------
 #define SB_BUILD_EB 4
 __global__ void __launch_bounds__(256)
 thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nbatch,
-                  int ld, const int* __restrict__ idx, const int* __restrict__ nred,
-                  const double* __restrict__ td, const int* __restrict__ tcol,
-                  const float* __restrict__ ts, float2* __restrict__ M) {
+                  int ld, const int* __restrict__ idx,
+                  const int* __restrict__ nred, float2* __restrict__ M) {
     __shared__ int ia[32], ib[32];
+    __shared__ double ta_[32], tb_[32];
+    // eta is the FAST grid index: CTAs resident at the same time work on the
+    // same 32x32 tile for ~900 neighbouring curvatures, whose gathers fall on
+    // the same / adjacent CS rows for small |theta1^2 - theta2^2| (L2 reuse)
     // pair index -> (ta <= tb)
     int p = blockIdx.y, ta = 0;
     const int T = ld / 32;
     while (p >= T - ta) { p -= T - ta; ++ta; }
     const int tb = ta + p;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int ntau = (int)g.ntau;
-    for (int e = blockIdx.x * SB_BUILD_EB; e < min(nbatch, (int)(blockIdx.x + 1) * SB_BUILD_EB); ++e) {
-        const int n = nred[eta0 + e];
-        if (tb * 32 >= n) continue;  // never read by the eigen kernel
-        const double eta = etas[eta0 + e];
-        const float sq2eta = sqrtf((float)fabs(2.0 * eta));
-        const int* id = idx + (size_t)(eta0 + e) * ld;
-        __syncthreads();
-        if (ty == 0) {
-            const int a = ta * 32 + tx;
-            ia[tx] = a < n ? id[a] : -1;
-        } else if (ty == 1) {
-            const int b = tb * 32 + tx;
-            ib[tx] = b < n ? id[b] : -1;
-        }
-        __syncthreads();
-        float2* Me = M + (size_t)e * ld * ld;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int la = ty + 8 * k, lb = tx;
-            if (ta == tb && lb < la) continue;      // lower triangle: not stored
-            const int i = ia[la], j = ib[lb];
-            float2 v = make_float2(0.f, 0.f);
-            if (i >= 0 && j > i && i + j != g.n - 1) {
-                const size_t t = (size_t)i * g.n + j;
-                const int code = __ldg(tcol + t);
-                if (code != SB_COL_NEVER) {
-                    // tau_inv (ththmod.py:94-95), exact floor
-                    const double a = __dadd_rn(__dsub_rn(__dmul_rn(eta, __ldg(td + t)), g.tau0),
-                                               g.half_dtau);
-                    const double tqd = floor_div_fast(a, g.dtau, g.inv_dtau);
-                    if (tqd > 0.0 && tqd < (double)ntau) {     // pnts, ththmod.py:100
-                        const int tq = (int)tqd;
-                        const int r = code < 0 ? ntau - tq : tq;
-                        const int c = code < 0 ? -code - 1 : code;
-                        v = __ldg(g.cs + (size_t)r * (size_t)g.cs_pitch + c);
-                        if (code < 0) v.y = -v.y;
-                        if (!g.coherent) v = make_float2(hypotf(v.x, v.y), 0.f);
-                        const float wf = sq2eta * __ldg(ts + t);
-                        v.x = nan_to_num(v.x * wf);
-                        v.y = nan_to_num(v.y * wf);
-                    }
-                }
-            }
-            Me[(size_t)(ta * 32 + la) * ld + tb * 32 + lb] = v;
-        }
+  // EB consecutive curvatures per CTA, back to back: their gathers hit the
+  // same or neighbouring CS rows
+  for (int e = blockIdx.x * SB_BUILD_EB; e < min(nbatch, (int)(blockIdx.x + 1) * SB_BUILD_EB); ++e) {
+    const int n = nred[eta0 + e];
+    if (tb * 32 >= n) continue;  // never read by the eigen kernel
+    const double eta = etas[eta0 + e];
+    const int* id = idx + (size_t)(eta0 + e) * ld;
+    __syncthreads();
+    if (ty == 0) {
+        int a = ta * 32 + tx;
+        ia[tx] = a < n ? id[a] : -1;
+        ta_[tx] = a < n ? g.th[id[a]] : 0.0;
+    } else if (ty == 1) {
+        int b = tb * 32 + tx;
+        ib[tx] = b < n ? id[b] : -1;
+        tb_[tx] = b < n ? g.th[id[b]] : 0.0;
     }
+    __syncthreads();
+    float2* Me = M + (size_t)e * ld * ld;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int la = ty + 8 * k, lb = tx;
+        if (ta == tb && lb < la) continue;      // lower triangle: not stored
+        const int i = ia[la], j = ib[lb];
+        float2 v = make_float2(0.f, 0.f);
+        if (i >= 0 && j > i && i + j != g.n - 1) {
+            ThthPoint pt = thth_point(g, eta, tb_[lb], ta_[la]);
+            v = thth_value(g, eta, tb_[lb], ta_[la], pt);
+            v.x = nan_to_num(v.x);
+            v.y = nan_to_num(v.y);
+        }
+        Me[(size_t)(ta * 32 + la) * ld + tb * 32 + lb] = v;
+    }
+  }
 }
 
 // --------------------------------------------------------------------------
@@ -661,21 +603,6 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
     if (batch > neta) batch = neta;
     float2* d_M = (float2*)workspace(2, per * batch);
     if (!d_M) return SB_ERR_NOMEM;
-    // eta-independent pair tables (fp64 d, int32 column code, fp32 sqrt|dtheta|)
-    const size_t npair = (size_t)g.n * g.n;
-    unsigned char* tbl = (unsigned char*)workspace(6, npair * 16 + 256);
-    if (!tbl) return SB_ERR_NOMEM;
-    double* d_td = (double*)tbl;
-    int* d_tcol = (int*)(tbl + npair * 8);
-    float* d_ts = (float*)(tbl + npair * 12);
-    {
-        long long blocks = (long long)((npair + 255) / 256);
-        if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-        prof_begin(PROF_THTH_PREP, st);
-        thth_pairs_kernel<<<(int)blocks, 256, 0, st>>>(g, d_td, d_tcol, d_ts);
-        prof_end(PROF_THTH_PREP, st);
-        SB_LAUNCH_CHECK();
-    }
     const int T = ld / 32;
     const int npairs = T * (T + 1) / 2;
     // TMA ring variant (ld <= 512): 256 threads, 2 stages -> 2 CTAs per SM so
@@ -696,8 +623,7 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
         int nb = neta - e0 < batch ? neta - e0 : batch;
         dim3 grid((nb + SB_BUILD_EB - 1) / SB_BUILD_EB, npairs), block(32, 8);
         prof_begin(PROF_THTH_BUILD, st);
-        thth_build_kernel<<<grid, block, 0, st>>>(g, d_etas, e0, nb, ld, d_idx, d_nred,
-                                                  d_td, d_tcol, d_ts, d_M);
+        thth_build_kernel<<<grid, block, 0, st>>>(g, d_etas, e0, nb, ld, d_idx, d_nred, d_M);
         prof_end(PROF_THTH_BUILD, st);
         SB_LAUNCH_CHECK();
         prof_begin(PROF_THTH_EIG, st);
