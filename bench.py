@@ -259,7 +259,10 @@ def b200_arm(args):
     ntau, nfd = (NPAD + 1) * NF, (NPAD + 1) * NT
     pitch = nfd // 2 + 16          # Hermitian half-plane CS (fd >= 0)
     d_cs = D.empty((ntau, pitch, 2), torch.float32)
-    cs = thth.DeviceCS(d_cs, nfd=nfd)
+    # the sweep gathers at fd = theta_j - theta_i <= 2*EDGE_LIM: only those fd
+    # columns of the CS are computed (exactly what single_search does)
+    keep = thth.needed_fd_columns(fd, edges) or 0
+    cs = thth.DeviceCS(d_cs, nfd=nfd, ncols_valid=keep or None)
     geom = thth._Geom(cs, tau, fd, edges, True)
     d_etas = D.upload(etas)
     d_eigs = D.empty((NETA,), torch.float64)
@@ -271,7 +274,7 @@ def b200_arm(args):
     L = _lib.lib
 
     def step():
-        _lib.check(L.sb_cs_f32(d_dyn.data_ptr(), NF, NT, NPAD, 0.0, 0, 1, pitch,
+        _lib.check(L.sb_cs_f32(d_dyn.data_ptr(), NF, NT, NPAD, 0.0, 0, 1, pitch, keep,
                                d_cs.data_ptr(), stream))
         _lib.check(L.sb_eta_sweep(geom.ref, d_etas.data_ptr(), NETA, thth.DEFAULT_TOL,
                                   0, d_eigs.data_ptr(), d_stat.data_ptr(),
@@ -363,7 +366,9 @@ def b200_arm(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             from oracle import thth_oracle as TO   # checker / CPU baseline only
-            CS_host = cs.numpy().astype(np.complex64)
+            full = thth.conjugate_spectrum(dyn, NPAD, 0.0)      # all columns, for the CPU leg
+            CS_host = full.numpy().astype(np.complex64)
+            del full
             sel = np.linspace(0, NETA - 1, 8).astype(int)
             secs, ref = cpu_sample(CS_host, tau, fd, edges, etas[sel], 1)
             rel = np.abs(eigs[sel] - ref) / np.abs(ref)
@@ -383,6 +388,9 @@ def b200_arm(args):
                                    "16384x32768 (fd>=0 half stored, 2.15 GB c64) recomputed every step, "
                                    "512-pt theta grid, 1024 etas per GPU",
                        "etas_total": world * NETA,
+                       "cs_columns": "%d of %d fd>=0 columns computed (those the "
+                                     "512-pt theta grid can reach)" % (keep or nfd // 2 + 1,
+                                                                      nfd // 2 + 1),
                        "l2": "inputs larger than L2 (CS half-plane 2.15 GB, matrices 1.07 GB)",
                        "tol": thth.DEFAULT_TOL,
                        "parallelism": "eta blocks per rank, CS replicated, one "

@@ -150,12 +150,17 @@ int sb_acf_sspec_f32(const float* dyn, int32_t nf, int32_t nt, const float* win_
  * writes only the fd >= 0 half, [(npad+1)nf][cs_pitch] with cs_pitch >=
  * (npad+1)nt/2 + 1 (see sb_thth_geom.cs_half): half the HBM traffic, and all
  * the theta-theta sweep needs.  half_plane=0: full array, cs_pitch ignored.
+ * ncols_keep > 0 (half-plane only): compute just the first ncols_keep fd >= 0
+ * columns; the others are left untouched.  The sweep gathers at
+ * fd = theta_j - theta_i <= max(theta) - min(theta), so a caller that knows
+ * its theta grid can skip the columns beyond that (the column passes dominate
+ * the transform).  0 = all nfd/2 + 1 columns.
  * Power-of-two padded sizes take the direct radix-16 path (rows <= 65536, cols
  * <= 32768); any other size runs a chirp-z (Bluestein) transform on both axes
  * (rows <= 32768, cols <= 8192, half_plane must be 0). */
 int sb_cs_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad,
               float pad_value, const uint8_t* tau_rowmask, int32_t half_plane,
-              int64_t cs_pitch, void* cs, void* stream);
+              int64_t cs_pitch, int32_t ncols_keep, void* cs, void* stream);
 
 /* ---- scint_sim.Simulation ------------------------------------------------ */
 

@@ -64,7 +64,7 @@ _SIGS = {
                              c_int, c_int, vp, vp, vp, vp]),
     "sb_acf_f32": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp]),
     "sb_acf_sspec_f32": (c_int, [vp, c_int, c_int, vp, vp, c_dbl, c_dbl, c_int, vp, vp]),
-    "sb_cs_f32": (c_int, [vp, c_int, c_int, c_int, c_flt, vp, c_int, c_i64, vp, vp]),
+    "sb_cs_f32": (c_int, [vp, c_int, c_int, c_int, c_flt, vp, c_int, c_i64, c_int, vp, vp]),
     "sb_sim_weights": (c_int, [ctypes.POINTER(SimParams), vp, vp]),
     "sb_sim_screen": (c_int, [c_int, c_int, vp, vp, vp, ctypes.c_uint64, vp, vp]),
     "sb_sim_intensity": (c_int, [c_int, c_int, c_int, vp, vp, c_dbl, c_dbl, vp,

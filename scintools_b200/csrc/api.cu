@@ -100,8 +100,8 @@ int sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
           const float* pd1, const float* pd2, float* sec, cudaStream_t st,
           int noshift = 0);
 int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
-                  const unsigned char* rowmask, int half, long pitch, float2* CS,
-                  cudaStream_t st);
+                  const unsigned char* rowmask, int half, long pitch, int ncols_keep,
+                  float2* CS, cudaStream_t st);
 int acf(const float* dyn, int nf, int nt, int subtract_mean, int normalise,
         float* out, cudaStream_t st);
 int acf_sspec(const float* dyn, int nf, int nt, const float* wt, const float* wf,
@@ -255,11 +255,11 @@ int sb_acf_sspec_f32(const float* dyn, int32_t nf, int32_t nt, const float* win_
 
 int sb_cs_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad,
               float pad_value, const uint8_t* tau_rowmask, int32_t half_plane,
-              int64_t cs_pitch, void* cs, void* stream) {
+              int64_t cs_pitch, int32_t ncols_keep, void* cs, void* stream) {
     SB_ARG(dspec && cs && nf >= 1 && nt >= 1 && npad >= 0);
     SB_ARG(!half_plane || cs_pitch >= (int64_t)(npad + 1) * nt / 2 + 1);
     return sb::conj_spectrum(dspec, nf, nt, npad, pad_value, tau_rowmask,
-                             half_plane, (long)cs_pitch, (float2*)cs,
+                             half_plane, (long)cs_pitch, ncols_keep, (float2*)cs,
                              (cudaStream_t)stream);
 }
 

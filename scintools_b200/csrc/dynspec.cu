@@ -120,11 +120,12 @@ struct DynRowLoad {
     }
 };
 
-struct HalfStore {   // X[k] -> H[row][k]
+struct HalfStore {   // X[k] -> H[row][k], only the first kmax bins are kept
     float2* H;
     long pitch;
+    int kmax;
     __device__ __forceinline__ void operator()(long row, int k, float2 v) const {
-        H[row * pitch + k] = v;
+        if (k < kmax) H[row * pitch + k] = v;
     }
 };
 
@@ -329,8 +330,8 @@ static int next_pow2(long v) {
 
 // rows: real dyn [nf_live][*] -> H[nf_live][pitch] half spectra of length NT
 static int rows_r2c(const DynRowLoad& ld, float2* H, long pitch, int NT,
-                    long nrows, cudaStream_t st) {
-    HalfStore hs{H, pitch};
+                    long nrows, cudaStream_t st, int kmax = 1 << 30) {
+    HalfStore hs{H, pitch, kmax};
     const int N = NT / 2;
     SB_ROW_DISPATCH(N, return (launch_row_r2c<float, N1, N2>(ld, hs, nrows, st)));
     return SB_OK;
@@ -520,8 +521,8 @@ static int conj_spectrum_bluestein(const float* dyn, int nf, int nt, int NF, int
 // conjugate spectrum of a zero(/constant)-padded chunk
 // (ththmod.py:777-787, dynspec.py:1572-1579)
 int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
-                  const unsigned char* rowmask, int half, long cs_pitch, float2* CS,
-                  cudaStream_t st) {
+                  const unsigned char* rowmask, int half, long cs_pitch, int ncols_keep,
+                  float2* CS, cudaStream_t st) {
     const long NFl = (long)(npad + 1) * nf, NTl = (long)(npad + 1) * nt;
     if (!is_pow2(NFl) || !is_pow2(NTl) || NTl / 2 < 8 || NFl < 4) {
         // arbitrary lengths: chirp-z on both axes, full plane only
@@ -563,15 +564,20 @@ int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,
         pad_value = 0.f;
     }
     DynRowLoad ld{dyn, nf, nt, nullptr, nullptr, stats, dev_mean ? 3 : 2, 0, pad_value};
+    // only the first ncols fd >= 0 columns are wanted (the theta-theta gather
+    // never reads beyond max(theta) - min(theta)): the column passes, which
+    // dominate, shrink proportionally
+    int ncols = NT / 2 + 1;
+    if (half && ncols_keep > 0 && ncols_keep < ncols) ncols = ncols_keep;
     prof_begin(PROF_CS_ROWS, st);
-    int rc = rows_r2c(ld, H, pitch, NT, nf, st);
+    int rc = rows_r2c(ld, H, pitch, NT, nf, st, ncols);
     prof_end(PROF_CS_ROWS, st);
     if (rc) return rc;
     int R1, R2;
     split_len(NF, &R1, &R2);
     CsStore cs{CS, NF, NT, R1, rowmask, pad_value * (float)NF * (float)NT, half, cs_pitch,
                dev_mean ? stats : nullptr};
-    return cols_forward(H, A, pitch, NF, nf, NT / 2 + 1, cs, st, PROF_CS_COLA, PROF_CS_COLB);
+    return cols_forward(H, A, pitch, NF, nf, ncols, cs, st, PROF_CS_COLA, PROF_CS_COLB);
 }
 
 

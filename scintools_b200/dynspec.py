@@ -354,10 +354,11 @@ class Dynspec:
         fd = U.value(thth.fft_axis(time2, "mHz", self.npad), "mHz")
         dspec2 = np.copy(self.dyn[fs, ts]).astype(np.float64)
         dspec2 -= np.nanmean(dspec2)
-        cs = thth.conjugate_spectrum(np.nan_to_num(dspec2), self.npad, 0.0,
-                                     tau, self.thth_tau_mask)
         etas = self._chunk_etas(freq2.mean())
         edges = self.edges * (freq2.mean() / self.fref)
+        cs = thth.conjugate_spectrum(np.nan_to_num(dspec2), self.npad, 0.0,
+                                     tau, self.thth_tau_mask,
+                                     ncols_keep=thth.needed_fd_columns(fd, edges))
         eigs = thth.eta_sweep(cs, tau, fd, etas, edges,
                               self.thetatheta_proc == 'standard')
         if not np.all(np.isfinite(eigs)) and verbose:

@@ -62,12 +62,15 @@ class DeviceCS:
     (unshifted k = 0..nfd/2) of the CS of a REAL dynamic spectrum; the other
     half is its Hermitian mirror and is never materialised."""
 
-    def __init__(self, tensor, nfd=None):
+    def __init__(self, tensor, nfd=None, ncols_valid=None):
         assert tensor.dim() == 3 and tensor.shape[2] == 2
         self.t = tensor
         self.half = nfd is not None
         self.pitch = int(tensor.shape[1])
         self.shape = (int(tensor.shape[0]), int(nfd) if self.half else self.pitch)
+        # half-plane only: number of fd >= 0 columns that were computed
+        self.ncols_valid = ncols_valid if ncols_valid is not None else \
+            (self.shape[1] // 2 + 1 if self.half else self.shape[1])
 
     @classmethod
     def from_numpy(cls, CS):
@@ -83,6 +86,10 @@ class DeviceCS:
             return (a[..., 0] + 1j * a[..., 1]).astype(np.complex128)
         ntau, nfd = self.shape
         h = nfd // 2
+        if self.ncols_valid < h + 1:
+            raise ValueError("this DeviceCS holds only the first %d fd columns "
+                             "(built with fd_max); it cannot be expanded"
+                             % self.ncols_valid)
         a = a[:, :h + 1]                         # drop the pitch padding
         pos = (a[..., 0] + 1j * a[..., 1]).astype(np.complex128)   # unshifted columns 0..h
         full = np.empty((ntau, nfd), dtype=np.complex128)
@@ -135,6 +142,11 @@ class _Geom:
         g.cs_half = 1 if (cs is not None and cs.half) else 0
         g.cs_pitch = cs.pitch if cs is not None else fd.shape[0]
         self.g = g
+        if cs is not None and cs.half and cs.ncols_valid < fd.shape[0] // 2 + 1:
+            need = needed_fd_columns(fd, edges)
+            if need is None or need > cs.ncols_valid:
+                raise ValueError("this DeviceCS was built for a narrower theta "
+                                 "grid (%d fd columns); rebuild it" % cs.ncols_valid)
 
     @property
     def ref(self):
@@ -257,14 +269,34 @@ def thth_redmap(CS, tau, fd, eta, edges, hermetian=True):
     return red, U.wrap(edges_red, "mHz", like=edges)
 
 
+def needed_fd_columns(fd, edges):
+    """How many fd >= 0 columns of the conjugate spectrum a theta-theta map on
+    ``edges`` can touch: above the diagonal fd = theta_j - theta_i lies in
+    (0, max(theta) - min(theta)].  Returns None when the grid reaches past the
+    fd axis (gathers wrap to negative fd -> every column may be needed)."""
+    fd = U.value(fd, "mHz")
+    th = theta_centres(U.value(edges, "mHz"))
+    dfd = float(np.diff(fd).mean())
+    span = float(th.max() - th.min())
+    n = fd.shape[0]
+    if n % 2 or not np.isfinite(span) or dfd <= 0 or fd[n // 2] != 0.0:
+        return None
+    cmax = int(np.floor(span / dfd + 0.5)) + 2          # +2 bins of slack
+    if cmax >= n // 2:
+        return None
+    return cmax + 1
+
+
 def conjugate_spectrum(dspec2, npad, pad_value=None, tau=None, tau_mask=0.0,
-                       half=True):
+                       half=True, ncols_keep=None):
     """CS stage of single_search (ththmod.py:777-787): pad, fft2, fftshift,
     zero |tau| < tau_mask.  Returns a DeviceCS.  ``pad_value=None`` pads with
     dspec2.mean() like single_search; 0.0 reproduces
     Dynspec.thetatheta_single (dynspec.py:1575-1579).  ``half=True`` keeps only
     the fd >= 0 half on the device (the spectrum of a real array is Hermitian;
-    ``.numpy()`` still returns the full array)."""
+    ``.numpy()`` still returns the full array).  ``ncols_keep`` (half-plane
+    only; see needed_fd_columns) restricts the transform to the fd columns a
+    given theta grid can reach."""
     import torch
     d = np.asarray(dspec2)
     nf, nt = d.shape
@@ -281,10 +313,12 @@ def conjugate_spectrum(dspec2, npad, pad_value=None, tau=None, tau_mask=0.0,
         m = np.abs(U.value(tau, "us")) < float(U.value(tau_mask, "us"))
         if m.any():
             mask = D.upload(m.astype(np.uint8))
+    keep = int(ncols_keep) if (half and ncols_keep) else 0
     _lib.check(_lib.lib.sb_cs_f32(dd.data_ptr(), nf, nt, npad, float(pad_value),
-                                  D.ptr(mask), 1 if half else 0, pitch,
+                                  D.ptr(mask), 1 if half else 0, pitch, keep,
                                   cs.data_ptr(), D.stream_ptr()))
-    return DeviceCS(cs, nfd=NT if half else None)
+    return DeviceCS(cs, nfd=NT if half else None,
+                    ncols_valid=keep if keep else None)
 
 
 def peak_fit(etas, eigs, fw):
@@ -330,7 +364,8 @@ def single_search(params):
     etas_v = U.value(etas, "s3")
     fd = U.value(fft_axis(time_v, "mHz", npad), "mHz")
     tau = U.value(fft_axis(freq_v, "us", npad), "us")
-    cs = conjugate_spectrum(dspec2, npad, None, tau, tauMask)
+    cs = conjugate_spectrum(dspec2, npad, None, tau, tauMask,
+                            ncols_keep=needed_fd_columns(fd, edges))
     eigs = eta_sweep(cs, tau, fd, etas_v, edges, bool(coher))
     eta_fit, eta_sig, _ = peak_fit(etas_v, eigs, fw)
     if verbose:

@@ -349,3 +349,31 @@ def test_dynspec_thetatheta_chunks(sb):
     assert ds.ththeta == pytest.approx(A / ds.fref ** 2, rel=1e-12)
     with pytest.raises(ValueError):
         ds.fit_thetatheta(pool=object())
+
+
+def test_column_limited_cs(sb):
+    """conjugate_spectrum(ncols_keep=needed_fd_columns(...)) gives the same
+    sweep as the full CS, and refuses a theta grid wider than it was built for."""
+    rng = np.random.default_rng(31)
+    nf, nt, npad = 64, 256, 3
+    d = rng.normal(size=(nf, nt))
+    d -= d.mean()
+    t = np.arange(nt) * 10.0
+    f = 1400 + 0.1 * np.arange(nf)
+    fd = TO.fft_axis(t, "mHz", npad)
+    tau = TO.fft_axis(f, "us", npad)
+    thth = sb.ththmod
+    edges = np.linspace(-6, 6, 128)
+    keep = thth.needed_fd_columns(fd, edges)
+    assert keep is not None and keep < fd.shape[0] // 2
+    etas = np.linspace(0.005, 0.05, 10)
+    full = thth.conjugate_spectrum(d, npad, 0.0)
+    lim = thth.conjugate_spectrum(d, npad, 0.0, ncols_keep=keep)
+    a = thth.eta_sweep(full, tau, fd, etas, edges)
+    b = thth.eta_sweep(lim, tau, fd, etas, edges)
+    assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        thth.eta_sweep(lim, tau, fd, etas, np.linspace(-12, 12, 128))
+    with pytest.raises(ValueError):
+        lim.numpy()
+    assert thth.needed_fd_columns(fd, np.linspace(-60, 60, 64)) is None
