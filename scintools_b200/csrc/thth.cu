@@ -11,6 +11,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "thth.cuh"
 
 namespace sb {
@@ -366,6 +368,110 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
     for (int it = 0; it < max_iter; ++it) {
         for (int c = tid; c < ld; c += THREADS) w[c] = make_float2(0.f, 0.f);
         __syncthreads();
+        if constexpr (TMA) {
+            // ---- single column chunk (ld <= 512).  Rows are grouped by JS =
+            // number of 32-float4 column groups entirely left of the diagonal,
+            // and the row body is specialised on JS (no per-group branches,
+            // masks only on the boundary group); row sums use split
+            // accumulators and one 5-step shuffle tree for (re, im) together.
+            float4 yc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) yc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int K = (n - 2 >= warp) ? (n - 2 - warp) / NW + 1 : 0;
+            const bool tail = ncol4 < 256;        // cropped matrix: mask the right edge too
+            const float4* v4 = reinterpret_cast<const float4*>(v);
+            // prologue: fill the ring
+            for (int k = 0; k < NST && k < K; ++k) {
+                const int st = gi % NST;
+                ++gi;
+                if (lane == 0) {
+                    const int a = warp + NW * k;
+                    const int c_lo = (a + 1) & ~1;
+                    const unsigned bytes = (unsigned)(2 * ncol4 - c_lo) * 8u;
+                    mbar_expect_tx(mybar + st, bytes);
+                    bulk_g2s(reinterpret_cast<float2*>(mystage + st * 256) + c_lo,
+                             M + (size_t)a * ld + c_lo, bytes, mybar + st);
+                }
+            }
+            int k = 0;
+            auto run_rows = [&](auto JSc) {
+                constexpr int JS = decltype(JSc)::value;
+                for (; k < K && ((warp + NW * k + 1) >> 6) == JS; ++k) {
+                    const int a = warp + NW * k;
+                    const int first4 = (a + 1) >> 1;
+                    const float2 xa = v[a];
+                    const int st = gc % NST;
+                    const unsigned par = (gc / NST) & 1u;
+                    ++gc;
+                    while (!mbar_try_wait(mybar + st, par)) {}
+                    const float4* sg = mystage + st * 256;
+                    float rxa = 0.f, rxb = 0.f, rya = 0.f, ryb = 0.f;
+#pragma unroll
+                    for (int j = JS; j < 8; ++j) {
+                        const int c4 = lane + 32 * j;
+                        float4 q = sg[c4];
+                        bool ok = (j > JS) || (c4 >= first4);
+                        if (tail) ok = ok && (c4 < ncol4);
+                        if (!ok) q = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 x = v4[c4];   // in-bounds of the dynamic smem for any ld
+                        if (tail && !ok) x = make_float4(0.f, 0.f, 0.f, 0.f);   // may be junk past ld
+                        rxa = fmaf(q.x, x.x, rxa); rxb = fmaf(-q.y, x.y, rxb);
+                        rxa = fmaf(q.z, x.z, rxa); rxb = fmaf(-q.w, x.w, rxb);
+                        rya = fmaf(q.x, x.y, rya); ryb = fmaf(q.y, x.x, ryb);
+                        rya = fmaf(q.z, x.w, rya); ryb = fmaf(q.w, x.z, ryb);
+                        // conj(A) * v[a]
+                        yc[j].x = fmaf(q.x, xa.x, yc[j].x); yc[j].x = fmaf(q.y, xa.y, yc[j].x);
+                        yc[j].y = fmaf(q.x, xa.y, yc[j].y); yc[j].y = fmaf(-q.y, xa.x, yc[j].y);
+                        yc[j].z = fmaf(q.z, xa.x, yc[j].z); yc[j].z = fmaf(q.w, xa.y, yc[j].z);
+                        yc[j].w = fmaf(q.z, xa.y, yc[j].w); yc[j].w = fmaf(-q.w, xa.x, yc[j].w);
+                    }
+                    __syncwarp();
+                    const bool more = k + NST < K;
+                    const int st2 = gi % NST;   // == the stage just consumed
+                    if (more) ++gi;
+                    if (lane == 0 && more) {
+                        const int a2 = warp + NW * (k + NST);
+                        const int c_lo = (a2 + 1) & ~1;
+                        const unsigned bytes = (unsigned)(2 * ncol4 - c_lo) * 8u;
+                        mbar_expect_tx(mybar + st2, bytes);
+                        bulk_g2s(reinterpret_cast<float2*>(mystage + st2 * 256) + c_lo,
+                                 M + (size_t)a2 * ld + c_lo, bytes, mybar + st2);
+                    }
+                    // (re, im) reduced together: upper half-warp keeps im, lower re
+                    const float rx = rxa + rxb, ry = rya + ryb;
+                    const bool hi = lane & 16;
+                    float keep = hi ? ry : rx;
+                    keep += __shfl_xor_sync(0xffffffffu, hi ? rx : ry, 16);
+                    keep += __shfl_xor_sync(0xffffffffu, keep, 8);
+                    keep += __shfl_xor_sync(0xffffffffu, keep, 4);
+                    keep += __shfl_xor_sync(0xffffffffu, keep, 2);
+                    keep += __shfl_xor_sync(0xffffffffu, keep, 1);
+                    if (lane == 0) w[a].x += keep;
+                    if (lane == 16) w[a].y += keep;
+                }
+            };
+            run_rows(std::integral_constant<int, 0>{});
+            run_rows(std::integral_constant<int, 1>{});
+            run_rows(std::integral_constant<int, 2>{});
+            run_rows(std::integral_constant<int, 3>{});
+            run_rows(std::integral_constant<int, 4>{});
+            run_rows(std::integral_constant<int, 5>{});
+            run_rows(std::integral_constant<int, 6>{});
+            run_rows(std::integral_constant<int, 7>{});
+            __syncthreads();   // every warp is done with its stages
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(part + warp * 512 + 2 * (lane + 32 * j)) = yc[j];
+            __syncthreads();
+            for (int c = tid; c < 512; c += THREADS) {
+                float sx = 0.f, sy = 0.f;
+#pragma unroll
+                for (int kk = 0; kk < NW; ++kk) { sx += part[kk * 512 + c].x; sy += part[kk * 512 + c].y; }
+                if (c < ld) u[c] = make_float2(sx, sy);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+        } else {
         for (int cb = 0; cb < nchunk; ++cb) {
             float4 yc[8];
 #pragma unroll
@@ -466,6 +572,7 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
             }
             if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
+        }
         }
         // ---- alpha = Re <v, A v>
         double apart = 0.0;
