@@ -67,9 +67,9 @@ def eta_grid(n_total):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
 # `ncu --set full` capture of this same command (profiles/
 # r1_ncu_full_summary_final.csv); bench.py cannot run ncu on itself.
-NCU_TRAFFIC_BYTES = {"thth_eig": 19.33e9 + 0.004e9, "thth_build": 1.37e9 + 1.04e9,
-                     "cs_rows": 0.134e9 + 0.480e9, "cs_colA": 0.539e9 + 2.089e9,
-                     "cs_colB": 2.150e9 + 2.099e9}
+NCU_TRAFFIC_BYTES = {"thth_eig": 19.325e9 + 0.004e9, "thth_build": 1.368e9 + 1.042e9,
+                     "cs_rows": 0.134e9 + 0.164e9, "cs_colA": 0.215e9 + 0.800e9,
+                     "cs_colB": 0.858e9 + 0.810e9}
 
 
 def peak_hbm():
