@@ -705,7 +705,13 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
     }
     // batch so that the matrix slab stays <= ~3 GiB
     const size_t per = (size_t)ld * ld * sizeof(float2);
-    int batch = (int)((3ull << 30) / per);
+    // SB_SWEEP_SLAB_MB overrides the slab budget (tests use it to force batching)
+    unsigned long long slab = 3ull << 30;
+    if (const char* ev = getenv("SB_SWEEP_SLAB_MB")) {
+        const long mb = atol(ev);
+        if (mb > 0) slab = (unsigned long long)mb << 20;
+    }
+    int batch = (int)(slab / per);
     if (batch < 1) batch = 1;
     if (batch > neta) batch = neta;
     float2* d_M = (float2*)workspace(2, per * batch);

@@ -377,3 +377,16 @@ def test_column_limited_cs(sb):
     with pytest.raises(ValueError):
         lim.numpy()
     assert thth.needed_fd_columns(fd, np.linspace(-60, 60, 64)) is None
+
+
+def test_eta_sweep_batched_slab(sb, sample, monkeypatch):
+    """Force the theta-theta matrix slab to a few MB so the sweep runs in many
+    build+eigen batches; results must not change."""
+    g, CS = sample
+    ref, _ = sb.ththmod.eta_sweep(CS, g["tau"], g["fd"], g["etas"][::3], g["edges"],
+                                  return_info=True)
+    monkeypatch.setenv("SB_SWEEP_SLAB_MB", "5")      # 2 matrices of 2 MB per batch
+    got, info = sb.ththmod.eta_sweep(CS, g["tau"], g["fd"], g["etas"][::3], g["edges"],
+                                     return_info=True)
+    assert np.array_equal(got, ref)
+    assert (info["status"] == 0).all()
