@@ -191,6 +191,7 @@ __device__ __forceinline__ void sturm_multisect(const LanczosShared& S, int m,
 // res <= tol*theta or res^2 <= etol*theta*gap.  Called by warp 0.
 __device__ void lanczos_check(LanczosShared& S, int m, double tol, double etol) {
     const int lane = threadIdx.x & 31;
+    __syncwarp();   // every lane has read S.next_check before lane 0 rewrites it below
     const double bnew = S.beta[m];
     double gh = -DBL_MAX, gl = DBL_MAX;
     for (int i = lane; i < m; i += 32) {
@@ -239,6 +240,7 @@ __device__ void lanczos_check(LanczosShared& S, int m, double tol, double etol) 
         const double gap = theta - hi2;
         done = gap > 0.0 && res * res <= etol * fabs(theta) * gap;
     }
+    __syncwarp();   // all lanes are done reading S.lo / S.next_check
     if (lane == 0) {
         S.theta = theta;
         S.lo = lo;
