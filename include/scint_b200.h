@@ -105,6 +105,30 @@ int sb_thth_map(const sb_thth_geom* geom, double eta, int32_t hermitian,
                 void* thth, int32_t* tau_inv, int32_t* fd_inv, uint8_t* pnts,
                 uint8_t* th_pnts, int32_t* err, void* stream);
 
+/* "Thin" (arclet) theta-theta: replaces the eta loop of
+ * ththmod.single_search_thin (scintools/ththmod.py:589-627), i.e. neta calls of
+ * ththmod.singularvalue_calc (:496-512 -> two_curve_map :1557-1636 ->
+ * numpy.linalg.svd, S[0]).  geom describes the CS and the theta1 (column) grid
+ * with THIS path's conventions: th_cents = (edges1[1:]+edges1[:-1])/2 (not
+ * recentred), tau0 = tau[1], fd0 = fd[1] (ththmod.py:1602-1604), tau_absmax =
+ * tau.max(), fd_half unused.  th2_cents: device float64 [n_th2], centres of
+ * the arclet grid (rows).  eta1 / eta2: device float64 [neta] (main-arc and
+ * arclet curvature per trial).  center_cut: columns with |theta1| < center_cut
+ * are zeroed.  power=1 gathers |CS|^2 (incoherent thin search, :609).
+ * Outputs: svals float64 [neta] (NaN where numpy would raise), status (SB_ETA_*
+ * bits), n1_red / n2_red (cropped sizes), iters. */
+int sb_thin_sweep(const sb_thth_geom* geom, const double* th2_cents, int32_t n_th2,
+                  double center_cut, int32_t power, const double* eta1, const double* eta2,
+                  int32_t neta, double tol, int32_t max_iter, double* svals,
+                  int32_t* status, int32_t* n1_red, int32_t* n2_red, int32_t* iters,
+                  void* stream);
+
+/* Uncropped two-curvature map thth [n_th2][n_th] (float2) of
+ * ththmod.two_curve_map (:1585-1617) for one (eta1, eta2); err as sb_thth_map. */
+int sb_thin_map(const sb_thth_geom* geom, const double* th2_cents, int32_t n_th2,
+                int32_t power, double eta1, double eta2, void* thth, int32_t* err,
+                void* stream);
+
 /* ---- Dynspec 2-D FFT paths ---------------------------------------------- */
 
 /* Replaces the arithmetic of Dynspec.calc_sspec (scintools/dynspec.py:3664-3721):

@@ -131,6 +131,44 @@ def golden_thth(pkg):
                         f_MHz=arch["f_MHz"], t_s=arch["t_s"])
 
 
+def golden_thin(pkg):
+    """two_curve_map / singularvalue_calc / single_search_thin on the tutorial
+    chunk (reference run through the units shim)."""
+    u = sys.modules["astropy.units"]
+    thth = pkg.ththmod
+    g = np.load(os.path.join(GOLD, "thth_sample_64x150.npz"))
+    d0 = g["dspec2"] - g["dspec2"].mean()
+    npad = int(g["npad"])
+    pad = np.pad(d0, ((0, npad * d0.shape[0]), (0, npad * d0.shape[1])))
+    CS = np.fft.fftshift(np.fft.fft2(pad))
+    tau, fd = g["tau"] * u.us, g["fd"] * u.mHz
+    edges = np.linspace(-0.4, 0.4, 512)
+    arc = edges[np.abs(edges) < 0.25]
+    etas = np.linspace(20.0, 80.0, 25)
+    cut = 0.02
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sv = np.array([thth.singularvalue_calc(CS, tau, fd, e * u.s ** 3, edges * u.mHz,
+                                               e * u.s ** 3, arc * u.mHz, cut * u.mHz)
+                       for e in etas])
+        red, er1, er2 = thth.two_curve_map(CS, tau, fd, etas[8] * u.s ** 3, edges * u.mHz,
+                                           etas[8] * u.s ** 3, arc * u.mHz)
+        res = thth.single_search_thin([d0, g["freq"] * u.MHz, g["time"] * u.s,
+                                       etas * u.s ** 3, edges * u.mHz, None, False, 0.2,
+                                       npad, True, False, arc * u.mHz, cut * u.mHz])
+        res_inc = thth.single_search_thin([d0, g["freq"] * u.MHz, g["time"] * u.s,
+                                           etas[::3] * u.s ** 3, edges * u.mHz, None, False,
+                                           0.2, npad, False, False, arc * u.mHz, 0 * u.mHz])
+    np.savez_compressed(os.path.join(GOLD, "thth_thin_64x150.npz"), edges=edges, arc=arc,
+                        etas=etas, cut=cut, sv=sv, eta_map=etas[8],
+                        red=np.asarray(red).astype(np.complex64),
+                        er1=np.asarray(er1.value), er2=np.asarray(er2.value),
+                        ss_eigs=np.asarray(res[4]),
+                        ss_eta_fit=float(np.asarray(getattr(res[0], "value", res[0]))),
+                        inc_etas=etas[::3], inc_eigs=np.asarray(res_inc[4]))
+    print("thin: peak eta = %.2f" % etas[np.argmax(sv)])
+
+
 def golden_sim(pkg):
     """scint_sim.Simulation at 64^2 / 32x96, seeded (legacy MT19937)."""
     Sim = pkg.scint_sim.Simulation
@@ -165,6 +203,8 @@ def main():
         golden_sspec_acf(pkg)
     if not only or "thth" in only:
         golden_thth(pkg)
+    if not only or "thin" in only:
+        golden_thin(pkg)
     if not only or "sim" in only:
         golden_sim(pkg)
     for fn in sorted(os.listdir(GOLD)):

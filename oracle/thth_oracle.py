@@ -206,3 +206,74 @@ def eta_grid(eta_min, eta_max, fw, fref, fmean):
     neta = int(1 + (l1 - l0) / np.log10(1 + fw / 10))
     return np.logspace(np.log10(eta_min), np.log10(eta_max), neta) * \
         (fref / fmean) ** 2
+
+
+# ---------------------------------------------------------------------------
+# "thin" theta-theta: two-curvature map + top
+# singular value.  Follows ththmod.py:1557-1636 (two_curve_map), :496-512
+# (singularvalue_calc), :515-712 (single_search_thin).
+# ---------------------------------------------------------------------------
+def two_curve_map(CS, tau, fd, eta1, edges1, eta2, edges2):
+    """ththmod.py:1557-1636.  Returns (thth_red, edges_red1, edges_red2)."""
+    tau = np.asarray(tau, dtype=np.float64)
+    fd = np.asarray(fd, dtype=np.float64)
+    edges1 = np.asarray(edges1, dtype=np.float64)
+    edges2 = np.asarray(edges2, dtype=np.float64)
+    c1 = (edges1[1:] + edges1[:-1]) / 2
+    c2 = (edges2[1:] + edges2[:-1]) / 2
+    th1 = np.ones((c2.shape[0], c1.shape[0])) * c1
+    th2 = np.ones((c2.shape[0], c1.shape[0])) * c2[:, np.newaxis]
+    dtau = np.diff(tau).mean()
+    dfd = np.diff(fd).mean()
+    tau_inv = (((eta1 * th1 ** 2 - eta2 * th2 ** 2) - tau[1] + dtau / 2)
+               // dtau).astype(int)
+    fd_inv = (((th1 - th2) - fd[1] + dfd / 2) // dfd).astype(int)
+    thth = np.zeros(tau_inv.shape, dtype=complex)
+    pnts = (tau_inv > 0) * (tau_inv < tau.shape[0] - 1) * \
+        (fd_inv < fd.shape[0] - 1)
+    thth[pnts] = np.asarray(CS)[tau_inv[pnts], fd_inv[pnts]]
+    thth *= np.sqrt(np.abs(2 * eta1 * th1 - 2 * eta2 * th2))
+    th2_max = np.sqrt(tau.max() / eta2)
+    th1_max = np.sqrt(tau.max() / eta1)
+    p1 = np.abs(c1) < th1_max
+    p2 = np.abs(c2) < th2_max
+    er1 = np.zeros(p1.sum() + 1)
+    er1[:-1] = edges1[:-1][p1]
+    er1[-1] = edges1[1:][p1].max()
+    er2 = np.zeros(p2.sum() + 1)
+    er2[:-1] = edges2[:-1][p2]
+    er2[-1] = edges2[1:][p2].max()
+    return thth[p2, :][:, p1], er1, er2
+
+
+def singularvalue_calc(CS, tau, fd, eta, edges, etaArclet, edgesArclet,
+                       centerCut):
+    """ththmod.py:496-512: largest singular value of the two-curvature map."""
+    red, er1, _ = two_curve_map(CS, tau, fd, eta, edges, etaArclet, edgesArclet)
+    cents1 = (er1[1:] + er1[:-1]) / 2
+    red[:, np.abs(cents1) < centerCut] = 0
+    return np.linalg.svd(red, compute_uv=False)[0]
+
+
+def thin_sweep(CS, tau, fd, etas, edges, edgesArclet, centerCut):
+    """Eta loop of single_search_thin (ththmod.py:589-627): NaN on failure."""
+    out = np.zeros(len(etas))
+    for i, eta in enumerate(etas):
+        try:
+            out[i] = singularvalue_calc(CS, tau, fd, eta, edges, eta,
+                                        edgesArclet, centerCut)
+        except Exception:
+            out[i] = np.nan
+    return out
+
+
+def single_search_thin(dspec2, freq, time, etas, edges, edgesArclet, centerCut,
+                       fw=0.1, npad=3, coher=True):
+    """ththmod.py:515-712 without plotting (incoherent uses |CS|**2, :609)."""
+    fd = fft_axis(time, "mHz", npad)
+    tau = fft_axis(freq, "us", npad)
+    CS = conjugate_spectrum(dspec2, npad, None)
+    src = CS if coher else np.abs(CS) ** 2
+    eigs = thin_sweep(src, tau, fd, etas, edges, edgesArclet, centerCut)
+    eta_fit, eta_sig, _ = peak_fit(etas, eigs, fw)
+    return eta_fit, eta_sig, np.mean(freq), np.mean(time), eigs

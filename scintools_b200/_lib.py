@@ -60,6 +60,10 @@ _SIGS = {
                              vp, vp, vp, vp, vp]),
     "sb_thth_map": (c_int, [ctypes.POINTER(ThthGeom), c_dbl, c_int, vp, vp, vp,
                             vp, vp, vp, vp]),
+    "sb_thin_sweep": (c_int, [ctypes.POINTER(ThthGeom), vp, c_int, c_dbl, c_int, vp, vp,
+                              c_int, c_dbl, c_int, vp, vp, vp, vp, vp, vp]),
+    "sb_thin_map": (c_int, [ctypes.POINTER(ThthGeom), vp, c_int, c_int, c_dbl, c_dbl, vp,
+                            vp, vp]),
     "sb_sspec_f32": (c_int, [vp, c_int, c_int, vp, vp, c_dbl, c_dbl, c_int,
                              c_int, c_int, vp, vp, vp, vp]),
     "sb_acf_f32": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp]),

@@ -125,6 +125,20 @@ __global__ void convert_kernel(const A* __restrict__ a, B* __restrict__ b, long 
         b[i] = (B)a[i];
 }
 
+struct ThinGeom {
+    ThthGeom g;
+    const double* th2;
+    int n2;
+    double tau_max;
+    double center_cut;
+    int power;
+};
+int thin_sweep(const ThinGeom& t, const double* d_eta1, const double* d_eta2, int neta,
+               double tol, int max_iter, double* d_sv, int* d_status, int* d_n1, int* d_n2,
+               int* d_iters, cudaStream_t st);
+int thin_map(const ThinGeom& t, double e1, double e2, float2* d_out, int* d_err,
+             cudaStream_t st);
+
 static int to_geom(const sb_thth_geom* in, ThthGeom* g) {
     SB_ARG(in != nullptr);
     SB_ARG(in->ntau > 0 && in->nfd > 0);
@@ -225,6 +239,43 @@ int sb_thth_map(const sb_thth_geom* geom, double eta, int32_t hermitian,
     SB_ARG(!wants_map || (err != nullptr && geom->cs != nullptr));
     return sb::thth_map(g, eta, hermitian, (float2*)thth, tau_inv, fd_inv,
                         pnts, th_pnts, err, (cudaStream_t)stream);
+}
+
+static int to_thin(const sb_thth_geom* geom, const double* th2, int32_t n2, double center_cut,
+                   int32_t power, sb::ThinGeom* t) {
+    int rc = sb::to_geom(geom, &t->g);
+    if (rc) return rc;
+    SB_ARG(geom->cs != nullptr && th2 != nullptr && n2 > 0);
+    t->th2 = th2;
+    t->n2 = n2;
+    t->tau_max = geom->tau_absmax;     // carries tau.max() for the thin map
+    t->center_cut = center_cut;
+    t->power = power;
+    return SB_OK;
+}
+
+int sb_thin_sweep(const sb_thth_geom* geom, const double* th2_cents, int32_t n_th2,
+                  double center_cut, int32_t power, const double* eta1, const double* eta2,
+                  int32_t neta, double tol, int32_t max_iter, double* svals,
+                  int32_t* status, int32_t* n1_red, int32_t* n2_red, int32_t* iters,
+                  void* stream) {
+    sb::ThinGeom t;
+    int rc = to_thin(geom, th2_cents, n_th2, center_cut, power, &t);
+    if (rc) return rc;
+    SB_ARG(neta >= 0 && eta1 && eta2 && svals && status && n1_red && n2_red && iters);
+    if (!(tol > 0)) tol = 2e-5;
+    return sb::thin_sweep(t, eta1, eta2, neta, tol, max_iter, svals, status, n1_red, n2_red,
+                          iters, (cudaStream_t)stream);
+}
+
+int sb_thin_map(const sb_thth_geom* geom, const double* th2_cents, int32_t n_th2,
+                int32_t power, double eta1, double eta2, void* thth, int32_t* err,
+                void* stream) {
+    sb::ThinGeom t;
+    int rc = to_thin(geom, th2_cents, n_th2, 0.0, power, &t);
+    if (rc) return rc;
+    SB_ARG(thth && err);
+    return sb::thin_map(t, eta1, eta2, (float2*)thth, err, (cudaStream_t)stream);
 }
 
 int sb_sspec_f32(const float* dyn, int32_t nf, int32_t nt, const float* win_t,

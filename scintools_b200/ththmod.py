@@ -376,6 +376,142 @@ def single_search(params):
             U.wrap(time_v.mean(), "s", like=time), eigs)
 
 
+# ---------------------------------------------------------------------------
+# "thin" (arclet) theta-theta: two-curvature map + largest singular value
+# ---------------------------------------------------------------------------
+class _ThinGeom(_Geom):
+    """sb_thth_geom with the conventions of two_curve_map (ththmod.py:1585-
+    1617): plain bin centres, offsets tau[1] / fd[1], tau.max()."""
+
+    def __init__(self, cs, tau, fd, edges1, edges2):
+        tauv = U.value(tau, "us")
+        fdv = U.value(fd, "mHz")
+        e1 = np.asarray(U.value(edges1, "mHz"), dtype=np.float64)
+        e2 = np.asarray(U.value(edges2, "mHz"), dtype=np.float64)
+        if cs.shape != (tauv.shape[0], fdv.shape[0]):
+            raise ValueError("CS shape does not match (len(tau), len(fd))")
+        self.cs = cs
+        self.th = np.ascontiguousarray((e1[1:] + e1[:-1]) / 2)
+        self.th2 = np.ascontiguousarray((e2[1:] + e2[:-1]) / 2)
+        self.th_dev = D.upload(self.th)
+        self.th2_dev = D.upload(self.th2)
+        g = _lib.ThthGeom()
+        g.cs = cs.t.data_ptr()
+        g.ntau, g.nfd = tauv.shape[0], fdv.shape[0]
+        g.tau0 = float(tauv[1])
+        g.dtau = float(np.diff(tauv).mean())
+        g.tau_absmax = float(tauv.max())
+        g.fd0 = float(fdv[1])
+        g.dfd = float(np.diff(fdv).mean())
+        g.fd_half = 0.0
+        g.th_cents = self.th_dev.data_ptr()
+        g.th_cents_host = self.th.ctypes.data
+        g.n_th = self.th.shape[0]
+        g.coherent = 1
+        g.cs_half = 1 if cs.half else 0
+        g.cs_pitch = cs.pitch
+        self.g = g
+        if cs.half and cs.ncols_valid < fdv.shape[0] // 2 + 1:
+            raise ValueError("thin theta-theta needs a DeviceCS with all fd columns")
+
+
+def thin_sweep(CS, tau, fd, etas, edges, edgesArclet, centerCut, etasArclet=None,
+               power=False, tol=DEFAULT_TOL, max_iter=0, return_info=False):
+    """Largest singular value of the two-curvature theta-theta map for every
+    curvature (the eta loop of single_search_thin, ththmod.py:589-627; one
+    singularvalue_calc per eta, :496-512).  NaN where numpy would raise."""
+    import torch
+    cs = _as_device_cs(CS)
+    geom = _ThinGeom(cs, tau, fd, edges, edgesArclet)
+    e1 = np.ascontiguousarray(np.atleast_1d(U.value(etas, "s3")))
+    e2 = e1 if etasArclet is None else \
+        np.ascontiguousarray(np.atleast_1d(U.value(etasArclet, "s3")))
+    neta = e1.shape[0]
+    d1, d2 = D.upload(e1), D.upload(e2)
+    sv = D.empty((neta,), torch.float64)
+    aux = [D.empty((neta,), torch.int32) for _ in range(4)]
+    _lib.check(_lib.lib.sb_thin_sweep(
+        geom.ref, geom.th2_dev.data_ptr(), geom.th2.shape[0],
+        float(U.value(centerCut, "mHz")), 1 if power else 0, d1.data_ptr(),
+        d2.data_ptr(), neta, tol, max_iter, sv.data_ptr(), aux[0].data_ptr(),
+        aux[1].data_ptr(), aux[2].data_ptr(), aux[3].data_ptr(), D.stream_ptr()))
+    out = sv.cpu().numpy()
+    if return_info:
+        return out, dict(status=aux[0].cpu().numpy(), n1=aux[1].cpu().numpy(),
+                         n2=aux[2].cpu().numpy(), iters=aux[3].cpu().numpy())
+    return out
+
+
+def two_curve_map(CS, tau, fd, eta1, edges1, eta2, edges2):
+    """Two-curvature theta-theta map (ththmod.py:1557-1636).
+    Returns (thth_red, edges_red1, edges_red2)."""
+    import torch
+    cs = _as_device_cs(CS)
+    geom = _ThinGeom(cs, tau, fd, edges1, edges2)
+    e1v, e2v = float(U.value(eta1, "s3")), float(U.value(eta2, "s3"))
+    n1, n2 = geom.th.shape[0], geom.th2.shape[0]
+    out = D.empty((n2, n1, 2), torch.float32)
+    err = D.zeros((1,), torch.int32)
+    _lib.check(_lib.lib.sb_thin_map(geom.ref, geom.th2_dev.data_ptr(), n2, 0, e1v, e2v,
+                                    out.data_ptr(), err.data_ptr(), D.stream_ptr()))
+    if int(err.cpu()[0]) & 1:
+        raise IndexError("index out of bounds (fd_inv < -nfd), ththmod.py:1614")
+    a = out.cpu().numpy()
+    thth = a[..., 0].astype(np.float64) + 1j * a[..., 1].astype(np.float64)
+    tauv = U.value(tau, "us")
+    ed1 = np.asarray(U.value(edges1, "mHz"), dtype=np.float64)
+    ed2 = np.asarray(U.value(edges2, "mHz"), dtype=np.float64)
+    p1 = np.abs(geom.th) < np.sqrt(tauv.max() / e1v)
+    p2 = np.abs(geom.th2) < np.sqrt(tauv.max() / e2v)
+    er1 = np.zeros(p1.sum() + 1)
+    er1[:-1] = ed1[:-1][p1]
+    er1[-1] = ed1[1:][p1].max()
+    er2 = np.zeros(p2.sum() + 1)
+    er2[:-1] = ed2[:-1][p2]
+    er2[-1] = ed2[1:][p2].max()
+    return (thth[p2, :][:, p1], U.wrap(er1, "mHz", like=edges1),
+            U.wrap(er2, "mHz", like=edges2))
+
+
+def singularvalue_calc(CS, tau, fd, eta, edges, etaArclet, edgesArclet, centerCut):
+    """ththmod.py:496-512."""
+    sv, info = thin_sweep(CS, tau, fd, np.array([float(U.value(eta, "s3"))]), edges,
+                          edgesArclet, centerCut,
+                          etasArclet=np.array([float(U.value(etaArclet, "s3"))]),
+                          return_info=True)
+    if int(info["status"][0]) & 1:
+        raise IndexError("theta-theta point maps outside the conjugate spectrum")
+    if not np.isfinite(sv[0]):
+        raise np.linalg.LinAlgError("SVD did not converge")
+    return float(sv[0])
+
+
+def single_search_thin(params):
+    """Thin-arclet curvature search for one chunk (ththmod.py:515-712).
+    ``params`` is the reference's 13-element list
+    [dspec2, freq, time, etas, edges, name, plot, fw, npad, coher, verbose,
+    edgesArclet, centerCut]."""
+    (dspec2, freq, time, etas, edges, name, plot, fw, npad, coher, verbose,
+     edgesArclet, centerCut) = params
+    if plot:
+        raise NotImplementedError("plotting is outside the B200 hot path")
+    time_v = U.value(time, "s")
+    freq_v = U.value(freq, "MHz")
+    etas_v = U.value(etas, "s3")
+    fd = U.value(fft_axis(time_v, "mHz", npad), "mHz")
+    tau = U.value(fft_axis(freq_v, "us", npad), "us")
+    cs = conjugate_spectrum(dspec2, npad, None)
+    eigs = thin_sweep(cs, tau, fd, etas_v, edges, edgesArclet, centerCut,
+                      power=not coher)
+    eta_fit, eta_sig, _ = peak_fit(etas_v, eigs, fw)
+    if verbose:
+        print("Chunk completed (eta = %s +- %s at %s)" %
+              (eta_fit, eta_sig, freq_v.mean()), flush=True)
+    return (U.wrap(eta_fit, "s3", like=etas), U.wrap(eta_sig, "s3", like=etas),
+            U.wrap(freq_v.mean(), "MHz", like=freq),
+            U.wrap(time_v.mean(), "s", like=time), eigs)
+
+
 def min_edges(fd_lim, fd, tau, eta, factor=2):
     """Minimum edges array that oversamples the CS (ththmod.py:1671-1705)."""
     fd_lim_v = float(U.value(fd_lim, "mHz"))

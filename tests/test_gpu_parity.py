@@ -390,3 +390,53 @@ def test_eta_sweep_batched_slab(sb, sample, monkeypatch):
                                      return_info=True)
     assert np.array_equal(got, ref)
     assert (info["status"] == 0).all()
+
+
+def test_thin_thetatheta(sb, golden_dir):
+    """two_curve_map / singularvalue_calc / single_search_thin against the
+    reference's own outputs (tutorial chunk, run through the units shim)."""
+    g = np.load(os.path.join(golden_dir, "thth_sample_64x150.npz"))
+    t = np.load(os.path.join(golden_dir, "thth_thin_64x150.npz"))
+    thth = sb.ththmod
+    d0 = g["dspec2"] - g["dspec2"].mean()
+    CS = TO.conjugate_spectrum(d0, int(g["npad"]), 0.0)
+    eta = float(t["eta_map"])
+    red, er1, er2 = thth.two_curve_map(CS, g["tau"], g["fd"], eta, t["edges"], eta, t["arc"])
+    assert red.shape == t["red"].shape
+    assert np.array_equal(er1, t["er1"]) and np.array_equal(er2, t["er2"])
+    assert maxrel(red, t["red"].astype(np.complex128)) < 2e-6
+    assert np.array_equal(red == 0, t["red"] == 0)
+    sv, info = thth.thin_sweep(CS, g["tau"], g["fd"], t["etas"], t["edges"], t["arc"],
+                               float(t["cut"]), return_info=True)
+    assert (np.abs(sv - t["sv"]) / t["sv"]).max() < RTOL
+    assert (info["status"] == 0).all()
+    assert thth.singularvalue_calc(CS, g["tau"], g["fd"], t["etas"][5], t["edges"],
+                                   t["etas"][5], t["arc"], float(t["cut"])) == \
+        pytest.approx(t["sv"][5], rel=RTOL)
+    arc, cut = t["arc"], float(t["cut"])
+    res = thth.single_search_thin([d0, g["freq"], g["time"], t["etas"], t["edges"], None,
+                                   False, 0.2, int(g["npad"]), True, False, arc, cut])
+    assert (np.abs(res[4] - t["ss_eigs"]) / t["ss_eigs"]).max() < RTOL
+    assert res[0] == pytest.approx(float(t["ss_eta_fit"]), rel=1e-4)
+    inc = thth.single_search_thin([d0, g["freq"], g["time"], t["inc_etas"], t["edges"], None,
+                                   False, 0.2, int(g["npad"]), False, False, arc, 0.0])
+    assert (np.abs(inc[4] - t["inc_eigs"]) / t["inc_eigs"]).max() < RTOL
+
+
+def test_thin_random_vs_oracle(sb):
+    rng = np.random.default_rng(55)
+    nf, nt, npad = 32, 128, 1
+    d = rng.normal(size=(nf, nt))
+    d -= d.mean()
+    t = np.arange(nt) * 10.0
+    f = 1400 + 0.2 * np.arange(nf)
+    fd = TO.fft_axis(t, "mHz", npad)
+    tau = TO.fft_axis(f, "us", npad)
+    cs = sb.ththmod.conjugate_spectrum(d, npad, 0.0)
+    CS = cs.numpy()
+    edges = np.linspace(-20, 20, 90)
+    arc = edges[np.abs(edges) < 11]
+    etas = np.linspace(0.002, 0.02, 9)
+    got = sb.ththmod.thin_sweep(cs, tau, fd, etas, edges, arc, 1.5)
+    ref = TO.thin_sweep(CS, tau, fd, etas, edges, arc, 1.5)
+    assert (np.abs(got - ref) / ref).max() < RTOL
