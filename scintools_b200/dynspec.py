@@ -249,10 +249,10 @@ class Dynspec:
         """Set up the theta-theta search (reference dynspec.py:1348-1537).
 
         Recognises cwf, cwt, fref, eta_min, eta_max, nedge, edges_lim, tau_lim,
-        tau_mask.  'thin' (two-curvature SVD variant) is outside the path."""
-        fitting_procs = ['standard', 'incoherent']
+        tau_mask and, for fitting_proc='thin', arclet_lim and center_cut."""
+        fitting_procs = ['standard', 'thin', 'incoherent']
         assert fitting_proc in fitting_procs, \
-            f'fitting_proc must be one of {fitting_procs} on the B200 path'
+            f'fitting_proc must be one of {fitting_procs}'
         self.thetatheta_proc = fitting_proc
         self.npad = npad
         self.fw = fw
@@ -303,7 +303,10 @@ class Dynspec:
         l1 = np.log10(self.eta_max)
         self.neta = int(1 + (l1 - l0) / np.log10(1 + self.fw / 10))
 
-        fd_cut = (fd.max() / 2) * (self.fref / np.max(self.freqs))
+        if self.thetatheta_proc == 'thin':
+            fd_cut = fd.max() * (self.fref / np.max(self.freqs))
+        else:
+            fd_cut = (fd.max() / 2) * (self.fref / np.max(self.freqs))
         if 'edges_lim' in kwargs:
             edges_lim = min((float(U.value(kwargs['edges_lim'], "mHz")), fd_cut))
         else:
@@ -318,6 +321,11 @@ class Dynspec:
                 edges_lim, fd, tau,
                 self.eta_max * (self.fref / np.min(self.freqs)), 2), "mHz") \
                 * (np.min(self.freqs) / self.fref)
+        if self.thetatheta_proc == 'thin':
+            self.arclet_lim = float(U.value(kwargs['arclet_lim'], "mHz")) \
+                if 'arclet_lim' in kwargs else float(edges_lim)
+            self.center_cut = float(U.value(kwargs['center_cut'], "mHz")) \
+                if 'center_cut' in kwargs else 0.0
         self.thth_tau_mask = float(U.value(kwargs['tau_mask'], "us")) \
             if 'tau_mask' in kwargs else 0.0
         if verbose:
@@ -356,11 +364,19 @@ class Dynspec:
         dspec2 -= np.nanmean(dspec2)
         etas = self._chunk_etas(freq2.mean())
         edges = self.edges * (freq2.mean() / self.fref)
-        cs = thth.conjugate_spectrum(np.nan_to_num(dspec2), self.npad, 0.0,
-                                     tau, self.thth_tau_mask,
-                                     ncols_keep=thth.needed_fd_columns(fd, edges))
-        eigs = thth.eta_sweep(cs, tau, fd, etas, edges,
-                              self.thetatheta_proc == 'standard')
+        if self.thetatheta_proc == 'thin':
+            # dynspec.py:1593-1600: one singularvalue_calc per curvature
+            cs = thth.conjugate_spectrum(np.nan_to_num(dspec2), self.npad, 0.0,
+                                         tau, self.thth_tau_mask)
+            eigs = thth.thin_sweep(cs, tau, fd, etas, edges,
+                                   edges[np.abs(edges) < self.arclet_lim],
+                                   self.center_cut)
+        else:
+            cs = thth.conjugate_spectrum(
+                np.nan_to_num(dspec2), self.npad, 0.0, tau, self.thth_tau_mask,
+                ncols_keep=thth.needed_fd_columns(fd, edges))
+            eigs = thth.eta_sweep(cs, tau, fd, etas, edges,
+                                  self.thetatheta_proc == 'standard')
         if not np.all(np.isfinite(eigs)) and verbose:
             print("some curvatures failed (NaN)")
         eta_fit, eta_sig, popt = thth.peak_fit(etas, eigs, self.fw)
@@ -399,11 +415,17 @@ class Dynspec:
                 dspec2 = np.copy(self.dyn[fs, ts]).astype(np.float64)
                 dspec2 -= np.nanmean(dspec2)
                 dspec2 = np.nan_to_num(dspec2)
-                params = [dspec2, freq2, time2, etas,
-                          self.edges * (freq2.mean() / self.fref), None, False,
-                          self.fw, self.npad, coher, self.thth_tau_mask,
-                          verbose]
-                res = thth.single_search(params)
+                scale = freq2.mean() / self.fref
+                params = [dspec2, freq2, time2, etas, self.edges * scale, None,
+                          False, self.fw, self.npad, coher]
+                if self.thetatheta_proc == 'thin':
+                    params += [verbose,
+                               self.edges[np.abs(self.edges) < self.arclet_lim]
+                               * scale, self.center_cut]
+                    res = thth.single_search_thin(params)
+                else:
+                    params += [self.thth_tau_mask, verbose]
+                    res = thth.single_search(params)
                 self.eta_evo[cf, ct] = U.value(res[0], "s3")
                 self.eta_evo_err[cf, ct] = U.value(res[1], "s3")
                 self.t0s[ct] = time2.mean()

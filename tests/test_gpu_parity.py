@@ -440,3 +440,33 @@ def test_thin_random_vs_oracle(sb):
     got = sb.ththmod.thin_sweep(cs, tau, fd, etas, edges, arc, 1.5)
     ref = TO.thin_sweep(CS, tau, fd, etas, edges, arc, 1.5)
     assert (np.abs(got - ref) / ref).max() < RTOL
+
+
+def test_dynspec_thetatheta_thin(sb):
+    """fitting_proc='thin' through Dynspec (dynspec.py:1480-1515, 1593-1600,
+    1701-1708) against the oracle's thin sweep."""
+    rng = np.random.default_rng(22)
+    nf, nt = 64, 256
+    t = np.arange(nt) * 20.0
+    f = 1400.0 + np.arange(nf) * 0.05
+    fdk = rng.uniform(-6, 6, 24)
+    ak = (rng.normal(size=24) + 1j * rng.normal(size=24)) * np.exp(-(fdk / 3) ** 2)
+    E = sum(a * np.exp(2j * np.pi * (k * 1e-3 * t[None, :] - 30.0 * k ** 2 * (f[:, None] - f[0])))
+            for a, k in zip(ak, fdk))
+    dyn = np.abs(E) ** 2 + rng.normal(0, 0.02, (nf, nt))
+    ds = sb.Dynspec(dyn=sb.BasicDyn(dyn, times=t, freqs=f, dt=20.0, df=0.05), verbose=False)
+    ds.prep_thetatheta(cwt=128, eta_min=15.0, eta_max=60.0, nedge=128, edges_lim=8.0,
+                       fw=0.2, npad=3, fitting_proc='thin', arclet_lim=3.0, center_cut=0.3)
+    assert (ds.arclet_lim, ds.center_cut) == (3.0, 0.3)
+    etas, eigs, popt = ds.thetatheta_single(cf=0, ct=1)
+    ts = slice(128, 256)
+    d2 = dyn[:, ts] - dyn[:, ts].mean()
+    CS = TO.conjugate_spectrum(d2, 3, 0.0)
+    tau, fd = TO.fft_axis(f, "us", 3), TO.fft_axis(t[ts], "mHz", 3)
+    edges = ds.edges * (f.mean() / ds.fref)
+    arc = edges[np.abs(edges) < 3.0]
+    ref = TO.thin_sweep(CS, tau, fd, etas, edges, arc, 0.3)
+    assert (np.abs(eigs - ref) / ref).max() < RTOL
+    ds.fit_thetatheta()
+    r = TO.peak_fit(etas, ref, ds.fw)
+    assert ds.eta_evo[0, 1] == pytest.approx(r[0], rel=1e-3)
