@@ -15,8 +15,14 @@
 
 #include "lanczos.cuh"
 #include "thth.cuh"
+#include "tma.cuh"
 
 namespace sb {
+
+// eig_cluster.cu: on-chip (cluster shared memory) solver for ld <= 512
+int eig_cluster_launch(const float2* d_M, int ld, int n_max, const int* d_nred, int e0,
+                       int nb, double* d_eigs, int* d_status, int* d_iters, double tol,
+                       double etol, int max_iter, cudaStream_t st);
 
 // status codes per eta (also in include/scint_b200.h)
 enum { ST_OK = 0, ST_INDEX_ERROR = 1, ST_ZERO_START = 2, ST_TOO_SMALL = 4,
@@ -134,33 +140,6 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
 // (scipy eigsh(..., k=1, which="LA"), ththmod.py:398-401), start vector =
 // row n//2.  No re-orthogonalisation: only the top Ritz value is wanted.
 // --------------------------------------------------------------------------
-// ---- TMA (bulk async copy) helpers ----------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) {
-    return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                 ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
-                                         unsigned long long* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
-    unsigned ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-
 // One CTA per eta.  The matrix is stored as its strict upper triangle; a warp
 // owns rows a = warp, warp+NW, ... and for every stored element A[a][b] adds
 //   A[a][b] * v[b]        to the row sum of a   (warp-shuffle reduction), and
@@ -625,7 +604,12 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
         prof_end(PROF_THTH_BUILD, st);
         SB_LAUNCH_CHECK();
         prof_begin(PROF_THTH_EIG, st);
-        if (use_tma)
+        const int rc = eig_cluster_launch(d_M, ld, g.n, d_nred, e0, nb, d_eigs, d_status,
+                                          d_iters, tol, 2e-7, max_iter, st);
+        if (rc < 0) return rc;
+        if (rc > 0) {
+            // the triangle stayed in cluster shared memory for the whole solve
+        } else if (use_tma)
             thth_eig_kernel<TT, true, TS><<<nb, TT, smem, st>>>(
                 d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter);
         else

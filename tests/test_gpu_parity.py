@@ -470,3 +470,29 @@ def test_dynspec_thetatheta_thin(sb):
     ds.fit_thetatheta()
     r = TO.peak_fit(etas, ref, ds.fw)
     assert ds.eta_evo[0, 1] == pytest.approx(r[0], rel=1e-3)
+
+
+@pytest.mark.parametrize("cluster", ["0", "1", "2", "3", "5", "6", "8"])
+def test_eta_sweep_solver_variants(sb, sample, monkeypatch, cluster):
+    """The on-chip cluster solver (eig_cluster.cu) at every cluster size and
+    the streaming solver (SB_EIG_CLUSTER=0) agree with the reference eigenvalues;
+    failure modes are reported identically."""
+    g, CS = sample
+    monkeypatch.setenv("SB_EIG_CLUSTER", cluster)
+    eigs, info = sb.ththmod.eta_sweep(CS, g["tau"], g["fd"], g["etas"], g["edges"],
+                                      return_info=True)
+    rel = np.abs(eigs - g["eigs"]) / g["eigs"]
+    assert rel.max() < RTOL, rel.max()
+    assert (info["status"] == 0).all()
+    assert info["iters"].max() < 64
+    # incoherent + masked rows, and a sweep with failing curvatures
+    CSm = CS.copy()
+    CSm[np.abs(g["tau"]) < 0.5] = 0
+    inc = sb.ththmod.eta_sweep(CSm, g["tau"], g["fd"], g["inc_etas"], g["edges"], coher=False)
+    assert (np.abs(inc - g["inc_eigs"]) / g["inc_eigs"]).max() < RTOL
+    wide = np.linspace(-6.0, 6.0, 64)
+    r2 = TO.eta_sweep(CS, g["tau"], g["fd"], np.array([20.0, 50.0]), wide)
+    e2 = sb.ththmod.eta_sweep(CS, g["tau"], g["fd"], np.array([20.0, 50.0]), wide)
+    assert np.array_equal(np.isnan(e2), np.isnan(r2))
+    z = sb.ththmod.eta_sweep(np.zeros_like(CS), g["tau"], g["fd"], np.array([40.0]), g["edges"])
+    assert np.isnan(z).all()
