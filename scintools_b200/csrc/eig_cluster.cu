@@ -253,18 +253,29 @@ thth_eig_cluster_kernel(const float2* __restrict__ Mbase, int ld,
                         const float2 xa1 = v[a1];
                         const float2 xa2 = a2 >= 0 ? v[a2] : make_float2(0.f, 0.f);
                         const float4* row1 = slice + tb.y;
-                        const float4* row2 = slice + tb.w;
+                        const float4* row2 = slice + (a2 >= 0 ? tb.w : tb.y);   // no 2nd row: xa2 = 0
                         float r1xa = 0.f, r1xb = 0.f, r1ya = 0.f, r1yb = 0.f;
                         float r2xa = 0.f, r2xb = 0.f, r2ya = 0.f, r2yb = 0.f;
 #pragma unroll
                         for (int j = JS; j < 8; ++j) {
                             const int c4 = lane + 32 * j;
-                            bool ok1 = (j > JS) || (c4 >= f1);
-                            bool ok2 = c4 >= f2;
-                            if (tail) { ok1 = ok1 && (c4 < ncol4); ok2 = ok2 && (c4 < ncol4); }
-                            float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f), q2 = q1;
-                            if (ok1) q1 = row1[c4];
-                            if (ok2) q2 = row2[c4];
+                            // unconditional loads (the addresses left of the diagonal /
+                            // right of the matrix are inside the CTA's shared memory);
+                            // masks only where a boundary can fall: the diagonal of row 1
+                            // in group JS, of row 2 (<= 2C-1 columns later) in JS, JS+1
+                            float4 q1 = row1[c4], q2 = row2[c4];
+                            if (j == JS || tail) {
+                                bool ok1 = c4 >= f1;
+                                if (tail) ok1 = ok1 && (c4 < ncol4);
+                                q1.x = ok1 ? q1.x : 0.f; q1.y = ok1 ? q1.y : 0.f;
+                                q1.z = ok1 ? q1.z : 0.f; q1.w = ok1 ? q1.w : 0.f;
+                            }
+                            if (j <= JS + 1 || tail) {
+                                bool ok2 = c4 >= f2;
+                                if (tail) ok2 = ok2 && (c4 < ncol4);
+                                q2.x = ok2 ? q2.x : 0.f; q2.y = ok2 ? q2.y : 0.f;
+                                q2.z = ok2 ? q2.z : 0.f; q2.w = ok2 ? q2.w : 0.f;
+                            }
                             const float4 x = xv[j];
                             r1xa = fmaf(q1.x, x.x, r1xa); r1xb = fmaf(-q1.y, x.y, r1xb);
                             r1xa = fmaf(q1.z, x.z, r1xa); r1xb = fmaf(-q1.w, x.w, r1xb);
@@ -448,7 +459,9 @@ static size_t cluster_smem(int n, int C, int* npair_max) {
         nq_max = nq > nq_max ? nq : nq_max;
     }
     *npair_max = (nq_max + 1) / 2;
-    return EC_FIXED_BYTES + (size_t)*npair_max * sizeof(int4) + worst;
+    // + slack: a cropped matrix (ncol4 < 256) is read, masked, up to column 255
+    return EC_FIXED_BYTES + (size_t)*npair_max * sizeof(int4) + worst +
+           (size_t)(EC_COL4 - ncol4) * 16;
 }
 static int pick_cluster(int n, size_t smem_max, size_t* smem_out, int* npair_max) {
     for (int C = 1; C <= 8; ++C) {
