@@ -150,12 +150,12 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
 // (mbarrier complete_tx), so ~NST row fetches per warp are in flight while the
 // warp does FMAs.  TMA = false: direct 16-byte loads, any ld, columns in
 // chunks of 512.
-template <int THREADS, bool TMA, int NST>
+template <int THREADS, bool TMA, int NST, bool FAST = false>
 __global__ void __launch_bounds__(THREADS)
 thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
                 const int* __restrict__ nred, int eta0,
                 double* __restrict__ eigs, int* __restrict__ status,
-                int* __restrict__ iters, double tol, double etol, int max_iter) {
+                int* __restrict__ iters, double tol, double etol, int max_iter, int nb) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NW = THREADS / 32;
     LanczosShared& S = *reinterpret_cast<LanczosShared*>(smem_raw);
@@ -170,27 +170,31 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
         reinterpret_cast<unsigned char*>(stages) +
         (TMA ? (size_t)NW * NST * 4096 : (size_t)NW * 4096));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int e = blockIdx.x;
+    if (TMA) {
+        if (tid == 0) {
+            for (int i = 0; i < NW * NST; ++i) mbar_init(mbar + i, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    unsigned gi = 0, gc = 0;             // ring producer / consumer counters
+    // grid-stride over the curvatures: gridDim.x == nb (one CTA per eta) or a
+    // persistent grid sized so that the matrices in flight stay L2-resident
+    for (int e = blockIdx.x; e < nb; e += gridDim.x) {
+    __syncthreads();                     // the previous eta is done with the shared buffers
     const int n = nred[eta0 + e];
     const float2* M = Mbase + (size_t)e * ld * ld;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
     if (status[eta0 + e] & ST_INDEX_ERROR) {
         if (tid == 0) { eigs[eta0 + e] = qnan; iters[eta0 + e] = 0; }
-        return;
+        continue;
     }
     if (n < 3) {
         if (tid == 0) {
             eigs[eta0 + e] = qnan; iters[eta0 + e] = 0;
             status[eta0 + e] |= ST_TOO_SMALL;
         }
-        return;
-    }
-    if (TMA) {
-        if (tid == 0) {
-            for (int i = 0; i < NW * NST; ++i) mbar_init(mbar + i, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
+        continue;
     }
     // v0 = row n//2 of the Hermitian matrix (ththmod.py:398-399)
     const int h = n / 2;
@@ -205,7 +209,10 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
     }
     part0 = warp_sum(part0);
     if (lane == 0) S.red[0][warp] = part0;
-    if (tid == 0) { S.done = 0; S.lo = 0.0; S.theta = 0.0; S.next_check = 1; S.beta2[0] = 0.0; }
+    if (tid == 0) {
+        S.done = 0; S.lo = 0.0; S.theta = 0.0; S.res = 0.0; S.m_lo2 = 0; S.lo2 = 0.0;
+        S.next_check = 1; S.beta2[0] = 0.0;
+    }
     __syncthreads();
     double nrm2 = 0.0;
     for (int k = 0; k < NW; ++k) nrm2 += S.red[0][k];
@@ -214,7 +221,7 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
             eigs[eta0 + e] = qnan; iters[eta0 + e] = 0;
             status[eta0 + e] |= ST_ZERO_START;
         }
-        return;
+        continue;
     }
     {
         float s = (float)(1.0 / sqrt(nrm2));
@@ -224,7 +231,6 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
 
     const int ncol4 = (n + 1) >> 1;      // float4 = two complex columns
     const int nchunk = (n + 511) / 512;  // column chunks of 512 (1 when TMA)
-    unsigned gi = 0, gc = 0;             // ring producer / consumer counters
     float4* mystage = stages + (size_t)warp * NST * 256;
     unsigned long long* mybar = mbar + warp * NST;
     float beta_prev = 0.f;
@@ -472,7 +478,10 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
         if (tid == 0) { S.alpha[it] = alpha; S.beta[m] = beta; S.beta2[m] = b2; }
         __syncthreads();
         const bool last = (it + 1 == max_iter);
-        if (warp == 0 && (m >= S.next_check || last || !(beta > 0.0))) lanczos_check(S, m, tol, etol);
+        if (warp == 0 && (m >= S.next_check || last || !(beta > 0.0))) {
+            if (FAST) lanczos_check_fast(S, m, tol, etol);
+            else lanczos_check(S, m, tol, etol);
+        }
         __syncthreads();
         if (S.done || !isfinite(alpha)) break;
         // ---- rotate: vp = v, v = w / beta
@@ -490,6 +499,7 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
         iters[eta0 + e] = m;
         if (!S.done) status[eta0 + e] |= ST_NOT_CONVERGED;
     }
+    }   // eta loop
 }
 
 // --------------------------------------------------------------------------
@@ -590,6 +600,16 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
     const size_t smem = sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2) +
                         (use_tma ? (size_t)(TT / 32) * TS * 4096 + 512
                                  : (size_t)(DT / 32) * 4096 + 512);
+    // SB_EIG_PERSIST=N: N persistent CTAs (1 per SM, 4-stage ring) walk the curvatures,
+    // so that only N matrices (N MB) are in flight and re-reads hit the L2
+    int persist = 0;
+    if (const char* ev = getenv("SB_EIG_PERSIST")) persist = atoi(ev);
+    constexpr int PS = 4;
+    const size_t smem_p = sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2) +
+                          (size_t)(TT / 32) * PS * 4096 + 512;
+    if (use_tma && persist > 0)
+        SB_CUDA(cudaFuncSetAttribute(thth_eig_kernel<TT, true, PS, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
     if (use_tma)
         SB_CUDA(cudaFuncSetAttribute(thth_eig_kernel<TT, true, TS>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -609,12 +629,15 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
         if (rc < 0) return rc;
         if (rc > 0) {
             // the triangle stayed in cluster shared memory for the whole solve
-        } else if (use_tma)
+        } else if (use_tma && persist > 0)
+            thth_eig_kernel<TT, true, PS, true><<<persist < nb ? persist : nb, TT, smem_p, st>>>(
+                d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter, nb);
+        else if (use_tma)
             thth_eig_kernel<TT, true, TS><<<nb, TT, smem, st>>>(
-                d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter);
+                d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter, nb);
         else
             thth_eig_kernel<DT, false, 1><<<nb, DT, smem, st>>>(
-                d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter);
+                d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter, nb);
         prof_end(PROF_THTH_EIG, st);
         SB_LAUNCH_CHECK();
     }

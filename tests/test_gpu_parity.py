@@ -379,6 +379,21 @@ def test_column_limited_cs(sb):
     assert thth.needed_fd_columns(fd, np.linspace(-60, 60, 64)) is None
 
 
+def test_eta_sweep_persistent_grid(sb, sample, monkeypatch):
+    """SB_EIG_PERSIST: a few persistent CTAs walk all curvatures (ring state
+    carried from one matrix to the next)."""
+    g, CS = sample
+    monkeypatch.setenv("SB_EIG_PERSIST", "7")
+    eigs, info = sb.ththmod.eta_sweep(CS, g["tau"], g["fd"], g["etas"], g["edges"],
+                                      return_info=True)
+    assert (np.abs(eigs - g["eigs"]) / g["eigs"]).max() < RTOL
+    assert (info["status"] == 0).all()
+    wide = np.linspace(-6.0, 6.0, 64)
+    r2 = TO.eta_sweep(CS, g["tau"], g["fd"], np.array([20.0, 50.0, 30.0]), wide)
+    e2 = sb.ththmod.eta_sweep(CS, g["tau"], g["fd"], np.array([20.0, 50.0, 30.0]), wide)
+    assert np.array_equal(np.isnan(e2), np.isnan(r2))
+
+
 def test_eta_sweep_batched_slab(sb, sample, monkeypatch):
     """Force the theta-theta matrix slab to a few MB so the sweep runs in many
     build+eigen batches; results must not change."""
