@@ -129,6 +129,34 @@ int sb_thin_map(const sb_thth_geom* geom, const double* th2_cents, int32_t n_th2
                 int32_t power, double eta1, double eta2, void* thth, int32_t* err,
                 void* stream);
 
+/* ---- phase retrieval ----------------------------------- */
+
+/* ththmod.rev_map (scintools/ththmod.py:176-258): scatter the n x n theta-theta
+ * matrix thth (float2, row-major, device) back into the conjugate spectrum
+ * recov [ntau][nfd] (float2, = the reference's recov.T).  Bins are those of
+ * np.histogram2d with edges (k - 0.5) * d + x0, bit-exact (x0 = tau[0] / fd[0],
+ * d = tau[1]-tau[0] / fd[1]-fd[0], both > 0); weights 1/sqrt|2 eta dtheta|; bin
+ * means; empty bins and the (0, 0) bin (zero Jacobian -> NaN -> nan_to_num) are 0.
+ * hermitian != 0 also adds the conjugate at (-fd, -tau) (:229-256).
+ * th_cents: float64 [n] on the device, already centred as in :208-209. */
+int sb_rev_map(const void* thth, int32_t n, const double* th_cents, double eta, double tau0,
+               double dtau, int32_t ntau, double fd0, double dfd, int32_t nfd,
+               int32_t hermitian, void* recov, void* stream);
+
+/* Largest-algebraic eigenpair of a full Hermitian float2 matrix a [n][ld] on
+ * the device: eigsh(thth_red, 1, which='LA') in ththmod.modeler (:300-307).
+ * w: float64 [1], v: float2 [n] (unit norm, arbitrary global phase like ARPACK),
+ * info: int32 [2] = {lanczos steps, status (SB_ETA_* bits)}.  tol: residual
+ * bound relative to w (<= 0: 1e-7); max_iter <= 0: 96. */
+int sb_herm_eigvec(const void* a, int32_t n, int32_t ld, double tol, int32_t max_iter,
+                   double* w, void* v, int32_t* info, void* stream);
+
+/* out[:crop0, :crop1] = scale * ifft2(ifftshift(in)) (centred != 0) or
+ * scale * ifft2(in), in: float2 [n0][n1], powers of two (ththmod.py:321, :1462-1465).
+ * real_only != 0 writes float (the real part), else float2.  crop <= 0: full. */
+int sb_ifft2_c2c_f32(const void* in, int32_t n0, int32_t n1, int32_t centred, int32_t crop0,
+                     int32_t crop1, double scale, int32_t real_only, void* out, void* stream);
+
 /* ---- Dynspec 2-D FFT paths ---------------------------------------------- */
 
 /* Replaces the arithmetic of Dynspec.calc_sspec (scintools/dynspec.py:3664-3721):

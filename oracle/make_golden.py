@@ -169,6 +169,48 @@ def golden_thin(pkg):
     print("thin: peak eta = %.2f" % etas[np.argmax(sv)])
 
 
+def golden_retrieval(pkg):
+    """rev_map / modeler / single_chunk_retrieval on a 64 x 128 piece of the
+    tutorial chunk (padded CS 256 x 512).  Eigenvector-dependent outputs are
+    stored as computed (their global phase is arbitrary: ARPACK start vector)."""
+    u = sys.modules["astropy.units"]
+    thth = pkg.ththmod
+    g = np.load(os.path.join(GOLD, "thth_sample_64x150.npz"))
+    d0 = g["dspec2"][:, :128]
+    d0 = d0 - d0.mean()
+    time, freq = g["time"][:128], g["freq"]
+    npad = int(g["npad"])
+    eta = 44.0
+    edges = np.linspace(-0.4, 0.4, 256)
+    fd = thth.fft_axis(time * u.s, u.mHz, npad)
+    tau = thth.fft_axis(freq * u.MHz, u.us, npad)
+    pad = np.pad(d0, ((0, npad * d0.shape[0]), (0, npad * d0.shape[1])),
+                 mode="constant", constant_values=d0.mean())
+    CS = np.fft.fftshift(np.fft.fft2(pad))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        thth_red, thth2_red, recov, model, edges_red, w, V = thth.modeler(
+            CS, tau, fd, eta * u.s ** 3, edges * u.mHz)
+        res = thth.single_chunk_retrieval([d0, edges * u.mHz, time * u.s, freq * u.MHz,
+                                           eta * u.s ** 3, 0, 0, npad, 0 * u.us, False])
+        # a generic (non rank-1) map through rev_map, both symmetries
+        rng = np.random.default_rng(5)
+        n = thth_red.shape[0]
+        tt = (rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n)))
+        rv_h = thth.rev_map(tt, tau, fd, eta * u.s ** 3, edges_red, hermetian=True)
+        rv_n = thth.rev_map(tt, tau, fd, eta * u.s ** 3, edges_red, hermetian=False)
+    np.savez_compressed(
+        os.path.join(GOLD, "retrieval_64x128.npz"), d0=d0, time=time, freq=freq, npad=npad,
+        eta=eta, edges=edges, tau=np.asarray(tau.value), fd=np.asarray(fd.value),
+        edges_red=np.asarray(edges_red.value), w=float(w), V=np.asarray(V).astype(np.complex64),
+        thth_red=np.asarray(thth_red).astype(np.complex64),
+        recov=np.asarray(recov).astype(np.complex64), model=np.asarray(model).astype(np.float32),
+        model_E=np.asarray(res[0]).astype(np.complex64), tt_seed=5,
+        rv_h=np.asarray(rv_h).astype(np.complex64), rv_n=np.asarray(rv_n).astype(np.complex64))
+    print("retrieval: n_red = %d, w = %.4g, |model_E| max = %.3f" %
+          (thth_red.shape[0], w, np.abs(res[0]).max()))
+
+
 def golden_sim(pkg):
     """scint_sim.Simulation at 64^2 / 32x96, seeded (legacy MT19937)."""
     Sim = pkg.scint_sim.Simulation
@@ -205,6 +247,8 @@ def main():
         golden_thth(pkg)
     if not only or "thin" in only:
         golden_thin(pkg)
+    if not only or "retrieval" in only:
+        golden_retrieval(pkg)
     if not only or "sim" in only:
         golden_sim(pkg)
     for fn in sorted(os.listdir(GOLD)):

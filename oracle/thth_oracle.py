@@ -277,3 +277,63 @@ def single_search_thin(dspec2, freq, time, etas, edges, edgesArclet, centerCut,
     eigs = thin_sweep(src, tau, fd, etas, edges, edgesArclet, centerCut)
     eta_fit, eta_sig, _ = peak_fit(etas, eigs, fw)
     return eta_fit, eta_sig, np.mean(freq), np.mean(time), eigs
+
+
+# ---------------------------------------------------------------------------
+# phase retrieval: inverse map, rank-1 model, wavefield of one chunk
+# ---------------------------------------------------------------------------
+def rev_map(thth, tau, fd, eta, edges, hermetian=True):
+    """ththmod.py:176-258: bin the theta-theta points back into the conjugate
+    spectrum (np.histogram2d with explicit edges; 1/sqrt|2 eta dtheta| weights;
+    bins with a zero-Jacobian (diagonal) point come out NaN -> 0)."""
+    tau = np.asarray(tau, dtype=np.float64)
+    fd = np.asarray(fd, dtype=np.float64)
+    th = theta_centres(edges)
+    fd_map = th[np.newaxis, :] - th[:, np.newaxis]
+    tau_map = eta * (th[np.newaxis, :] ** 2 - th[:, np.newaxis] ** 2)
+    fd_edges = (np.linspace(0, fd.shape[0], fd.shape[0] + 1) - .5) * (fd[1] - fd[0]) + fd[0]
+    tau_edges = (np.linspace(0, tau.shape[0], tau.shape[0] + 1) - .5) * (tau[1] - tau[0]) + tau[0]
+    bins = (fd_edges, tau_edges)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        wts = np.ravel(thth / np.sqrt(np.abs(2 * eta * fd_map.T)))
+        x, y = np.ravel(fd_map), np.ravel(tau_map)
+        recov = (np.histogram2d(x, y, bins=bins, weights=wts.real)[0]
+                 + np.histogram2d(x, y, bins=bins, weights=wts.imag)[0] * 1j)
+        norm = np.histogram2d(x, y, bins=bins)[0]
+        if hermetian:
+            recov += (np.histogram2d(-x, -y, bins=bins, weights=wts.real)[0]
+                      - np.histogram2d(-x, -y, bins=bins, weights=wts.imag)[0] * 1j)
+            norm += np.histogram2d(-x, -y, bins=bins)[0]
+        recov /= norm
+        recov = np.nan_to_num(recov)
+    return recov.T
+
+
+def modeler(CS, tau, fd, eta, edges):
+    """ththmod.py:261-327, hermetian=True branch (the other branch raises
+    IndexError in the reference).  The eigenvector's phase
+    is arbitrary (ARPACK start vector)."""
+    thth_red, edges_red = thth_redmap(CS, tau, fd, eta, edges)
+    w, V = eigsh(thth_red, 1, which="LA")
+    w, V = w[0], V[:, 0]
+    thth2_red = np.outer(V, np.conjugate(V)) * np.abs(w)
+    recov = rev_map(thth2_red, tau, fd, eta, edges_red, hermetian=True)
+    model = np.fft.ifft2(np.fft.ifftshift(recov)).real
+    return thth_red, thth2_red, recov, model, edges_red, w, V
+
+
+def single_chunk_retrieval(dspec2, edges, time, freq, eta, npad, tau_mask=0.0):
+    """ththmod.py:1390-1476: wavefield of one chunk (zeros if anything fails)."""
+    fd = fft_axis(time, "mHz", npad)
+    tau = fft_axis(freq, "us", npad)
+    CS = conjugate_spectrum(dspec2, npad, None, tau, tau_mask)
+    try:
+        thth_red, _, _, _, edges_red, w, V = modeler(CS, tau, fd, eta, edges)
+        ththE = thth_red * 0
+        ththE[ththE.shape[0] // 2, :] = np.conjugate(V) * np.sqrt(w)
+        recov_E = rev_map(ththE, tau, fd, eta, edges_red, hermetian=False)
+        model_E = np.fft.ifft2(np.fft.ifftshift(recov_E))[:dspec2.shape[0], :dspec2.shape[1]]
+        model_E = model_E * (dspec2.shape[0] * dspec2.shape[1] / 4)
+    except Exception:
+        model_E = np.zeros(dspec2.shape, dtype=complex)
+    return model_E

@@ -139,6 +139,14 @@ int thin_sweep(const ThinGeom& t, const double* d_eta1, const double* d_eta2, in
 int thin_map(const ThinGeom& t, double e1, double e2, float2* d_out, int* d_err,
              cudaStream_t st);
 
+int rev_map(const float2* thth, int n, const double* th_dev, double eta, double tau0,
+            double dtau, int ntau, double fd0, double dfd, int nfd, int hermitian,
+            float2* recov, cudaStream_t st);
+int herm_eigvec(const float2* A, int n, int ld, double tol, int max_iter, double* w_dev,
+                float2* V_dev, int* info_dev, cudaStream_t st);
+int ifft2_c2c(const float2* in, int n0, int n1, int centred, int crop0, int crop1,
+              double scale, int real_only, void* out, cudaStream_t st);
+
 static int to_geom(const sb_thth_geom* in, ThthGeom* g) {
     SB_ARG(in != nullptr);
     SB_ARG(in->ntau > 0 && in->nfd > 0);
@@ -276,6 +284,28 @@ int sb_thin_map(const sb_thth_geom* geom, const double* th2_cents, int32_t n_th2
     if (rc) return rc;
     SB_ARG(thth && err);
     return sb::thin_map(t, eta1, eta2, (float2*)thth, err, (cudaStream_t)stream);
+}
+
+int sb_rev_map(const void* thth, int32_t n, const double* th_cents, double eta, double tau0,
+               double dtau, int32_t ntau, double fd0, double dfd, int32_t nfd,
+               int32_t hermitian, void* recov, void* stream) {
+    SB_ARG(thth && th_cents && recov && n >= 1 && ntau >= 1 && nfd >= 1);
+    return sb::rev_map((const float2*)thth, n, th_cents, eta, tau0, dtau, ntau, fd0, dfd, nfd,
+                       hermitian, (float2*)recov, (cudaStream_t)stream);
+}
+
+int sb_herm_eigvec(const void* a, int32_t n, int32_t ld, double tol, int32_t max_iter,
+                   double* w, void* v, int32_t* info, void* stream) {
+    SB_ARG(a && w && v && info && n >= 1 && ld >= n);
+    return sb::herm_eigvec((const float2*)a, n, ld, tol, max_iter, w, (float2*)v, info,
+                           (cudaStream_t)stream);
+}
+
+int sb_ifft2_c2c_f32(const void* in, int32_t n0, int32_t n1, int32_t centred, int32_t crop0,
+                     int32_t crop1, double scale, int32_t real_only, void* out, void* stream) {
+    SB_ARG(in && out);
+    return sb::ifft2_c2c((const float2*)in, n0, n1, centred, crop0, crop1, scale, real_only,
+                         out, (cudaStream_t)stream);
 }
 
 int sb_sspec_f32(const float* dyn, int32_t nf, int32_t nt, const float* win_t,

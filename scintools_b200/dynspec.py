@@ -445,3 +445,43 @@ class Dynspec:
             A_err = np.sqrt(1 / np.sum(2 / ((f0 ** 2) * self.eta_evo_err)[tofit] ** 2))
         self.ththeta = A / self.fref ** 2
         self.ththetaerr = A_err / self.fref ** 2
+
+    def thetatheta_chunks(self, verbose=False, pool=None, memmap=False):
+        """Phase retrieval on every half-overlapping retrieval chunk
+        (reference dynspec.py:1765-1828) -> self.chunks [ncf_ret][nct_ret][cwf][cwt].
+        ``pool`` must be None (see fit_thetatheta); memmap is not supported."""
+        if pool is not None:
+            raise ValueError("thetatheta_chunks on the B200 path takes pool=None "
+                             "(CUDA is not fork-safe)")
+        if memmap:
+            raise NotImplementedError("memmap chunk storage is outside the B200 path")
+        if not hasattr(self, "ththeta"):
+            self.fit_thetatheta(verbose=verbose)
+        self.chunks = np.zeros((self.ncf_ret, self.nct_ret, self.cwf, self.cwt),
+                               dtype=complex)
+        for cf in range(self.ncf_ret):
+            fs = slice(cf * (self.cwf // 2), cf * (self.cwf // 2) + self.cwf)
+            freq2 = np.copy(self.freqs[fs]).astype(np.float64)
+            freq = freq2.mean()
+            eta = self.ththeta * (self.fref / freq) ** 2
+            for ct in range(self.nct_ret):
+                ts = slice(ct * (self.cwt // 2), ct * (self.cwt // 2) + self.cwt)
+                time2 = np.copy(self.times[ts]).astype(np.float64)
+                dspec2 = np.copy(self.dyn[fs, ts]).astype(np.float64)
+                dspec2 -= np.nanmean(dspec2)
+                dspec2 = np.nan_to_num(dspec2)
+                res = thth.single_chunk_retrieval(
+                    (dspec2, self.edges * (freq / self.fref), time2, freq2, eta, ct, cf,
+                     self.npad, self.thth_tau_mask, verbose))
+                self.chunks[cf, ct, :, :] = res[0]
+
+    def calc_wavefield(self, verbose=False, pool=None, gs=False, memmap=False,
+                       niter=1):
+        """Mosaic the retrieved chunks into self.wavefield (reference
+        dynspec.py:1830-1856).  Gerchberg-Saxton refinement (gs=True) is not
+        part of this version."""
+        if gs:
+            raise NotImplementedError("gerchberg_saxton is a 'next' row (SURVEY 8f)")
+        if not hasattr(self, "chunks"):
+            self.thetatheta_chunks(verbose=verbose, pool=pool, memmap=memmap)
+        self.wavefield = thth.mosaic(self.chunks)

@@ -512,6 +512,166 @@ def single_search_thin(params):
             U.wrap(time_v.mean(), "s", like=time), eigs)
 
 
+# ---------------------------------------------------------------------------
+# phase retrieval: inverse map, rank-1 model, wavefield of one chunk
+# ---------------------------------------------------------------------------
+def _c64(t):
+    a = t.cpu().numpy()
+    return a[..., 0].astype(np.float64) + 1j * a[..., 1].astype(np.float64)
+
+
+def _rev_map_device(thth_dev, n, tau, fd, eta, edges, hermetian):
+    """sb_rev_map on a device theta-theta matrix; returns the device recov
+    [ntau][nfd][2] (= the reference's ``recov.T`` before any host copy)."""
+    import torch
+    tau = U.value(tau, "us")
+    fd = U.value(fd, "mHz")
+    th = theta_centres(U.value(edges, "mHz"))
+    if th.shape[0] != n:
+        raise ValueError("thth is %d x %d but edges give %d centres" % (n, n, th.shape[0]))
+    recov = D.empty((tau.shape[0], fd.shape[0], 2), torch.float32)
+    th_dev = D.upload(th)
+    _lib.check(_lib.lib.sb_rev_map(
+        thth_dev.data_ptr(), n, th_dev.data_ptr(), float(U.value(eta, "s3")),
+        float(tau[0]), float(tau[1] - tau[0]), tau.shape[0],
+        float(fd[0]), float(fd[1] - fd[0]), fd.shape[0], 1 if hermetian else 0,
+        recov.data_ptr(), D.stream_ptr()))
+    return recov
+
+
+def rev_map(thth, tau, fd, eta, edges, hermetian=True):
+    """Inverse map from theta-theta to the conjugate spectrum
+    (ththmod.py:176-258).  Returns the complex [len(tau)][len(fd)] array."""
+    thth = np.asarray(thth)
+    n = thth.shape[0]
+    if thth.ndim != 2 or thth.shape[1] != n:
+        raise ValueError("thth must be square")
+    recov = _c64(_rev_map_device(D.upload_f32(thth.astype(np.complex128)), n, tau, fd, eta,
+                                 edges, hermetian))
+    if not hermetian:
+        # the (0, 0) bin holds the zero-Jacobian diagonal points: NaN real part,
+        # imaginary part sum(imag / 0) -> nan_to_num (ththmod.py:219-258)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            h = np.sum(np.diagonal(thth).imag / 0.0)
+        if np.isinf(h):
+            tauv, fdv = U.value(tau, "us"), U.value(fd, "mHz")
+            fe = (np.linspace(0, fdv.shape[0], fdv.shape[0] + 1) - .5) * (fdv[1] - fdv[0]) + fdv[0]
+            te = (np.linspace(0, tauv.shape[0], tauv.shape[0] + 1) - .5) * (tauv[1] - tauv[0]) + tauv[0]
+            bx = np.searchsorted(fe, 0.0, side="right") - 1
+            by = np.searchsorted(te, 0.0, side="right") - 1
+            if 0 <= bx < fdv.shape[0] and 0 <= by < tauv.shape[0]:
+                recov[by, bx] = np.nan_to_num(complex(0.0, h))
+    return recov
+
+
+def _top_eigenpair(thth_red):
+    """eigsh(thth_red, 1, which='LA') on the device (sb_herm_eigvec)."""
+    import torch
+    n = thth_red.shape[0]
+    a = D.upload_f32(np.asarray(thth_red).astype(np.complex128))
+    w = D.empty((1,), torch.float64)
+    V = D.empty((n, 2), torch.float32)
+    info = D.zeros((2,), torch.int32)
+    _lib.check(_lib.lib.sb_herm_eigvec(a.data_ptr(), n, n, 0.0, 0, w.data_ptr(), V.data_ptr(),
+                                       info.data_ptr(), D.stream_ptr()))
+    wv = float(w.cpu()[0])
+    if not np.isfinite(wv):
+        raise np.linalg.LinAlgError("theta-theta matrix has a zero start vector / no eigenpair")
+    return wv, _c64(V), V
+
+
+def modeler(CS, tau, fd, eta, edges, hermetian=True):
+    """Model theta-theta, conjugate spectrum and dynamic spectrum from the top
+    eigenpair (ththmod.py:261-327).  Returns (thth_red, thth2_red, recov, model,
+    edges_red, w, V).  The padded CS must have power-of-two sizes (the inverse
+    2-D FFT of this version); V has an arbitrary global phase, like ARPACK's."""
+    import torch
+    if not hermetian:
+        raise NotImplementedError(
+            "modeler(hermetian=False) raises IndexError in the reference "
+            "(ththmod.py:316-320) and is not part of the B200 path")
+    tauv, fdv = U.value(tau, "us"), U.value(fd, "mHz")
+    thth_red, edges_red = thth_redmap(CS, tau, fd, eta, edges, hermetian=True)
+    w, V, _ = _top_eigenpair(thth_red)
+    thth2_red = np.outer(V, np.conjugate(V)) * np.abs(w)
+    n = thth_red.shape[0]
+    recov_dev = _rev_map_device(D.upload_f32(thth2_red), n, tauv, fdv, eta, edges_red, True)
+    model = D.empty((tauv.shape[0], fdv.shape[0]), torch.float32)
+    _lib.check(_lib.lib.sb_ifft2_c2c_f32(recov_dev.data_ptr(), tauv.shape[0], fdv.shape[0], 1,
+                                         0, 0, 1.0, 1, model.data_ptr(), D.stream_ptr()))
+    return (thth_red, thth2_red, _c64(recov_dev), model.cpu().numpy().astype(np.float64),
+            edges_red, w, V)
+
+
+def single_chunk_retrieval(params):
+    """Phase retrieval on one chunk (ththmod.py:1390-1476).  ``params`` is the
+    reference's tuple (dspec2, edges, time, freq, eta, idx_t, idx_f, npad,
+    tauMask, verbose); returns (model_E, idx_f, idx_t).  A chunk that cannot
+    be recovered gives zeros, as in the reference."""
+    import torch
+    dspec2, edges, time, freq, eta, idx_t, idx_f, npad, tauMask, verbose = params
+    dspec2 = np.asarray(dspec2, dtype=np.float64)
+    time_v, freq_v = U.value(time, "s"), U.value(freq, "MHz")
+    if verbose:
+        print("Starting Chunk %s-%s" % (idx_f, idx_t), flush=True)
+    fd = U.value(fft_axis(time_v, "mHz", npad), "mHz")
+    tau = U.value(fft_axis(freq_v, "us", npad), "us")
+    nf, nt = dspec2.shape
+    try:
+        cs = conjugate_spectrum(dspec2, npad, None, tau, float(U.value(tauMask, "us")))
+        thth_red, edges_red = thth_redmap(cs, tau, fd, eta, edges, hermetian=True)
+        w, V, _ = _top_eigenpair(thth_red)
+        n = thth_red.shape[0]
+        ththE = np.zeros((n, n), dtype=np.complex128)
+        with np.errstate(invalid="ignore"):
+            ththE[n // 2, :] = np.conjugate(V) * np.sqrt(w)
+        recov_dev = _rev_map_device(D.upload_f32(ththE), n, tau, fd, eta, edges_red, False)
+        out = D.empty((nf, nt, 2), torch.float32)
+        _lib.check(_lib.lib.sb_ifft2_c2c_f32(recov_dev.data_ptr(), tau.shape[0], fd.shape[0], 1,
+                                             nf, nt, nf * nt / 4.0, 0, out.data_ptr(),
+                                             D.stream_ptr()))
+        model_E = _c64(out)
+        if verbose:
+            print("Chunk %s-%s success" % (idx_f, idx_t), flush=True)
+    except Exception as e:          # same catch-all as ththmod.py:1470-1475
+        print(e, flush=True)
+        model_E = np.zeros(dspec2.shape, dtype=complex)
+    return (model_E, idx_f, idx_t)
+
+
+def mask_func(w):
+    """sin^2 ramp used to weight overlapping chunks (ththmod.py:1478-1489)."""
+    x = np.linspace(0, w - 1, w)
+    return np.sin((np.pi / 2) * x / w) ** 2
+
+
+def mosaic(chunks):
+    """Stitch the half-overlapping wavefield chunks [ncf][nct][cwf][cwt] into one
+    wavefield, rotating each new chunk to the phase of what is already there
+    (ththmod.py:1492-1554).  Sequential by construction: host numpy."""
+    ncf, nct, cwf, cwt = chunks.shape
+    hf, ht = cwf // 2, cwt // 2
+    E = np.zeros(((ncf - 1) * hf + cwf, (nct - 1) * ht + cwt), dtype=complex)
+    up_f, up_t = mask_func(hf), mask_func(ht)
+    for cf in range(ncf):
+        for ct in range(nct):
+            new = chunks[cf, ct, :, :]
+            fs = slice(cf * cwf // 2, cf * cwf // 2 + cwf)
+            ts = slice(ct * cwt // 2, ct * cwt // 2 + cwt)
+            mask = np.ones(new.shape)
+            if cf > 0:
+                mask[:hf, :] *= up_f[:, np.newaxis]
+            if cf < ncf - 1:
+                mask[hf:, :] *= 1 - up_f[:, np.newaxis]
+            if ct > 0:
+                mask[:, :ht] *= up_t
+            if ct < nct - 1:
+                mask[:, ht:] *= 1 - up_t
+            rot = np.angle((E[fs, ts] * np.conjugate(new) * mask).mean())
+            E[fs, ts] += new * mask * np.exp(1j * rot)
+    return E
+
+
 def min_edges(fd_lim, fd, tau, eta, factor=2):
     """Minimum edges array that oversamples the CS (ththmod.py:1671-1705)."""
     fd_lim_v = float(U.value(fd_lim, "mHz"))
