@@ -157,6 +157,15 @@ int sb_herm_eigvec(const void* a, int32_t n, int32_t ld, double tol, int32_t max
 int sb_ifft2_c2c_f32(const void* in, int32_t n0, int32_t n1, int32_t centred, int32_t crop0,
                      int32_t crop1, double scale, int32_t real_only, void* out, void* stream);
 
+/* The loop of Dynspec.gerchberg_saxton (scintools/dynspec.py:1883-1896), niter
+ * times, in place on wavefield (float2 [n0][n1], powers of two):
+ *   CWF = fft2(w); CWF[rowmask != 0, :] = 0; w = ifft2(CWF);
+ *   w = amp * exp(i angle(w)) where amp is not NaN.
+ * rowmask: uint8 [n0] over the UNSHIFTED delay rows (1 where tau < 0);
+ * amp: float [n0][n1] = sqrt(dyn) where dyn is finite and > 0, NaN elsewhere. */
+int sb_gerchberg_saxton_f32(void* wavefield, const float* amp, const uint8_t* rowmask,
+                            int32_t n0, int32_t n1, int32_t niter, void* stream);
+
 /* ---- Dynspec 2-D FFT paths ---------------------------------------------- */
 
 /* Replaces the arithmetic of Dynspec.calc_sspec (scintools/dynspec.py:3664-3721):

@@ -211,6 +211,26 @@ def golden_retrieval(pkg):
           (thth_red.shape[0], w, np.abs(res[0]).max()))
 
 
+def golden_wavefield(pkg):
+    """mosaic + Dynspec.calc_wavefield(gs=True) of the reference on preset
+    (random) chunks: deterministic, no eigenvectors involved."""
+    rng = np.random.default_rng(17)
+    ncf, nct, cwf, cwt = 3, 3, 16, 32
+    chunks = rng.normal(size=(ncf, nct, cwf, cwt)) + 1j * rng.normal(size=(ncf, nct, cwf, cwt))
+    nf, nt = (ncf - 1) * (cwf // 2) + cwf, (nct - 1) * (cwt // 2) + cwt     # 32 x 64
+    dyn = rng.exponential(1.0, (nf + 3, nt + 5))
+    dyn[4, 7] = np.nan
+    dyn[9, 11] = -0.5
+    ds = _ref_dynspec(pkg, dyn, 10.0, 0.1)
+    ds.chunks = chunks.copy()
+    mos = pkg.ththmod.mosaic(chunks)
+    ds.calc_wavefield(gs=True, niter=2)
+    np.savez_compressed(os.path.join(GOLD, "wavefield_gs_32x64.npz"), chunks=chunks, dyn=dyn,
+                        freqs=np.asarray(ds.freqs), dt=10.0, df=0.1, niter=2,
+                        mosaic=mos, wavefield=np.asarray(ds.wavefield))
+    print("wavefield: |W| max %.3f" % np.abs(ds.wavefield).max())
+
+
 def golden_sim(pkg):
     """scint_sim.Simulation at 64^2 / 32x96, seeded (legacy MT19937)."""
     Sim = pkg.scint_sim.Simulation
@@ -249,6 +269,8 @@ def main():
         golden_thin(pkg)
     if not only or "retrieval" in only:
         golden_retrieval(pkg)
+    if not only or "wavefield" in only:
+        golden_wavefield(pkg)
     if not only or "sim" in only:
         golden_sim(pkg)
     for fn in sorted(os.listdir(GOLD)):

@@ -337,3 +337,50 @@ def single_chunk_retrieval(dspec2, edges, time, freq, eta, npad, tau_mask=0.0):
     except Exception:
         model_E = np.zeros(dspec2.shape, dtype=complex)
     return model_E
+
+
+def mask_func(w):
+    """ththmod.py:1478-1489."""
+    x = np.linspace(0, w - 1, w)
+    return np.sin((np.pi / 2) * x / w) ** 2
+
+
+def mosaic(chunks):
+    """ththmod.py:1492-1554: phase-align and stack half-overlapping chunks."""
+    ncf, nct, cwf, cwt = chunks.shape
+    E = np.zeros(((ncf - 1) * (cwf // 2) + cwf, (nct - 1) * (cwt // 2) + cwt), dtype=complex)
+    for cf in range(ncf):
+        for ct in range(nct):
+            new = chunks[cf, ct]
+            sl = (slice(cf * cwf // 2, cf * cwf // 2 + cwf),
+                  slice(ct * cwt // 2, ct * cwt // 2 + cwt))
+            mask = np.ones(new.shape)
+            if cf > 0:
+                mask[:cwf // 2, :] *= mask_func(cwf // 2)[:, np.newaxis]
+            if cf < ncf - 1:
+                mask[cwf // 2:, :] *= 1 - mask_func(cwf // 2)[:, np.newaxis]
+            if ct > 0:
+                mask[:, :cwt // 2] *= mask_func(cwt // 2)
+            if ct < nct - 1:
+                mask[:, cwt // 2:] *= 1 - mask_func(cwt // 2)
+            rot = np.angle((E[sl] * np.conjugate(new) * mask).mean())
+            E[sl] += new * mask * np.exp(1j * rot)
+    return E
+
+
+def gerchberg_saxton(wavefield, dyn, freqs, niter=1):
+    """dynspec.py:1858-1896 after calc_wavefield: amplitude = sqrt(dyn) where
+    dyn is finite and positive, causality (tau < 0 zeroed) in between."""
+    W = np.array(wavefield, dtype=complex)
+    n0, n1 = W.shape
+    d = np.asarray(dyn)[:n0, :n1]
+    pos = np.isfinite(d) * (d > 0)
+    tau = fft_axis(np.asarray(freqs)[:n0], "us")
+    W *= np.sqrt(d[pos].mean() / np.abs(W[pos] ** 2).mean())
+    W[pos] = np.sqrt(d[pos]) * np.exp(1j * np.angle(W[pos]))
+    for _ in range(niter):
+        C = np.fft.fftshift(np.fft.fft2(W))
+        C[tau < 0] = 0
+        W = np.fft.ifft2(np.fft.ifftshift(C))
+        W[pos] = np.sqrt(d[pos]) * np.exp(1j * np.angle(W[pos]))
+    return W

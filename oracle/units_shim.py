@@ -111,6 +111,11 @@ def _val(x):
 
 def _convert(x, unit):
     """Value of x expressed in ``unit`` (no arithmetic when factor == 1)."""
+    # astropy lets bare 0 / inf / nan stand in for any unit (``tau < 0``)
+    if not isinstance(x, (Quantity, UnitBase)):
+        a = np.asarray(x)
+        if a.dtype.kind in "fiub" and a.size and bool(np.all((a == 0) | ~np.isfinite(a))):
+            return a
     f = _unit_of(x)._to(unit)
     v = _val(x)
     return v if f == 1.0 else v * f

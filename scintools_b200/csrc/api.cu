@@ -147,6 +147,9 @@ int herm_eigvec(const float2* A, int n, int ld, double tol, int max_iter, double
 int ifft2_c2c(const float2* in, int n0, int n1, int centred, int crop0, int crop1,
               double scale, int real_only, void* out, cudaStream_t st);
 
+int gerchberg_saxton(float2* W, const float* amp, const unsigned char* rowmask, int n0, int n1,
+                     int niter, cudaStream_t st);
+
 static int to_geom(const sb_thth_geom* in, ThthGeom* g) {
     SB_ARG(in != nullptr);
     SB_ARG(in->ntau > 0 && in->nfd > 0);
@@ -306,6 +309,13 @@ int sb_ifft2_c2c_f32(const void* in, int32_t n0, int32_t n1, int32_t centred, in
     SB_ARG(in && out);
     return sb::ifft2_c2c((const float2*)in, n0, n1, centred, crop0, crop1, scale, real_only,
                          out, (cudaStream_t)stream);
+}
+
+int sb_gerchberg_saxton_f32(void* wavefield, const float* amp, const uint8_t* rowmask,
+                            int32_t n0, int32_t n1, int32_t niter, void* stream) {
+    SB_ARG(wavefield && amp && rowmask && niter >= 0);
+    return sb::gerchberg_saxton((float2*)wavefield, amp, rowmask, n0, n1, niter,
+                                (cudaStream_t)stream);
 }
 
 int sb_sspec_f32(const float* dyn, int32_t nf, int32_t nt, const float* win_t,

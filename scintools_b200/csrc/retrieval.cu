@@ -375,4 +375,80 @@ int ifft2_c2c(const float2* in, int n0, int n1, int centred, int crop0, int crop
     return cols_generic<float, +1>(la, B2, n1, n0, crop1, cs, st);
 }
 
+// --------------------------------------------------------------------------
+// Gerchberg-Saxton iterations on a wavefield (Dynspec.gerchberg_saxton,
+// dynspec.py:1883-1896): fft2 -> zero the tau < 0 rows -> ifft2 -> put the
+// measured amplitude back where it is known.  fftshift / ifftshift cancel, so
+// the causality mask is applied to the unshifted rows; mask and amplitude are
+// fused into the final stores of the two column passes.
+// --------------------------------------------------------------------------
+struct PitchRowLoadC {
+    const float2* in;
+    long pitch;
+    __device__ __forceinline__ float2 operator()(long row, int n) const {
+        return in[(size_t)row * pitch + n];
+    }
+};
+struct RowMaskStore {     // out[k][c] = rowmask[k] ? 0 : v,  k = k1 + R1 k2
+    float2* out;
+    long pitch;
+    int R1;
+    const unsigned char* rowmask;
+    __device__ __forceinline__ void operator()(int y, int k, int c, float2 v) const {
+        const int row = y + R1 * k;
+        out[(size_t)row * pitch + c] = rowmask[row] ? make_float2(0.f, 0.f) : v;
+    }
+};
+struct AmplitudeStore {   // w = v / (n0 n1); where amp is not NaN: amp * exp(i angle(w))
+    float2* out;
+    long pitch;
+    int R1;
+    const float* amp;
+    float scale;
+    __device__ __forceinline__ void operator()(int y, int k, int c, float2 v) const {
+        const int row = y + R1 * k;
+        const size_t o = (size_t)row * pitch + c;
+        float2 w = make_float2(v.x * scale, v.y * scale);
+        const float a = amp[o];
+        if (a == a) {
+            const float m = hypotf(w.x, w.y);
+            w = (m > 0.f) ? make_float2(a * (w.x / m), a * (w.y / m)) : make_float2(a, 0.f);
+        }
+        out[o] = w;
+    }
+};
+
+int gerchberg_saxton(float2* W, const float* amp, const unsigned char* rowmask, int n0, int n1,
+                     int niter, cudaStream_t st) {
+    if (n0 < 8 || n1 < 8 || (n0 & (n0 - 1)) || (n1 & (n1 - 1)) || n0 > 65536 || n1 > 32768) {
+        set_error("gerchberg_saxton: wavefield %d x %d must have power-of-two sizes", n0, n1);
+        return SB_ERR_UNSUPPORTED;
+    }
+    const size_t bytes = (size_t)n0 * n1 * sizeof(float2);
+    float2* B1 = (float2*)workspace(3, bytes);
+    float2* B2 = (float2*)workspace(4, bytes);
+    float2* B3 = (float2*)workspace(5, bytes);
+    if (!B1 || !B2 || !B3) return SB_ERR_NOMEM;
+    int R1, R2;
+    split_len(n0, &R1, &R2);
+    for (int it = 0; it < niter; ++it) {
+        int rc = SB_OK;
+        PitchRowLoadC l0{W, n1};
+        PlainRowStore<float2> s1{B1, n1};
+        SB_ROW_DISPATCH(n1, rc = (launch_row_c2c<float, N1, N2, -1>(l0, s1, n0, st)));
+        if (rc) return rc;
+        StrideALoad<float2> la{B1, n1, R2};
+        RowMaskStore ms{B3, n1, R1, rowmask};
+        rc = cols_generic<float, -1>(la, B2, n1, n0, n1, ms, st);
+        if (rc) return rc;
+        PitchRowLoadC l3{B3, n1};
+        SB_ROW_DISPATCH(n1, rc = (launch_row_c2c<float, N1, N2, +1>(l3, s1, n0, st)));
+        if (rc) return rc;
+        AmplitudeStore as{W, n1, R1, amp, (float)(1.0 / ((double)n0 * (double)n1))};
+        rc = cols_generic<float, +1>(la, B2, n1, n0, n1, as, st);
+        if (rc) return rc;
+    }
+    return SB_OK;
+}
+
 }  // namespace sb

@@ -478,10 +478,36 @@ class Dynspec:
     def calc_wavefield(self, verbose=False, pool=None, gs=False, memmap=False,
                        niter=1):
         """Mosaic the retrieved chunks into self.wavefield (reference
-        dynspec.py:1830-1856).  Gerchberg-Saxton refinement (gs=True) is not
-        part of this version."""
-        if gs:
-            raise NotImplementedError("gerchberg_saxton is a 'next' row (SURVEY 8f)")
+        dynspec.py:1830-1856); gs=True refines it with ``niter``
+        Gerchberg-Saxton iterations."""
         if not hasattr(self, "chunks"):
             self.thetatheta_chunks(verbose=verbose, pool=pool, memmap=memmap)
         self.wavefield = thth.mosaic(self.chunks)
+        if gs:
+            self.gerchberg_saxton(verbose=verbose, pool=pool, niter=niter)
+
+    def gerchberg_saxton(self, niter=1, verbose=False, pool=None):
+        """Gerchberg-Saxton refinement of self.wavefield: measured amplitude
+        where the dynamic spectrum is finite and positive, causality
+        (tau < 0 zeroed) in between (reference dynspec.py:1858-1896).  The
+        wavefield must have power-of-two sizes."""
+        import torch
+        from . import _device as D, _lib
+        self.calc_wavefield(verbose=verbose, pool=pool)
+        n0, n1 = self.wavefield.shape
+        d = np.asarray(self.dyn[:n0, :n1], dtype=np.float64)
+        pos = np.isfinite(d) * (d > 0)
+        tau = U.value(thth.fft_axis(np.asarray(self.freqs[:n0], dtype=np.float64), "us"), "us")
+        W = self.wavefield * np.sqrt(d[pos].mean() / np.abs(self.wavefield[pos] ** 2).mean())
+        W[pos] = np.sqrt(d[pos]) * np.exp(1j * np.angle(W[pos]))
+        if niter > 0:
+            amp = np.full((n0, n1), np.nan, dtype=np.float32)
+            amp[pos] = np.sqrt(d[pos])
+            rowmask = np.fft.ifftshift(tau < 0).astype(np.uint8)     # unshifted row order
+            wd, ad, md = D.upload_f32(W), D.upload(amp), D.upload(rowmask)
+            _lib.check(_lib.lib.sb_gerchberg_saxton_f32(wd.data_ptr(), ad.data_ptr(),
+                                                        md.data_ptr(), n0, n1, int(niter),
+                                                        D.stream_ptr()))
+            a = wd.cpu().numpy()
+            W = a[..., 0].astype(np.float64) + 1j * a[..., 1].astype(np.float64)
+        self.wavefield = W
