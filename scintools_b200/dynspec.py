@@ -404,6 +404,7 @@ class Dynspec:
         self.f0s = np.zeros(self.ncf_fit)
         self.t0s = np.zeros(self.nct_fit)
         coher = (self.thetatheta_proc != 'incoherent')
+        pars, where = [], []
         for cf in range(self.ncf_fit):
             fs = slice(cf * self.cwf, (cf + 1) * self.cwf)
             freq2 = np.copy(self.freqs[fs]).astype(np.float64)
@@ -422,13 +423,20 @@ class Dynspec:
                     params += [verbose,
                                self.edges[np.abs(self.edges) < self.arclet_lim]
                                * scale, self.center_cut]
-                    res = thth.single_search_thin(params)
                 else:
                     params += [self.thth_tau_mask, verbose]
-                    res = thth.single_search(params)
-                self.eta_evo[cf, ct] = U.value(res[0], "s3")
-                self.eta_evo_err[cf, ct] = U.value(res[1], "s3")
+                pars.append(params)
+                where.append((cf, ct))
                 self.t0s[ct] = time2.mean()
+        # the reference's pool.map over the chunks (dynspec.py:1715-1719): here the
+        # chunks run back to back on the GPU, uploads overlapped with the sweeps
+        if self.thetatheta_proc == 'thin':
+            results = [thth.single_search_thin(p) for p in pars]
+        else:
+            results = thth.search_batch(pars)
+        for (cf, ct), res in zip(where, results):
+            self.eta_evo[cf, ct] = U.value(res[0], "s3")
+            self.eta_evo_err[cf, ct] = U.value(res[1], "s3")
         f0 = self.f0s[:, np.newaxis]
         if time_avg:
             eta_avg = np.nanmean(self.eta_evo, 1)

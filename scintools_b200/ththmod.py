@@ -298,11 +298,15 @@ def conjugate_spectrum(dspec2, npad, pad_value=None, tau=None, tau_mask=0.0,
     only; see needed_fd_columns) restricts the transform to the fd columns a
     given theta grid can reach."""
     import torch
-    d = np.asarray(dspec2)
-    nf, nt = d.shape
+    if isinstance(dspec2, torch.Tensor):     # already staged on the device (search_batch)
+        dd = dspec2
+        if dd.dtype != torch.float32 or not dd.is_cuda or dd.dim() != 2 or not dd.is_contiguous():
+            raise ValueError("device dynamic spectra must be contiguous float32 [nf][nt]")
+    else:
+        dd = D.upload_f32(np.asarray(dspec2))
+    nf, nt = int(dd.shape[0]), int(dd.shape[1])
     if pad_value is None:
         pad_value = float("nan")     # = dspec2.mean(), evaluated on the device
-    dd = D.upload_f32(d)
     NF, NT = (npad + 1) * nf, (npad + 1) * nt
     if (NF & (NF - 1)) or (NT & (NT - 1)) or NT < 16 or NF < 4:
         half = False        # chirp-z path for arbitrary lengths: full plane
@@ -353,12 +357,18 @@ def single_search(params):
     [dspec2, freq, time, etas, edges, name, plot, fw, npad, coher, tauMask,
     verbose]; returns (eta_fit, eta_sig, freq.mean(), time.mean(), eigs).
     Plotting is not part of the hot path: ``plot=True`` raises."""
+    return _single_search(params, None)
+
+
+def _single_search(params, staged):
     (dspec2, freq, time, etas, edges, name, plot, fw, npad, coher, tauMask,
      verbose) = params
     if plot:
         raise NotImplementedError("plotting is outside the B200 hot path; "
                                   "use scintools.ththmod.plot_func on the "
                                   "returned eigenvalues")
+    if staged is not None:
+        dspec2 = staged
     time_v = U.value(time, "s")
     freq_v = U.value(freq, "MHz")
     etas_v = U.value(etas, "s3")
@@ -374,6 +384,47 @@ def single_search(params):
     return (U.wrap(eta_fit, "s3", like=etas), U.wrap(eta_sig, "s3", like=etas),
             U.wrap(freq_v.mean(), "MHz", like=freq),
             U.wrap(time_v.mean(), "s", like=time), eigs)
+
+
+def search_batch(params_list):
+    """single_search over a sequence of chunks -- the loop of
+    Dynspec.fit_thetatheta (dynspec.py:1680-1712) / ``pool.map(single_search,
+    pars)`` (:1715-1719) -- with the host->device copy of chunk i+1 running on
+    a copy stream while chunk i is swept.  The copy is asynchronous when the
+    dynamic spectra sit in pinned host memory; otherwise it is merely issued
+    early.  Returns the list of single_search results, in order."""
+    import torch
+    params_list = list(params_list)
+    if not params_list:
+        return []
+    D.device()
+    main = torch.cuda.current_stream()
+    side = torch.cuda.Stream()
+
+    def stage(p):
+        a = np.asarray(p[0])
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        with torch.cuda.stream(side):
+            t = torch.from_numpy(np.ascontiguousarray(a)).to(D.device(), non_blocking=True)
+            if t.dtype != torch.float32:
+                t32 = torch.empty(t.shape, dtype=torch.float32, device=t.device)
+                _lib.check(_lib.lib.sb_convert_f64_f32(t.data_ptr(), t32.data_ptr(), t.numel(),
+                                                       side.cuda_stream))
+                t = t32
+            ev = torch.cuda.Event()
+            ev.record(side)
+        t.record_stream(main)
+        return t, ev
+
+    out = []
+    nxt = stage(params_list[0])
+    for i, p in enumerate(params_list):
+        t, ev = nxt
+        main.wait_event(ev)
+        nxt = stage(params_list[i + 1]) if i + 1 < len(params_list) else None
+        out.append(_single_search(p, t))
+    return out
 
 
 # ---------------------------------------------------------------------------
