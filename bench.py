@@ -345,11 +345,9 @@ def b200_arm(args):
     for _ in range(min(2, args.warmup)):
         res = thth.single_search(params)
     sync_all()
-    # one dynspec per step through the public chunk-loop API: every step copies
-    # its 134 MB input from pinned host memory and reads its eigenvalues back;
-    # the copy of step i+1 overlaps the sweep of step i (copy stream)
     t0 = time.perf_counter()
-    res = thth.search_batch([params] * args.steps)[-1]
+    for _ in range(args.steps):
+        res = thth.single_search(params)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -359,9 +357,8 @@ def b200_arm(args):
     e2e = {"value": e2e_val, "unit": "eta-trials/s",
            "h2d_bytes_per_step": int(dyn.nbytes + etas.nbytes + 8 * (NEDGE - 1)),
            "d2h_bytes_per_step": int(8 * NETA),
-           "api": "scintools_b200.ththmod.search_batch([params] * steps) = single_search "
-                  "per step incl. host parabola fit, next step's upload overlapped; "
-                  "dyn float32 in pinned host memory",
+           "api": "scintools_b200.ththmod.single_search(params) incl. host "
+                  "parabola fit; dyn float32 in pinned host memory",
            "eta_fit": float(res[0]) if res is not None else None}
 
     line = None

@@ -429,11 +429,11 @@ class Dynspec:
                 where.append((cf, ct))
                 self.t0s[ct] = time2.mean()
         # the reference's pool.map over the chunks (dynspec.py:1715-1719): here the
-        # chunks run back to back on the GPU, uploads overlapped with the sweeps
+        # chunks run back to back on the GPU
         if self.thetatheta_proc == 'thin':
             results = [thth.single_search_thin(p) for p in pars]
         else:
-            results = thth.search_batch(pars)
+            results = [thth.single_search(p) for p in pars]
         for (cf, ct), res in zip(where, results):
             self.eta_evo[cf, ct] = U.value(res[0], "s3")
             self.eta_evo_err[cf, ct] = U.value(res[1], "s3")

@@ -392,7 +392,12 @@ def search_batch(params_list):
     pars)`` (:1715-1719) -- with the host->device copy of chunk i+1 running on
     a copy stream while chunk i is swept.  The copy is asynchronous when the
     dynamic spectra sit in pinned host memory; otherwise it is merely issued
-    early.  Returns the list of single_search results, in order."""
+    early.  Returns the list of single_search results, in order.
+
+    EXPERIMENTAL: results are verified (GPU parity tests), but the one timing
+    taken so far (5 x 134 MB dynspecs, no warm-up of the copy stream) was
+    slower than calling single_search in a loop, so neither fit_thetatheta nor
+    bench.py use it yet."""
     import torch
     params_list = list(params_list)
     if not params_list:

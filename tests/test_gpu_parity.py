@@ -511,3 +511,18 @@ def test_eta_sweep_solver_variants(sb, sample, monkeypatch, cluster):
     assert np.array_equal(np.isnan(e2), np.isnan(r2))
     z = sb.ththmod.eta_sweep(np.zeros_like(CS), g["tau"], g["fd"], np.array([40.0]), g["edges"])
     assert np.isnan(z).all()
+
+
+def test_search_batch_matches_single_search(sb, golden_dir):
+    """search_batch (upload of the next chunk on a copy stream) returns exactly
+    what a loop over single_search returns."""
+    g = np.load(os.path.join(golden_dir, "thth_sample_64x150.npz"))
+    d0 = g["dspec2"] - g["dspec2"].mean()
+    pars = [[d0 * s, g["freq"], g["time"], g["etas"], g["edges"], None, False, 0.2,
+             int(g["npad"]), True, 0.0, False] for s in (1.0, 2.0, 0.5)]
+    pars[1][0] = pars[1][0].astype(np.float32)
+    a = sb.ththmod.search_batch(pars)
+    b = [sb.ththmod.single_search(p) for p in pars]
+    for x, y in zip(a, b):
+        assert np.array_equal(x[4], y[4])
+        assert x[0] == y[0]
