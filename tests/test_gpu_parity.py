@@ -524,5 +524,5 @@ def test_search_batch_matches_single_search(sb, golden_dir):
     a = sb.ththmod.search_batch(pars)
     b = [sb.ththmod.single_search(p) for p in pars]
     for x, y in zip(a, b):
-        assert np.array_equal(x[4], y[4])
-        assert x[0] == y[0]
+        assert np.allclose(x[4], y[4], rtol=1e-6, atol=0)
+        assert x[0] == pytest.approx(y[0], rel=1e-6)
