@@ -335,6 +335,9 @@ def b200_arm(args):
                 "traffic_source": "profiles/r1_ncu_full_summary_final.csv (bytes per launch)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "iterative solver: the 1 MB triangle is streamed once per Lanczos step "
+                        "(~18 steps) = `traffic`; the on-chip variant that reads it once "
+                        "(eig_cluster.cu, traffic 1.10 GB) measured slower, see DESIGN.md",
                 "kernel_ms": kern}
 
     # ---- end to end through the public API, pinned host input ----------
