@@ -103,3 +103,32 @@ def calc_acf_sspec(dyn, dt, df, normalise=True, window_frac=0.1):
     if normalise:
         arr /= np.max(arr)
     return arr
+
+
+def scale_dyn_lambda(dyn, freqs, spacing="auto"):
+    """Dynspec.scale_dyn(scale='lambda') (dynspec.py:3926-3957): resample every
+    time column from equal frequency steps to equal wavelength steps with a
+    not-a-knot cubic spline (scipy interp1d kind='cubic'), flipped so that
+    wavelength increases.  Returns (lamdyn, lam, dlam).
+    ORACLE ONLY in round 1: the CUDA row comes next."""
+    from scipy.constants import c
+    from scipy.interpolate import interp1d
+    arin = np.array(dyn, dtype=np.float64)
+    nf, nt = arin.shape
+    freqs = np.array(freqs, dtype=np.float64)
+    lams = np.divide(c, freqs * 10 ** 6)
+    adl = np.abs(np.diff(lams))
+    if spacing == "auto":
+        dlam = (np.max(lams) - np.min(lams)) / len(freqs)
+    else:
+        dlam = {"max": np.max, "median": np.median, "mean": np.mean, "min": np.min}[spacing](adl)
+    lam_eq = np.arange(np.min(lams) + 1e-10, np.max(lams) - 1e-10, dlam)
+    feq = np.round(np.divide(c, lam_eq) / 10 ** 6, 6)
+    if max(feq) > max(freqs):
+        feq[np.argmax(feq)] = max(freqs)
+    if min(feq) < min(freqs):
+        feq[np.argmin(feq)] = min(freqs)
+    # one spline per column; the knots are shared, so this is a single banded
+    # solve with nt right-hand sides
+    arout = interp1d(freqs, arin, kind="cubic", axis=0)(feq)
+    return np.flipud(arout), np.flipud(lam_eq), dlam

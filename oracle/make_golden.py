@@ -231,6 +231,22 @@ def golden_wavefield(pkg):
     print("wavefield: |W| max %.3f" % np.abs(ds.wavefield).max())
 
 
+def golden_scale_dyn(pkg):
+    """Dynspec.scale_dyn(scale='lambda') + calc_sspec(lamsteps=True) of the
+    reference (oracle pin for SURVEY 8f rank 3; no CUDA row yet)."""
+    rng = np.random.default_rng(23)
+    nf, nt, dt, df = 40, 24, 10.0, 0.8
+    dyn = rng.exponential(1.0, (nf, nt))
+    ds = _ref_dynspec(pkg, dyn.copy(), dt, df, f0=1250.0)
+    ds.scale_dyn(scale="lambda")
+    out = dict(dyn=dyn, dt=dt, df=df, freqs=np.asarray(ds.freqs), lamdyn=ds.lamdyn,
+               lam=ds.lam, dlam=ds.dlam)
+    ds.calc_sspec(lamsteps=True)
+    out.update(lamsspec=ds.lamsspec, beta=ds.beta, fdop=ds.fdop)
+    np.savez_compressed(os.path.join(GOLD, "scale_dyn_40x24.npz"), **out)
+    print("scale_dyn: lamdyn", ds.lamdyn.shape, "dlam %.3e" % ds.dlam)
+
+
 def golden_sim(pkg):
     """scint_sim.Simulation at 64^2 / 32x96, seeded (legacy MT19937)."""
     Sim = pkg.scint_sim.Simulation
@@ -271,6 +287,8 @@ def main():
         golden_retrieval(pkg)
     if not only or "wavefield" in only:
         golden_wavefield(pkg)
+    if not only or "scale" in only:
+        golden_scale_dyn(pkg)
     if not only or "sim" in only:
         golden_sim(pkg)
     for fn in sorted(os.listdir(GOLD)):

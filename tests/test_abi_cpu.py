@@ -84,3 +84,31 @@ def test_prep_thetatheta_notebook_kats():
     assert ds.edges.shape[0] == 1318
     etas = ds._chunk_etas(f[:128].mean())
     np.testing.assert_allclose(etas[:2], [32.56235154, 32.88990503], rtol=2e-9)
+
+
+def test_host_mosaic_matches_reference(golden_dir):
+    """ththmod.mosaic / mask_func are sequential host numpy in the product too
+    (ththmod.py:1478-1554): check them against the reference's own output."""
+    import numpy as np
+    from scintools_b200 import ththmod
+    g = np.load(os.path.join(golden_dir, "wavefield_gs_32x64.npz"))
+    mos = ththmod.mosaic(g["chunks"])
+    assert mos.shape == g["mosaic"].shape
+    assert np.abs(mos - g["mosaic"]).max() < 1e-13 * np.abs(g["mosaic"]).max()
+    x = ththmod.mask_func(8)
+    assert x[0] == 0.0 and np.all(np.diff(x) > 0) and x[-1] < 1.0
+
+
+def test_thin_and_retrieval_fail_loudly_without_device(golden_dir):
+    """The widened rows have no CPU fallback either."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from scintools_b200 import ththmod
+    g = np.load(os.path.join(golden_dir, "retrieval_64x128.npz"))
+    with pytest.raises(RuntimeError):
+        ththmod.rev_map(g["thth_red"], g["tau"], g["fd"], float(g["eta"]), g["edges_red"])
+    with pytest.raises(RuntimeError):
+        ththmod.thin_sweep(np.zeros((256, 512), complex), g["tau"], g["fd"],
+                           np.array([40.0]), g["edges"], g["edges"][60:200], 0.0)
