@@ -24,6 +24,11 @@ int eig_cluster_launch(const float2* d_M, int ld, int n_max, const int* d_nred, 
                        int nb, double* d_eigs, int* d_status, int* d_iters, double tol,
                        double etol, int max_iter, cudaStream_t st);
 
+// eig_mixed.cu: bf16 iteration + fp32 Rayleigh quotient (SB_EIG_MIXED=1, unverified)
+int eig_mixed_launch(const float2* d_M, int ld, const int* d_nred, int e0, int nb,
+                     double* d_eigs, int* d_status, int* d_iters, double tol, double etol,
+                     int max_iter, cudaStream_t st);
+
 // status codes per eta (also in include/scint_b200.h)
 enum { ST_OK = 0, ST_INDEX_ERROR = 1, ST_ZERO_START = 2, ST_TOO_SMALL = 4,
        ST_NOT_CONVERGED = 8 };
@@ -624,11 +629,15 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
         prof_end(PROF_THTH_BUILD, st);
         SB_LAUNCH_CHECK();
         prof_begin(PROF_THTH_EIG, st);
-        const int rc = eig_cluster_launch(d_M, ld, g.n, d_nred, e0, nb, d_eigs, d_status,
-                                          d_iters, tol, 2e-7, max_iter, st);
+        // experimental solvers, each enabled by its own environment variable
+        int rc = eig_mixed_launch(d_M, ld, d_nred, e0, nb, d_eigs, d_status, d_iters, tol,
+                                  2e-7, max_iter, st);
+        if (rc == 0)
+            rc = eig_cluster_launch(d_M, ld, g.n, d_nred, e0, nb, d_eigs, d_status, d_iters,
+                                    tol, 2e-7, max_iter, st);
         if (rc < 0) return rc;
         if (rc > 0) {
-            // the triangle stayed in cluster shared memory for the whole solve
+            // handled by eig_mixed.cu / eig_cluster.cu
         } else if (use_tma && persist > 0)
             thth_eig_kernel<TT, true, PS, true><<<persist < nb ? persist : nb, TT, smem_p, st>>>(
                 d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter, nb);
