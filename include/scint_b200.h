@@ -168,6 +168,20 @@ int sb_gerchberg_saxton_f32(void* wavefield, const float* amp, const uint8_t* ro
 
 /* ---- Dynspec 2-D FFT paths ---------------------------------------------- */
 
+/* UNVERIFIED ON GPU (round-2 candidate).  Dynspec.scale_dyn(scale='lambda')
+ * (scintools/dynspec.py:3926-3957): not-a-knot cubic spline of every time
+ * column of dyn [nf][nt] at nlam query frequencies, written flipped
+ * (out [nlam][nt], wavelength ascending).  The column-independent tables are
+ * built by the host (scintools_b200/dynspec.py::_spline_tables, fp64 -> fp32):
+ * a, cp, inv, g: float [nf] Thomas factors of the second-derivative system,
+ * p0, pn: not-a-knot end ratios, idx: int32 [nlam] interval of each query,
+ * w4: float [nlam][4] weights of (y_i, y_i+1, M_i, M_i+1).  flip_rows != 0 when
+ * the frequency axis of dyn is descending. */
+int sb_scale_dyn_lambda_f32(const float* dyn, int32_t nf, int32_t nt, int32_t flip_rows,
+                            const float* a, const float* cp, const float* inv, const float* g,
+                            float p0, float pn, const int32_t* idx, const float* w4,
+                            int32_t nlam, float* out, void* stream);
+
 /* Replaces the arithmetic of Dynspec.calc_sspec (scintools/dynspec.py:3664-3721):
  *   x = win_t[t]*win_f[f]*(dyn - mean(dyn)); x -= mean(x); [prewhite: 2x2
  *   first difference]; |FFT2 zero-padded to nrfft x ncfft|^2; fftshift;

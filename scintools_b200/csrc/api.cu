@@ -150,6 +150,10 @@ int ifft2_c2c(const float2* in, int n0, int n1, int centred, int crop0, int crop
 int gerchberg_saxton(float2* W, const float* amp, const unsigned char* rowmask, int n0, int n1,
                      int niter, cudaStream_t st);
 
+int scale_dyn_lambda(const float* dyn, int nf, int nt, int flip, const float* a,
+                     const float* cp, const float* inv, const float* g, float p0, float pn,
+                     const int* idx, const float4* W, int nlam, float* out, cudaStream_t st);
+
 static int to_geom(const sb_thth_geom* in, ThthGeom* g) {
     SB_ARG(in != nullptr);
     SB_ARG(in->ntau > 0 && in->nfd > 0);
@@ -316,6 +320,15 @@ int sb_gerchberg_saxton_f32(void* wavefield, const float* amp, const uint8_t* ro
     SB_ARG(wavefield && amp && rowmask && niter >= 0);
     return sb::gerchberg_saxton((float2*)wavefield, amp, rowmask, n0, n1, niter,
                                 (cudaStream_t)stream);
+}
+
+int sb_scale_dyn_lambda_f32(const float* dyn, int32_t nf, int32_t nt, int32_t flip_rows,
+                            const float* a, const float* cp, const float* inv, const float* g,
+                            float p0, float pn, const int32_t* idx, const float* w4,
+                            int32_t nlam, float* out, void* stream) {
+    SB_ARG(dyn && a && cp && inv && g && idx && w4 && out && nt >= 1 && nlam >= 1);
+    return sb::scale_dyn_lambda(dyn, nf, nt, flip_rows, a, cp, inv, g, p0, pn, idx,
+                                (const float4*)w4, nlam, out, (cudaStream_t)stream);
 }
 
 int sb_sspec_f32(const float* dyn, int32_t nf, int32_t nt, const float* win_t,

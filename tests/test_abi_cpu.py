@@ -112,3 +112,40 @@ def test_thin_and_retrieval_fail_loudly_without_device(golden_dir):
     with pytest.raises(RuntimeError):
         ththmod.thin_sweep(np.zeros((256, 512), complex), g["tau"], g["fd"],
                            np.array([40.0]), g["edges"], g["edges"][60:200], 0.0)
+
+
+def test_spline_tables_match_scipy(golden_dir):
+    """Host half of scale_dyn (round-2 candidate): the column-independent
+    not-a-knot spline tables, applied with numpy exactly as csrc/scale_dyn.cu
+    applies them, reproduce scipy's interp1d(kind='cubic') and the reference's
+    lamdyn (tests/golden/scale_dyn_40x24.npz)."""
+    import numpy as np
+    from scipy.constants import c
+    from scintools_b200.dynspec import Dynspec
+    g = np.load(os.path.join(golden_dir, "scale_dyn_40x24.npz"))
+    freqs, dyn = g["freqs"], g["dyn"]
+    lam_eq = np.flipud(g["lam"])
+    feq = np.round(np.divide(c, lam_eq) / 10 ** 6, 6)
+    feq = np.clip(feq, freqs.min(), freqs.max())
+    T = Dynspec._spline_tables(freqs, feq)
+    n = len(freqs)
+    y = dyn
+    d = np.zeros_like(y)
+    M = np.zeros_like(y)
+    prev = np.zeros(y.shape[1])
+    for i in range(1, n - 1):
+        r = (y[i + 1] - y[i]) * T["g"][i] - (y[i] - y[i - 1]) * T["g"][i - 1]
+        prev = (r - T["a"][i] * prev) * T["inv"][i]
+        d[i] = prev
+    nxt = np.zeros(y.shape[1])
+    for i in range(n - 2, 0, -1):
+        nxt = d[i] - T["cp"][i] * nxt
+        M[i] = nxt
+    M[0] = (1 + T["p0"]) * M[1] - T["p0"] * M[2]
+    M[n - 1] = (1 + T["pn"]) * M[n - 2] - T["pn"] * M[n - 3]
+    W, idx = T["W"], T["idx"]
+    out = (W[:, 0, None] * y[idx] + W[:, 1, None] * y[idx + 1] +
+           W[:, 2, None] * M[idx] + W[:, 3, None] * M[idx + 1])
+    lamdyn = np.flipud(out)
+    assert lamdyn.shape == g["lamdyn"].shape
+    assert np.abs(lamdyn - g["lamdyn"]).max() < 1e-12 * np.abs(g["lamdyn"]).max()

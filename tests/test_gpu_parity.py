@@ -548,3 +548,23 @@ def test_eta_sweep_mixed_precision_solver(sb, sample, monkeypatch):
     assert (np.abs(got - ref) / ref).max() < RTOL
     z = sb.ththmod.eta_sweep(np.zeros_like(CS), g["tau"], g["fd"], np.array([40.0]), g["edges"])
     assert np.isnan(z).all()
+
+
+@pytest.mark.skipif(not os.environ.get("SB_TEST_UNVERIFIED"),
+                    reason="scale_dyn.cu was written after the round-1 GPU budget ran out; "
+                           "opt in with SB_TEST_UNVERIFIED=1 (round 2)")
+def test_scale_dyn_lambda(sb, golden_dir, monkeypatch):
+    monkeypatch.setenv("SB_ENABLE_UNVERIFIED", "1")
+    g = np.load(os.path.join(golden_dir, "scale_dyn_40x24.npz"))
+    dyn = g["dyn"]
+    nf, nt = dyn.shape
+    for flip in (False, True):
+        d, f = (dyn[::-1].copy(), g["freqs"][::-1].copy()) if flip else (dyn, g["freqs"])
+        ds = sb.Dynspec(dyn=sb.BasicDyn(d, times=float(g["dt"]) * np.arange(nt), freqs=f,
+                                        dt=float(g["dt"]), df=float(g["df"])), verbose=False)
+        ds.scale_dyn(scale="lambda")
+        assert np.array_equal(ds.lam, g["lam"]) and ds.dlam == float(g["dlam"])
+        assert maxrel(ds.lamdyn, g["lamdyn"]) < RTOL
+    ds.calc_sspec(lamsteps=True)
+    lin_g, lin_r = 10 ** (ds.lamsspec / 10), 10 ** (g["lamsspec"] / 10)
+    assert maxrel(lin_g, lin_r) < 1e-4
