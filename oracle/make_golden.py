@@ -211,6 +211,32 @@ def golden_retrieval(pkg):
           (thth_red.shape[0], w, np.abs(res[0]).max()))
 
 
+def golden_retrieval_tutorial(pkg):
+    """modeler / single_chunk_retrieval on the full 64 x 150 tutorial chunk
+    (padded CS 256 x 600: NOT powers of two -> chirp-z inverse FFT)."""
+    u = sys.modules["astropy.units"]
+    thth = pkg.ththmod
+    g = np.load(os.path.join(GOLD, "thth_sample_64x150.npz"))
+    d0 = g["dspec2"] - g["dspec2"].mean()
+    npad = int(g["npad"])
+    eta = 44.0
+    edges = np.linspace(-0.4, 0.4, 256)
+    fd = thth.fft_axis(g["time"] * u.s, u.mHz, npad)
+    tau = thth.fft_axis(g["freq"] * u.MHz, u.us, npad)
+    pad = np.pad(d0, ((0, npad * d0.shape[0]), (0, npad * d0.shape[1])),
+                 mode="constant", constant_values=d0.mean())
+    CS = np.fft.fftshift(np.fft.fft2(pad))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = thth.modeler(CS, tau, fd, eta * u.s ** 3, edges * u.mHz)
+        res = thth.single_chunk_retrieval([d0, edges * u.mHz, g["time"] * u.s, g["freq"] * u.MHz,
+                                           eta * u.s ** 3, 0, 0, npad, 0 * u.us, False])
+    np.savez_compressed(os.path.join(GOLD, "retrieval_64x150.npz"), eta=eta, edges=edges,
+                        w=float(out[5]), model_crop=np.asarray(out[3])[:64, :150].astype(np.float32),
+                        model_E=np.asarray(res[0]).astype(np.complex64))
+    print("retrieval tutorial: n_red = %d" % out[0].shape[0])
+
+
 def golden_wavefield(pkg):
     """mosaic + Dynspec.calc_wavefield(gs=True) of the reference on preset
     (random) chunks: deterministic, no eigenvectors involved."""
@@ -285,6 +311,8 @@ def main():
         golden_thin(pkg)
     if not only or "retrieval" in only:
         golden_retrieval(pkg)
+    if not only or "tutorial" in only:
+        golden_retrieval_tutorial(pkg)
     if not only or "wavefield" in only:
         golden_wavefield(pkg)
     if not only or "scale" in only:

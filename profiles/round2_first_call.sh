@@ -2,8 +2,9 @@
 # First gpurun call of round 2: validates what round 1 could only compile.
 #   gpurun --timeout 1200 -- 'bash profiles/round2_first_call.sh'
 mkdir -p gpurun_out
-SB_TEST_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x \
-    -k "mixed_precision or search_batch or scale_dyn" 2>&1 | tail -15 > gpurun_out/r2_tests.txt
+SB_TEST_UNVERIFIED=1 timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_retrieval.py \
+    -m gpu -q -k "mixed_precision or search_batch or scale_dyn or non_power_of_two" 2>&1 | tail -25 \
+    > gpurun_out/r2_tests.txt
 cat gpurun_out/r2_tests.txt
 for v in 0 1; do
   SB_EIG_MIXED=$v timeout 150 python bench.py --steps 5 --warmup 3 --no-cpu 2>/dev/null | tail -1 | python -c "

@@ -802,6 +802,90 @@ static int conj_spectrum_bluestein(const float* dyn, int nf, int nt, int NF, int
     return cols_generic_f<+1>(pa, C0, pt, MF, NT, cs, st);
 }
 
+// ------------------------------------------------------------------------
+// out[:crop0, :crop1] = scale * ifft2(ifftshift(in)) for ANY sizes (phase
+// retrieval on the tutorial's 256 x 600 conjugate spectrum), by the same
+// chirp-z machinery: ifft2(X) = conj(fft2(conj X)) / (N0 N1).
+//   STATUS: round-2 candidate, NOT yet run on a GPU (written after the round-1
+//   GPU budget was spent); reached only with SB_ENABLE_UNVERIFIED=1.
+// ------------------------------------------------------------------------
+struct ChirpRowLoadC {   // a[n] = conj(x[r'][n']) * w[n] with the ifftshift folded in
+    const float2* in;
+    int n0, n1, centred;
+    const float2* w;
+    __device__ __forceinline__ float2 operator()(long row, int n) const {
+        if (n >= n1) return make_float2(0.f, 0.f);
+        const int r = centred ? (int)((row + n0 / 2) % n0) : (int)row;
+        const int c = centred ? (n + n1 / 2) % n1 : n;
+        float2 v = in[(size_t)r * n1 + c];
+        v.y = -v.y;
+        return cmul(v, w[n]);
+    }
+};
+struct ChirpCropStore {  // out[k][c] = conj(v * wF[k]) * scale, k < crop0, c < crop1
+    float2* outc;
+    float* outr;
+    int R1, crop0, crop1;
+    const float2* w;
+    float scale;
+    __device__ __forceinline__ void operator()(int y, int k, int c, float2 v) const {
+        const int kf = y + R1 * k;
+        if (kf >= crop0 || c >= crop1) return;
+        const float2 r = cmul(v, w[kf]);
+        const size_t o = (size_t)kf * crop1 + c;
+        if (outr) outr[o] = r.x * scale;
+        else outc[o] = make_float2(r.x * scale, -r.y * scale);
+    }
+};
+
+int ifft2_c2c_any(const float2* in, int n0, int n1, int centred, int crop0, int crop1,
+                  double scale, int real_only, void* out, cudaStream_t st) {
+    const int MT = next_pow2(2L * n1 - 1), MF = next_pow2(2L * n0 - 1);
+    if (n0 < 2 || n1 < 2 || MT < 8 || MT > 16384 || MF < 4 || MF > 65536) {
+        set_error("ifft2 (chirp-z): %d x %d outside 2..32768 x 4..8192", n0, n1);
+        return SB_ERR_UNSUPPORTED;
+    }
+    if (crop0 <= 0 || crop0 > n0) crop0 = n0;
+    if (crop1 <= 0 || crop1 > n1) crop1 = n1;
+    const long pt = ((long)n1 + 15) & ~15L;
+    float2* tabs = (float2*)workspace(6, (size_t)(n1 + 3L * MT + n0 + 3L * MF + 64) * sizeof(float2));
+    float2* R1buf = (float2*)workspace(3, (size_t)n0 * MT * sizeof(float2));
+    float2* Ybuf = (float2*)workspace(4, (size_t)n0 * pt * sizeof(float2));
+    float2* C0 = (float2*)workspace(5, (size_t)MF * pt * sizeof(float2));
+    float2* C1 = (float2*)workspace(7, (size_t)MF * pt * sizeof(float2));
+    if (!tabs || !R1buf || !Ybuf || !C0 || !C1) return SB_ERR_NOMEM;
+    float2* wT = tabs;
+    float2* BT = wT + n1;
+    float2* wF = BT + MT;
+    float2* BF = wF + n0;
+    float2* scratch = BF + MF;      // 2*max(MT, MF)
+    int rc = bluestein_tables(n1, MT, wT, BT, scratch, st);
+    if (rc) return rc;
+    rc = bluestein_tables(n0, MF, wF, BF, scratch, st);
+    if (rc) return rc;
+    {
+        ChirpRowLoadC ld{in, n0, n1, centred, wT};
+        MulVecRowStore ms{R1buf, MT, BT};
+        SB_ROW_DISPATCH(MT, rc = (launch_row_c2c<float, N1, N2, -1>(ld, ms, n0, st)));
+        if (rc) return rc;
+        PitchRowLoad pl{R1buf, MT};
+        ChirpOutRowStore os{Ybuf, pt, wT, n1, 1.0f / (float)MT};
+        SB_ROW_DISPATCH(MT, rc = (launch_row_c2c<float, N1, N2, +1>(pl, os, n0, st)));
+        if (rc) return rc;
+    }
+    int R1, R2;
+    split_len(MF, &R1, &R2);
+    ChirpColALoad la{Ybuf, pt, R2, n0, wF};
+    MulVecColStore mc{C1, pt, R1, BF};
+    rc = cols_generic_f<-1>(la, C0, pt, MF, crop1, mc, st);
+    if (rc) return rc;
+    PlainColALoad pa{C1, pt, R2};
+    ChirpCropStore cs{real_only ? nullptr : (float2*)out, real_only ? (float*)out : nullptr, R1,
+                      crop0, crop1, wF,
+                      (float)(scale / ((double)MF * (double)n0 * (double)n1))};
+    return cols_generic_f<+1>(pa, C0, pt, MF, crop1, cs, st);
+}
+
 // Dynspec.calc_acf(method='direct') (dynspec.py:3780-3797)
 int acf(const float* dyn, int nf, int nt, int subtract_mean, int normalise,
         float* out, cudaStream_t st) {

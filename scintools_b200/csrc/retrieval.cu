@@ -6,6 +6,7 @@
 // used by the Python mirrors of modeler / single_chunk_retrieval.
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "fft_generic.cuh"
 #include "lanczos.cuh"
@@ -351,8 +352,14 @@ struct CropStore {        // out[k][c], k = k1 + R1 k2
     }
 };
 
+// dynspec.cu: chirp-z variant for arbitrary sizes (round-2 candidate, unverified)
+int ifft2_c2c_any(const float2* in, int n0, int n1, int centred, int crop0, int crop1,
+                  double scale, int real_only, void* out, cudaStream_t st);
+
 int ifft2_c2c(const float2* in, int n0, int n1, int centred, int crop0, int crop1,
               double scale, int real_only, void* out, cudaStream_t st) {
+    if (((n0 & (n0 - 1)) || (n1 & (n1 - 1))) && getenv("SB_ENABLE_UNVERIFIED"))
+        return ifft2_c2c_any(in, n0, n1, centred, crop0, crop1, scale, real_only, out, st);
     if (n0 < 8 || n1 < 8 || (n0 & (n0 - 1)) || (n1 & (n1 - 1)) || n0 > 65536 || n1 > 32768) {
         set_error("ifft2: sizes %d x %d must be powers of two (8..65536 x 8..32768)", n0, n1);
         return SB_ERR_UNSUPPORTED;
