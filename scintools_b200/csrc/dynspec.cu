@@ -811,14 +811,14 @@ static int conj_spectrum_bluestein(const float* dyn, int nf, int nt, int NF, int
 // ------------------------------------------------------------------------
 struct ChirpRowLoadC {   // a[n] = conj(x[r'][n']) * w[n] with the ifftshift folded in
     const float2* in;
-    int n0, n1, centred;
+    int n0, n1, centred, keep;     // keep != 0: transform conj(in), i.e. no negation here
     const float2* w;
     __device__ __forceinline__ float2 operator()(long row, int n) const {
         if (n >= n1) return make_float2(0.f, 0.f);
         const int r = centred ? (int)((row + n0 / 2) % n0) : (int)row;
         const int c = centred ? (n + n1 / 2) % n1 : n;
         float2 v = in[(size_t)r * n1 + c];
-        v.y = -v.y;
+        if (!keep) v.y = -v.y;
         return cmul(v, w[n]);
     }
 };
@@ -838,8 +838,10 @@ struct ChirpCropStore {  // out[k][c] = conj(v * wF[k]) * scale, k < crop0, c < 
     }
 };
 
+// conj_in != 0: returns ifft2(conj(in)) = conj(fft2(in)) / (n0 n1) (used for the
+// forward transform of the Gerchberg-Saxton loop)
 int ifft2_c2c_any(const float2* in, int n0, int n1, int centred, int crop0, int crop1,
-                  double scale, int real_only, void* out, cudaStream_t st) {
+                  double scale, int real_only, void* out, cudaStream_t st, int conj_in) {
     const int MT = next_pow2(2L * n1 - 1), MF = next_pow2(2L * n0 - 1);
     if (n0 < 2 || n1 < 2 || MT < 8 || MT > 16384 || MF < 4 || MF > 65536) {
         set_error("ifft2 (chirp-z): %d x %d outside 2..32768 x 4..8192", n0, n1);
@@ -864,7 +866,7 @@ int ifft2_c2c_any(const float2* in, int n0, int n1, int centred, int crop0, int 
     rc = bluestein_tables(n0, MF, wF, BF, scratch, st);
     if (rc) return rc;
     {
-        ChirpRowLoadC ld{in, n0, n1, centred, wT};
+        ChirpRowLoadC ld{in, n0, n1, centred, conj_in, wT};
         MulVecRowStore ms{R1buf, MT, BT};
         SB_ROW_DISPATCH(MT, rc = (launch_row_c2c<float, N1, N2, -1>(ld, ms, n0, st)));
         if (rc) return rc;

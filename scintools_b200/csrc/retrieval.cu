@@ -354,12 +354,12 @@ struct CropStore {        // out[k][c], k = k1 + R1 k2
 
 // dynspec.cu: chirp-z variant for arbitrary sizes (round-2 candidate, unverified)
 int ifft2_c2c_any(const float2* in, int n0, int n1, int centred, int crop0, int crop1,
-                  double scale, int real_only, void* out, cudaStream_t st);
+                  double scale, int real_only, void* out, cudaStream_t st, int conj_in);
 
 int ifft2_c2c(const float2* in, int n0, int n1, int centred, int crop0, int crop1,
               double scale, int real_only, void* out, cudaStream_t st) {
     if (((n0 & (n0 - 1)) || (n1 & (n1 - 1))) && getenv("SB_ENABLE_UNVERIFIED"))
-        return ifft2_c2c_any(in, n0, n1, centred, crop0, crop1, scale, real_only, out, st);
+        return ifft2_c2c_any(in, n0, n1, centred, crop0, crop1, scale, real_only, out, st, 0);
     if (n0 < 8 || n1 < 8 || (n0 & (n0 - 1)) || (n1 & (n1 - 1)) || n0 > 65536 || n1 > 32768) {
         set_error("ifft2: sizes %d x %d must be powers of two (8..65536 x 8..32768)", n0, n1);
         return SB_ERR_UNSUPPORTED;
@@ -425,8 +425,50 @@ struct AmplitudeStore {   // w = v / (n0 n1); where amp is not NaN: amp * exp(i 
     }
 };
 
+// ---- any-size variant on the chirp-z inverse (round-2 candidate, unverified):
+//   T = ifft2(conj W) = conj(fft2 W) / N;  zero the masked rows of T;
+//   W = N * ifft2(conj T) = ifft2(masked fft2 W);  amplitude step.
+__global__ void gs_rowmask_kernel(float2* T, const unsigned char* __restrict__ rowmask,
+                                  long n0, long n1) {
+    for (long o = blockIdx.x * (long)blockDim.x + threadIdx.x; o < n0 * n1;
+         o += (long)gridDim.x * blockDim.x)
+        if (rowmask[o / n1]) T[o] = make_float2(0.f, 0.f);
+}
+__global__ void gs_amplitude_kernel(float2* W, const float* __restrict__ amp, long count) {
+    for (long o = blockIdx.x * (long)blockDim.x + threadIdx.x; o < count;
+         o += (long)gridDim.x * blockDim.x) {
+        const float a = amp[o];
+        if (a == a) {
+            const float2 w = W[o];
+            const float m = hypotf(w.x, w.y);
+            W[o] = (m > 0.f) ? make_float2(a * (w.x / m), a * (w.y / m)) : make_float2(a, 0.f);
+        }
+    }
+}
+static int gerchberg_saxton_any(float2* W, const float* amp, const unsigned char* rowmask,
+                                int n0, int n1, int niter, cudaStream_t st) {
+    const long count = (long)n0 * n1;
+    float2* T = (float2*)workspace(2, (size_t)count * sizeof(float2));
+    if (!T) return SB_ERR_NOMEM;
+    int blocks = (int)((count + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    for (int it = 0; it < niter; ++it) {
+        int rc = ifft2_c2c_any(W, n0, n1, 0, 0, 0, 1.0, 0, T, st, 1);
+        if (rc) return rc;
+        gs_rowmask_kernel<<<blocks, 256, 0, st>>>(T, rowmask, n0, n1);
+        SB_LAUNCH_CHECK();
+        rc = ifft2_c2c_any(T, n0, n1, 0, 0, 0, (double)count, 0, W, st, 1);
+        if (rc) return rc;
+        gs_amplitude_kernel<<<blocks, 256, 0, st>>>(W, amp, count);
+        SB_LAUNCH_CHECK();
+    }
+    return SB_OK;
+}
+
 int gerchberg_saxton(float2* W, const float* amp, const unsigned char* rowmask, int n0, int n1,
                      int niter, cudaStream_t st) {
+    if (((n0 & (n0 - 1)) || (n1 & (n1 - 1))) && getenv("SB_ENABLE_UNVERIFIED"))
+        return gerchberg_saxton_any(W, amp, rowmask, n0, n1, niter, st);
     if (n0 < 8 || n1 < 8 || (n0 & (n0 - 1)) || (n1 & (n1 - 1)) || n0 > 65536 || n1 > 32768) {
         set_error("gerchberg_saxton: wavefield %d x %d must have power-of-two sizes", n0, n1);
         return SB_ERR_UNSUPPORTED;
