@@ -28,6 +28,7 @@
 
 #include <type_traits>
 
+#include "bf16_pack.cuh"
 #include "lanczos.cuh"
 #include "tma.cuh"
 
@@ -39,24 +40,6 @@ enum { EM_ST_INDEX_ERROR = 1, EM_ST_ZERO_START = 2, EM_ST_TOO_SMALL = 4,
 constexpr int EM_THREADS = 256;
 constexpr int EM_NW = EM_THREADS / 32;
 constexpr int EM_NB = 24;            // basis slots
-
-__device__ __forceinline__ unsigned bf16_bits(float x) {
-    const unsigned u = __float_as_uint(x);
-    if ((u & 0x7f800000u) == 0x7f800000u) return u >> 16;          // inf / nan: as is
-    unsigned r = u + 0x7fffu + ((u >> 16) & 1u);                    // round to nearest even
-    if ((r & 0x7f800000u) == 0x7f800000u) r = (u & 0x80000000u) | 0x7f7f0000u;   // no overflow to inf
-    return r >> 16;
-}
-
-// Mb[i] = bf16(re) | bf16(im) << 16
-__global__ void thth_pack_bf16_kernel(const float2* __restrict__ M, unsigned* __restrict__ Mb,
-                                      size_t count) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const float2 v = M[i];
-        Mb[i] = bf16_bits(v.x) | (bf16_bits(v.y) << 16);
-    }
-}
 
 __global__ void __launch_bounds__(EM_THREADS)
 thth_eig_mixed_kernel(const float2* __restrict__ Mbase, const unsigned* __restrict__ Mbbase,

@@ -17,7 +17,9 @@
 // One thread per time column (coalesced over t), then a gather kernel
 //   out[nlam-1-k][t] = W_k0 y[i_k][t] + W_k1 y[i_k+1][t] + W_k2 M[i_k][t] + W_k3 M[i_k+1][t].
 // HBM-bound: ~7 passes over nf*nt*4 B.
+#ifndef SB_HOST_EMU            // tests/host_emu compiles the kernels for the CPU
 #include "common.cuh"
+#endif
 
 namespace sb {
 
@@ -69,6 +71,7 @@ __global__ void spline_eval_kernel(const float* __restrict__ dyn, const float* _
     out[(size_t)(nlam - 1 - k) * nt + t] = v;     // np.flipud: wavelength ascending
 }
 
+#ifndef SB_HOST_EMU
 int scale_dyn_lambda(const float* dyn, int nf, int nt, int flip, const float* a,
                      const float* cp, const float* inv, const float* g, float p0, float pn,
                      const int* idx, const float4* W, int nlam, float* out, cudaStream_t st) {
@@ -86,5 +89,6 @@ int scale_dyn_lambda(const float* dyn, int nf, int nt, int flip, const float* a,
     SB_LAUNCH_CHECK();
     return SB_OK;
 }
+#endif  // SB_HOST_EMU
 
 }  // namespace sb

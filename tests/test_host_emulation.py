@@ -1,0 +1,113 @@
+"""CPU emulation of barrier-free CUDA kernels (tests/host_emu/*.cpp compile the
+.cu source with g++ and run every thread sequentially).  Used for round-2
+candidates that could not be run on a GPU in round 1: it checks the device
+code's arithmetic and indexing, not its performance."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "host_emu")
+
+
+def _build(name):
+    src = os.path.join(EMU, name + ".cpp")
+    out = os.path.join(EMU, "_build", name + ".so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or os.path.getmtime(out) < max(
+            os.path.getmtime(src),
+            os.path.getmtime(os.path.join(ROOT, "scintools_b200", "csrc", "scale_dyn.cu"))):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC",
+                        "-x", "c++", src, "-o", out], check=True)
+    return ctypes.CDLL(out)
+
+
+@pytest.mark.parametrize("flip", [0, 1])
+def test_scale_dyn_kernels_on_host(golden_dir, flip):
+    """csrc/scale_dyn.cu (spline_moments_kernel + spline_eval_kernel) run on the
+    CPU reproduce the reference's lamdyn (scale_dyn_40x24 fixture) to fp32."""
+    from scipy.constants import c
+    from scintools_b200.dynspec import Dynspec
+    lib = _build("scale_dyn_emu")
+    g = np.load(os.path.join(golden_dir, "scale_dyn_40x24.npz"))
+    freqs, dyn = g["freqs"], g["dyn"]
+    nf, nt = dyn.shape
+    lam_eq = np.flipud(g["lam"])
+    feq = np.clip(np.round(np.divide(c, lam_eq) / 10 ** 6, 6), freqs.min(), freqs.max())
+    T = Dynspec._spline_tables(freqs, feq)
+    d32 = np.ascontiguousarray(dyn[::-1] if flip else dyn, dtype=np.float32)
+    f32 = lambda v: np.ascontiguousarray(v, dtype=np.float32)
+    a, cp, inv, gg, W = f32(T["a"]), f32(T["cp"]), f32(T["inv"]), f32(T["g"]), f32(T["W"])
+    idx = np.ascontiguousarray(T["idx"], dtype=np.int32)
+    nlam = len(feq)
+    M = np.zeros((nf, nt), np.float32)
+    out = np.zeros((nlam, nt), np.float32)
+    P = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    lib.emu_scale_dyn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int] + \
+        [ctypes.c_void_p] * 4 + [ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
+                                 ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.emu_scale_dyn(P(d32), nf, nt, flip, P(a), P(cp), P(inv), P(gg), float(T["p0"]),
+                      float(T["pn"]), P(idx), P(W), nlam, P(M), P(out))
+    ref = g["lamdyn"]
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() < 1e-5 * np.abs(ref).max()
+
+
+def test_bf16_pack_kernel_on_host():
+    """csrc/bf16_pack.cuh: round-to-nearest-even bf16 of (re, im), no overflow to
+    inf, compared with torch.bfloat16."""
+    import torch
+    src = os.path.join(EMU, "bf16_pack_emu.cpp")
+    out = os.path.join(EMU, "_build", "bf16_pack_emu.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", out],
+                   check=True)
+    lib = ctypes.CDLL(out)
+    rng = np.random.default_rng(0)
+    n = 5000
+    x = (rng.normal(size=2 * n) * 10.0 ** rng.uniform(-20, 20, 2 * n)).astype(np.float32)
+    x[:8] = [0.0, -0.0, 1.0, -1.0, 3.3895314e38, -3.3895314e38, 1.0039062, 1.0117188]  # near max, ties
+    xb = np.ascontiguousarray(x)
+    packed = np.zeros(n, np.uint32)
+    lib.emu_pack_bf16.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+    lib.emu_pack_bf16(xb.ctypes.data_as(ctypes.c_void_p), packed.ctypes.data_as(ctypes.c_void_p), n)
+    re = ((packed & 0xffff).astype(np.uint32) << 16).view(np.float32)
+    im = (packed & 0xffff0000).view(np.float32)
+    ref = torch.from_numpy(xb).to(torch.bfloat16).to(torch.float32).numpy()
+    ref = np.where(np.isinf(ref), np.sign(ref) * np.float32(3.3895314e38), ref)   # we clamp, torch overflows
+    assert np.array_equal(re, ref[0::2])
+    assert np.array_equal(im, ref[1::2])
+
+
+@pytest.mark.parametrize("n0,n1,c0,c1", [(12, 10, 0, 0), (9, 20, 5, 7), (16, 15, 16, 4)])
+def test_chirp_ifft2_functors_on_host(n0, n1, c0, c1):
+    """The chirp-z any-size inverse FFT (dynspec.cu::ifft2_c2c_any): tables and
+    load / store functors of csrc/chirp.cuh around a reference DFT reproduce
+    numpy's ifft2(ifftshift(x)) (and ifft2(conj x) for the Gerchberg-Saxton
+    forward step), crop and scale included."""
+    src = os.path.join(EMU, "chirp_ifft2_emu.cpp")
+    out = os.path.join(EMU, "_build", "chirp_ifft2_emu.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", out],
+                   check=True)
+    lib = ctypes.CDLL(out)
+    lib.emu_ifft2_any.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_double] + \
+        [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    rng = np.random.default_rng(n0 * 100 + n1)
+    x = (rng.normal(size=(n0, n1)) + 1j * rng.normal(size=(n0, n1))).astype(np.complex64)
+    cc0, cc1 = (c0 or n0), (c1 or n1)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    got = np.zeros((cc0, cc1), np.complex64)
+    lib.emu_ifft2_any(P(x), n0, n1, 1, c0, c1, 3.0, 0, 0, P(got))
+    ref = 3.0 * np.fft.ifft2(np.fft.ifftshift(x))[:cc0, :cc1]
+    assert np.abs(got - ref).max() < 2e-5 * np.abs(ref).max()
+    gotr = np.zeros((cc0, cc1), np.float32)
+    lib.emu_ifft2_any(P(x), n0, n1, 0, c0, c1, 1.0, 1, 0, P(gotr))
+    refr = np.fft.ifft2(x).real[:cc0, :cc1]
+    assert np.abs(gotr - refr).max() < 2e-5 * np.abs(refr).max()
+    lib.emu_ifft2_any(P(x), n0, n1, 0, c0, c1, 1.0, 0, 1, P(got))
+    refc = np.fft.ifft2(np.conj(x))[:cc0, :cc1]
+    assert np.abs(got - refc).max() < 2e-5 * np.abs(refc).max()
