@@ -1,9 +1,12 @@
 // Mixed-precision Lanczos for the theta-theta eigenvalue (ththmod.Eval_calc,
 // scintools/ththmod.py:371-401) -- ROUND-2 CANDIDATE, OFF BY DEFAULT.
 //
-//   STATUS: written after the round-1 GPU budget was spent; it compiles, it has
-//   NOT run on a GPU yet.  Enabled only by SB_EIG_MIXED=1; nothing in the
-//   default path calls it and its test is opt-in (SB_TEST_UNVERIFIED=1).
+//   STATUS: written after the round-1 GPU budget was spent.  It has NOT run on a
+//   GPU yet; it does run, unchanged, under the CPU SIMT emulator of
+//   tests/host_emu (test_eig_mixed_kernel_on_host: reference eigenvalues to
+//   1.5e-7, fp32 restart path included).  Enabled only by SB_EIG_MIXED=1;
+//   nothing in the default path calls it; its GPU test is opt-in
+//   (SB_TEST_UNVERIFIED=1).
 //
 // Idea (numerics verified on the CPU, profiles/probe_mixed_precision.py and
 // r1_probe_mixed_precision.json): the streaming solver is bound by re-reading
@@ -21,7 +24,9 @@
 //   * up to 24 basis vectors (half2) in shared memory; if the solve needs more
 //     steps it restarts in plain fp32 mode and reports the Ritz value, i.e.
 //     exactly what thth_eig_kernel does.
+#ifndef SB_HOST_EMU
 #include <cuda_fp16.h>
+#endif
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
@@ -39,7 +44,11 @@ enum { EM_ST_INDEX_ERROR = 1, EM_ST_ZERO_START = 2, EM_ST_TOO_SMALL = 4,
 
 constexpr int EM_THREADS = 256;
 constexpr int EM_NW = EM_THREADS / 32;
+#ifdef SB_EM_NB
+constexpr int EM_NB = SB_EM_NB;      // tests/host_emu: few slots to exercise the fp32 restart
+#else
 constexpr int EM_NB = 24;            // basis slots
+#endif
 
 __global__ void __launch_bounds__(EM_THREADS)
 thth_eig_mixed_kernel(const float2* __restrict__ Mbase, const unsigned* __restrict__ Mbbase,
@@ -76,7 +85,7 @@ thth_eig_mixed_kernel(const float2* __restrict__ Mbase, const unsigned* __restri
     }
     if (tid == 0) {
         for (int i = 0; i < 2 * EM_NW; ++i) mbar_init(mbar + i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbarrier_init();
     }
     __syncthreads();
     const int ncol4 = (n + 1) >> 1;            // float4 / uint2 groups = two complex columns
@@ -177,7 +186,7 @@ thth_eig_mixed_kernel(const float2* __restrict__ Mbase, const unsigned* __restri
         }
         // the scratch aliases the stages: order these generic writes before the
         // next bulk copies (async proxy)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fence_proxy_async();
         __syncthreads();
     };
 
@@ -346,6 +355,7 @@ thth_eig_mixed_kernel(const float2* __restrict__ Mbase, const unsigned* __restri
     }
 }
 
+#ifndef SB_HOST_EMU
 // Returns 1 when the mixed-precision solver ran, 0 when it is not enabled /
 // not applicable (caller falls back), < 0 on error.
 int eig_mixed_launch(const float2* d_M, int ld, const int* d_nred, int e0, int nb,
@@ -370,5 +380,7 @@ int eig_mixed_launch(const float2* d_M, int ld, const int* d_nred, int e0, int n
     SB_LAUNCH_CHECK();
     return 1;
 }
+
+#endif  // SB_HOST_EMU
 
 }  // namespace sb

@@ -4,7 +4,9 @@
 #pragma once
 #include <float.h>
 
+#ifndef SB_HOST_EMU
 #include "common.cuh"
+#endif
 
 namespace sb {
 

@@ -1,6 +1,26 @@
 // cp.async.bulk (TMA, non-tensor) + mbarrier helpers shared by the eigen solvers.
 #pragma once
 
+#ifdef SB_HOST_EMU
+// tests/host_emu/simt.h: bulk copies complete synchronously, the 8-byte barrier
+// word holds the phase parity
+namespace sb {
+inline void mbar_init(unsigned long long* bar, int) { *bar = 0; }
+inline void mbar_expect_tx(unsigned long long*, unsigned) {}
+inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    std::memcpy(dst, src, bytes);
+    *bar ^= 1ull;
+}
+inline bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    if ((unsigned)(*bar & 1ull) != parity) return true;
+    emu::yield();
+    return false;
+}
+inline void fence_mbarrier_init() {}
+inline void fence_proxy_async() {}
+}  // namespace sb
+#else
+
 namespace sb {
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
@@ -29,4 +49,13 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
     return ok != 0;
 }
 
+__device__ __forceinline__ void fence_mbarrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// order generic-proxy shared-memory writes before later bulk copies (async proxy)
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 }  // namespace sb
+#endif  // SB_HOST_EMU

@@ -111,3 +111,58 @@ def test_chirp_ifft2_functors_on_host(n0, n1, c0, c1):
     lib.emu_ifft2_any(P(x), n0, n1, 0, c0, c1, 1.0, 0, 1, P(got))
     refc = np.fft.ifft2(np.conj(x))[:cc0, :cc1]
     assert np.abs(got - refc).max() < 2e-5 * np.abs(refc).max()
+
+
+def _triangles(golden_dir, etas_idx):
+    """theta-theta matrices as thth_build_kernel lays them out: [ld][ld] float2,
+    strict upper triangle valid, diagonal and columns >= n zero, the rest junk."""
+    from oracle import thth_oracle as TO
+    g = np.load(os.path.join(golden_dir, "thth_sample_64x150.npz"))
+    d0 = g["dspec2"] - g["dspec2"].mean()
+    CS = TO.conjugate_spectrum(d0, int(g["npad"]), 0.0)
+    mats = [TO.thth_redmap(CS, g["tau"], g["fd"], g["etas"][i], g["edges"])[0] for i in etas_idx]
+    ld = 32 * ((max(m.shape[0] for m in mats) + 31) // 32)
+    M = np.full((len(mats), ld, ld), np.nan + 1j * np.nan, dtype=np.complex64)   # junk everywhere
+    nred = np.zeros(len(mats), np.int32)
+    for e, A in enumerate(mats):
+        n = A.shape[0]
+        nred[e] = n
+        up = np.triu(A, 1).astype(np.complex64)
+        blk = np.zeros((n, ld), np.complex64)
+        blk[:, :n] = up
+        iu = np.triu_indices(n, 0)
+        rows = np.arange(n)[:, None]
+        cols = np.arange(ld)[None, :]
+        keep = cols >= rows                       # diagonal and everything right of it
+        M[e, :n][keep] = blk[keep]
+    return g, M, nred, ld
+
+
+@pytest.mark.parametrize("slots", [24, 3])
+def test_eig_mixed_kernel_on_host(golden_dir, slots):
+    """csrc/eig_mixed.cu under the SIMT emulator (tests/host_emu/simt.h): the
+    bf16 Lanczos iteration + fp32 Rayleigh quotient (slots=24) and the fp32
+    restart taken when the basis slots run out (slots=3) both reproduce the
+    reference eigenvalues of the tutorial chunk."""
+    src = os.path.join(EMU, "eig_mixed_emu.cpp")
+    out = os.path.join(EMU, "_build", "eig_mixed_emu_%d.so" % slots)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DSB_EM_NB=%d" % slots,
+                    "-x", "c++", src, "-o", out], check=True)
+    lib = ctypes.CDLL(out)
+    idx = [5, 37, 60]
+    g, M, nred, ld = _triangles(golden_dir, idx)
+    nb = len(idx)
+    eigs = np.zeros(nb)
+    status = np.zeros(nb, np.int32)
+    iters = np.zeros(nb, np.int32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib.emu_eig_mixed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_double, ctypes.c_double, ctypes.c_int]
+    Mc = np.ascontiguousarray(M)
+    lib.emu_eig_mixed(P(Mc), ld, P(nred), nb, P(eigs), P(status), P(iters), 2e-5, 2e-7, 256)
+    ref = g["eigs"][idx]
+    assert (status == 0).all(), status
+    assert (np.abs(eigs - ref) / ref).max() < 1e-5, (eigs, ref, iters)
+    assert iters.max() < 64
