@@ -1,5 +1,6 @@
 // Shared helpers for libscint_b200 (sm_100a only).
 #pragma once
+#ifndef SB_HOST_EMU            // tests/host_emu compiles the device code for the CPU
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -61,6 +62,19 @@ void count_launch();
             return SB_ERR_ARG;                                               \
         }                                                                    \
     } while (0)
+
+}  // namespace sb
+#endif  // SB_HOST_EMU
+
+// statically sized shared arrays: one per block on the device, one function-local
+// static shared by all fibers under tests/host_emu
+#ifdef SB_HOST_EMU
+#define SB_SHARED static
+#else
+#define SB_SHARED __shared__
+#endif
+
+namespace sb {
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

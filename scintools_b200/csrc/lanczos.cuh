@@ -4,9 +4,7 @@
 #pragma once
 #include <float.h>
 
-#ifndef SB_HOST_EMU
 #include "common.cuh"
-#endif
 
 namespace sb {
 

@@ -17,9 +17,7 @@
 // One thread per time column (coalesced over t), then a gather kernel
 //   out[nlam-1-k][t] = W_k0 y[i_k][t] + W_k1 y[i_k+1][t] + W_k2 M[i_k][t] + W_k3 M[i_k+1][t].
 // HBM-bound: ~7 passes over nf*nt*4 B.
-#ifndef SB_HOST_EMU            // tests/host_emu compiles the kernels for the CPU
 #include "common.cuh"
-#endif
 
 namespace sb {
 

@@ -19,6 +19,7 @@
 
 namespace sb {
 
+#ifndef SB_HOST_EMU
 // eig_cluster.cu: on-chip (cluster shared memory) solver for ld <= 512
 int eig_cluster_launch(const float2* d_M, int ld, int n_max, const int* d_nred, int e0,
                        int nb, double* d_eigs, int* d_status, int* d_iters, double tol,
@@ -28,6 +29,8 @@ int eig_cluster_launch(const float2* d_M, int ld, int n_max, const int* d_nred, 
 int eig_mixed_launch(const float2* d_M, int ld, const int* d_nred, int e0, int nb,
                      double* d_eigs, int* d_status, int* d_iters, double tol, double etol,
                      int max_iter, cudaStream_t st);
+
+#endif  // SB_HOST_EMU
 
 // status codes per eta (also in include/scint_b200.h)
 enum { ST_OK = 0, ST_INDEX_ERROR = 1, ST_ZERO_START = 2, ST_TOO_SMALL = 4,
@@ -93,8 +96,8 @@ __global__ void __launch_bounds__(256)
 thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nbatch,
                   int ld, const int* __restrict__ idx,
                   const int* __restrict__ nred, float2* __restrict__ M) {
-    __shared__ int ia[32], ib[32];
-    __shared__ double ta_[32], tb_[32];
+    SB_SHARED int ia[32], ib[32];
+    SB_SHARED double ta_[32], tb_[32];
     // eta is the FAST grid index: CTAs resident at the same time work on the
     // same 32x32 tile for ~900 neighbouring curvatures, whose gathers fall on
     // the same / adjacent CS rows for small |theta1^2 - theta2^2| (L2 reuse)
@@ -178,7 +181,7 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
     if (TMA) {
         if (tid == 0) {
             for (int i = 0; i < NW * NST; ++i) mbar_init(mbar + i, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            fence_mbarrier_init();
         }
     }
     unsigned gi = 0, gc = 0;             // ring producer / consumer counters
@@ -344,7 +347,7 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
                 for (int kk = 0; kk < NW; ++kk) { sx += part[kk * 512 + c].x; sy += part[kk * 512 + c].y; }
                 if (c < ld) u[c] = make_float2(sx, sy);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            fence_proxy_async();
             __syncthreads();
         } else {
         for (int cb = 0; cb < nchunk; ++cb) {
@@ -445,7 +448,7 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
                 for (int k = 0; k < NW; ++k) { sx += part[k * 512 + c].x; sy += part[k * 512 + c].y; }
                 if (cb * 512 + c < ld) u[cb * 512 + c] = make_float2(sx, sy);
             }
-            if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (TMA) fence_proxy_async();
             __syncthreads();
         }
         }
@@ -546,6 +549,7 @@ __global__ void thth_map_kernel(ThthGeom g, double eta, int hermitian,
     }
 }
 
+#ifndef SB_HOST_EMU
 // --------------------------------------------------------------------------
 // host drivers
 // --------------------------------------------------------------------------
@@ -679,5 +683,7 @@ int thth_map(const ThthGeom& g, double eta, int hermitian, float2* d_out,
     SB_LAUNCH_CHECK();
     return SB_OK;
 }
+
+#endif  // SB_HOST_EMU
 
 }  // namespace sb

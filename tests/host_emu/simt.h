@@ -8,6 +8,8 @@
 #pragma once
 #include <ucontext.h>
 
+#include <math.h>
+
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -37,6 +39,18 @@ static inline float __uint_as_float(unsigned u) { float x; std::memcpy(&x, &u, 4
 static inline double __longlong_as_double(long long v) { double x; std::memcpy(&x, &v, 8); return x; }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 static inline int __ffs(unsigned v) { return v ? __builtin_ffs((int)v) : 0; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+// compile the emulation with -ffp-contract=off: these are single IEEE operations
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+// one fiber runs at a time: plain read-modify-write is atomic here
+static inline int atomicOr(int* p, int v) { int o = *p; *p = o | v; return o; }
+static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 using std::isfinite;
 
 namespace emu {
@@ -49,6 +63,7 @@ struct Warp {
 };
 struct Block {
     int nthreads = 0, cur = 0;
+    Dim3 bdim{1, 1, 1}, gdim{1, 1, 1};
     std::vector<Fiber> th;
     ucontext_t sched;
     int bar_count = 0;
@@ -59,7 +74,11 @@ struct Block {
 };
 inline Block*& B() { static Block* b = nullptr; return b; }
 inline void yield() { Block* b = B(); swapcontext(&b->th[b->cur].ctx, &b->sched); }
-inline Dim3 thread_idx() { return Dim3{(unsigned)B()->cur, 0, 0}; }
+inline Dim3 thread_idx() {
+    const Block* b = B();
+    return Dim3{(unsigned)b->cur % b->bdim.x, ((unsigned)b->cur / b->bdim.x) % b->bdim.y,
+                (unsigned)b->cur / (b->bdim.x * b->bdim.y)};
+}
 inline Dim3 block_idx() { return B()->bidx; }
 inline void trampoline() {
     Block* b = B();
@@ -68,12 +87,19 @@ inline void trampoline() {
     swapcontext(&b->th[b->cur].ctx, &b->sched);
 }
 // run one thread block of `nthreads` threads executing `body`
+inline void run_block(Dim3 bdim, Dim3 bidx, Dim3 gdim, std::function<void()> body);
 inline void run_block(int nthreads, unsigned block_x, std::function<void()> body) {
+    run_block(Dim3{(unsigned)nthreads, 1, 1}, Dim3{block_x, 0, 0}, Dim3{block_x + 1, 1, 1}, body);
+}
+inline void run_block(Dim3 bdim, Dim3 bidx, Dim3 gdim, std::function<void()> body) {
+    const int nthreads = (int)(bdim.x * bdim.y * bdim.z);
     Block blk;
+    blk.bdim = bdim;
+    blk.gdim = gdim;
     blk.nthreads = nthreads;
     blk.th.resize(nthreads);
     blk.warps.resize((nthreads + 31) / 32);
-    blk.bidx = Dim3{block_x, 0, 0};
+    blk.bidx = bidx;
     blk.body = body;
     B() = &blk;
     for (int i = 0; i < nthreads; ++i) {
@@ -131,8 +157,8 @@ template <typename T> inline T from_bits(unsigned long long u) {
 
 #define threadIdx (emu::thread_idx())
 #define blockIdx (emu::block_idx())
-#define blockDim (emu::Dim3{(unsigned)emu::B()->nthreads, 1, 1})
-#define gridDim (emu::Dim3{1, 1, 1})
+#define blockDim (emu::B()->bdim)
+#define gridDim (emu::B()->gdim)
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline void __syncthreads() { emu::block_barrier(); }
@@ -150,6 +176,12 @@ template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
     emu::warp_gather(emu::to_bits(v), all);
     return emu::from_bits<T>(all[((int)(emu::B()->cur & 31)) ^ m]);
 }
+static inline bool __any_sync(unsigned, bool p) {
+    unsigned long long all[32];
+    emu::warp_gather(p ? 1ull : 0ull, all);
+    for (int i = 0; i < 32; ++i) if (all[i]) return true;
+    return false;
+}
 static inline unsigned __ballot_sync(unsigned, bool p) {
     unsigned long long all[32];
     emu::warp_gather(p ? 1ull : 0ull, all);
@@ -157,18 +189,6 @@ static inline unsigned __ballot_sync(unsigned, bool p) {
     for (int i = 0; i < 32; ++i) r |= (unsigned)(all[i] & 1ull) << i;
     return r;
 }
-
-// ---- what csrc/common.cuh provides to the kernels --------------------------
-namespace sb {
-static inline float warp_sum(float v) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-static inline double warp_sum(double v) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-}  // namespace sb
 
 // ---- cuda_fp16.h subset: IEEE half, round to nearest even ------------------
 struct __half2 { unsigned short x, y; };

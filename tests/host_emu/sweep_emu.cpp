@@ -1,0 +1,76 @@
+// CPU run of the DEFAULT curvature-sweep device code of csrc/thth.cu under the
+// SIMT emulator: thth_prep_kernel (crop mask + compaction), thth_indexerr_kernel,
+// thth_build_kernel (gather into the strict upper triangle) and
+// thth_eig_kernel<256, TMA, 2> (bulk-copy ring + Lanczos), sources unchanged,
+// launch geometry as in sb::eta_sweep.  Optionally the triangle goes through
+// csrc/eig_mixed.cu instead of thth_eig_kernel (mixed != 0).
+// TEST INFRASTRUCTURE (tests/test_host_emulation.py).
+#define SB_HOST_EMU 1
+#include "simt.h"
+
+#include <float.h>
+#include <limits.h>
+
+#include <type_traits>
+
+namespace sb {
+alignas(128) unsigned char smem_raw[256 * 1024];
+}
+#include "../../scintools_b200/csrc/thth.cu"
+#include "../../scintools_b200/csrc/eig_mixed.cu"
+
+extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, long long cs_pitch,
+                             int cs_half, double tau0, double dtau, double tau_absmax, double fd0,
+                             double dfd, double fd_half, const double* th, int n_th, int coherent,
+                             const double* etas, int neta, double tol, int max_iter, int mixed,
+                             double* eigs, int* status, int* nred, int* iters) {
+    using namespace sb;
+    ThthGeom g;
+    g.cs = reinterpret_cast<const float2*>(cs);
+    g.ntau = ntau; g.nfd = nfd;
+    g.tau0 = tau0; g.dtau = dtau; g.half_dtau = dtau / 2; g.tau_absmax = tau_absmax;
+    g.fd0 = fd0; g.dfd = dfd; g.half_dfd = dfd / 2; g.fd_half = fd_half;
+    g.inv_dtau = 1.0 / dtau; g.inv_dfd = 1.0 / dfd;
+    g.th = th; g.n = n_th; g.coherent = coherent; g.cs_half = cs_half;
+    g.cs_pitch = cs_half ? cs_pitch : (cs_pitch > 0 ? cs_pitch : nfd);
+    const int ld = (n_th + 31) / 32 * 32;
+    if (ld > 512) return -1;
+    std::vector<int> idx((size_t)neta * ld, 0);
+    std::vector<float2> M((size_t)neta * ld * ld);
+    std::memset(M.data(), 0xff, M.size() * sizeof(float2));          // NaN junk, like a fresh slab
+    for (int e = 0; e < neta; ++e) status[e] = 0;
+    for (int e = 0; e < neta; ++e)
+        emu::run_block(emu::Dim3{32, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
+                       emu::Dim3{(unsigned)neta, 1, 1},
+                       [&]() { thth_prep_kernel(g, etas, neta, ld, idx.data(), nred); });
+    for (int e = 0; e < neta; ++e)
+        for (unsigned bx = 0; bx < 4; ++bx)
+            emu::run_block(emu::Dim3{256, 1, 1}, emu::Dim3{bx, (unsigned)e, 0},
+                           emu::Dim3{4, (unsigned)neta, 1},
+                           [&]() { thth_indexerr_kernel(g, etas, status); });
+    const int T = ld / 32, npairs = T * (T + 1) / 2;
+    const unsigned gx = (unsigned)((neta + SB_BUILD_EB - 1) / SB_BUILD_EB);
+    for (unsigned bx = 0; bx < gx; ++bx)
+        for (unsigned by = 0; by < (unsigned)npairs; ++by)
+            emu::run_block(emu::Dim3{32, 8, 1}, emu::Dim3{bx, by, 0}, emu::Dim3{gx, (unsigned)npairs, 1},
+                           [&]() { thth_build_kernel(g, etas, 0, neta, ld, idx.data(), nred, M.data()); });
+    if (max_iter <= 0 || max_iter > SB_LANCZOS_MAXIT) max_iter = SB_LANCZOS_MAXIT;
+    if (mixed) {
+        std::vector<unsigned> Mb(M.size());
+        for (size_t i = 0; i < M.size(); ++i) Mb[i] = bf16_bits(M[i].x) | (bf16_bits(M[i].y) << 16);
+        for (int e = 0; e < neta; ++e)
+            emu::run_block(emu::Dim3{(unsigned)EM_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
+                           emu::Dim3{(unsigned)neta, 1, 1}, [&]() {
+                               thth_eig_mixed_kernel(M.data(), Mb.data(), ld, nred, 0, eigs, status,
+                                                     iters, tol, 2e-7, max_iter);
+                           });
+    } else {
+        for (int e = 0; e < neta; ++e)
+            emu::run_block(emu::Dim3{256, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
+                           emu::Dim3{(unsigned)neta, 1, 1}, [&]() {
+                               thth_eig_kernel<256, true, 2>(M.data(), ld, nred, 0, eigs, status,
+                                                             iters, tol, 2e-7, max_iter, neta);
+                           });
+    }
+    return 0;
+}

@@ -166,3 +166,49 @@ def test_eig_mixed_kernel_on_host(golden_dir, slots):
     assert (status == 0).all(), status
     assert (np.abs(eigs - ref) / ref).max() < 1e-5, (eigs, ref, iters)
     assert iters.max() < 64
+
+
+@pytest.mark.parametrize("mixed", [0, 1])
+def test_default_sweep_kernels_on_host(golden_dir, mixed):
+    """The DEFAULT device code of the curvature sweep (csrc/thth.cu:
+    thth_prep_kernel, thth_indexerr_kernel, thth_build_kernel,
+    thth_eig_kernel<256, TMA, 2>) under the SIMT emulator, launch geometry as in
+    sb::eta_sweep, against the reference: cropped sizes bit-exact, eigenvalues to
+    1e-5.  mixed=1 routes the same triangle through csrc/eig_mixed.cu."""
+    from oracle import thth_oracle as TO
+    src = os.path.join(EMU, "sweep_emu.cpp")
+    out = os.path.join(EMU, "_build", "sweep_emu.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    csrc = os.path.join(ROOT, "scintools_b200", "csrc")
+    newest = max(os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc))
+    if not os.path.exists(out) or os.path.getmtime(out) < max(newest, os.path.getmtime(src)):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC",
+                        "-x", "c++", src, "-o", out], check=True)
+    lib = ctypes.CDLL(out)
+    g = np.load(os.path.join(golden_dir, "thth_sample_64x150.npz"))
+    d0 = g["dspec2"] - g["dspec2"].mean()
+    CS = TO.conjugate_spectrum(d0, int(g["npad"]), 0.0)
+    cs32 = np.ascontiguousarray(CS.astype(np.complex64))
+    tau, fd = g["tau"], g["fd"]
+    th = TO.theta_centres(g["edges"])
+    sel = [5, 37, 60, 90]
+    etas = np.ascontiguousarray(g["etas"][sel])
+    neta = len(sel)
+    eigs = np.zeros(neta)
+    status = np.zeros(neta, np.int32)
+    nred = np.zeros(neta, np.int32)
+    iters = np.zeros(neta, np.int32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    c_ll, c_d, c_i, vp = ctypes.c_longlong, ctypes.c_double, ctypes.c_int, ctypes.c_void_p
+    lib.emu_eta_sweep.argtypes = [vp, c_ll, c_ll, c_ll, c_i, c_d, c_d, c_d, c_d, c_d, c_d, vp, c_i,
+                                  c_i, vp, c_i, c_d, c_i, c_i, vp, vp, vp, vp]
+    rc = lib.emu_eta_sweep(P(cs32), CS.shape[0], CS.shape[1], CS.shape[1], 0, float(tau[0]),
+                           float(np.diff(tau).mean()), float(abs(tau.max())), float(fd[0]),
+                           float(np.diff(fd).mean()), float(abs(fd.max()) / 2), P(th), len(th), 1,
+                           P(etas), neta, 2e-5, 0, mixed, P(eigs), P(status), P(nred), P(iters))
+    assert rc == 0
+    want_n = [int(TO.th_points(tau, fd, e, g["edges"]).sum()) for e in etas]
+    assert list(nred) == want_n
+    assert (status == 0).all()
+    ref = g["eigs"][sel]
+    assert (np.abs(eigs - ref) / ref).max() < 1e-5, (eigs, ref)
