@@ -17,9 +17,11 @@ def _build(name):
     src = os.path.join(EMU, name + ".cpp")
     out = os.path.join(EMU, "_build", name + ".so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    if not os.path.exists(out) or os.path.getmtime(out) < max(
-            os.path.getmtime(src),
-            os.path.getmtime(os.path.join(ROOT, "scintools_b200", "csrc", "scale_dyn.cu"))):
+    csrc = os.path.join(ROOT, "scintools_b200", "csrc")
+    newest = max([os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc)] +
+                 [os.path.getmtime(os.path.join(EMU, f)) for f in os.listdir(EMU)
+                  if f.endswith((".cpp", ".h"))])
+    if not os.path.exists(out) or os.path.getmtime(out) < newest:
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC",
                         "-x", "c++", src, "-o", out], check=True)
     return ctypes.CDLL(out)
