@@ -318,6 +318,7 @@ __global__ void thin_map_kernel(ThinGeom t, double e1, double e2, float2* __rest
     }
 }
 
+#ifndef SB_HOST_EMU
 int thin_map(const ThinGeom& t, double e1, double e2, float2* d_out, int* d_err,
              cudaStream_t st) {
     SB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
@@ -375,5 +376,7 @@ int thin_sweep(const ThinGeom& t, const double* d_eta1, const double* d_eta2, in
     }
     return SB_OK;
 }
+
+#endif  // SB_HOST_EMU
 
 }  // namespace sb

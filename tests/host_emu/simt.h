@@ -46,6 +46,8 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 // one fiber runs at a time: plain read-modify-write is atomic here
 static inline int atomicOr(int* p, int v) { int o = *p; *p = o | v; return o; }

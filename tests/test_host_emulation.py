@@ -214,3 +214,41 @@ def test_default_sweep_kernels_on_host(golden_dir, mixed):
     assert (status == 0).all()
     ref = g["eigs"][sel]
     assert (np.abs(eigs - ref) / ref).max() < 1e-5, (eigs, ref)
+
+
+def test_thin_kernels_on_host(golden_dir):
+    """csrc/thin.cu (prep, index check, two-curvature gather, sigma_max by
+    Lanczos on A^H A) under the SIMT emulator against the reference's
+    singularvalue_calc values (tests/golden/thth_thin_64x150.npz)."""
+    from oracle import thth_oracle as TO
+    lib = _build("thin_emu")
+    g = np.load(os.path.join(golden_dir, "thth_sample_64x150.npz"))
+    t = np.load(os.path.join(golden_dir, "thth_thin_64x150.npz"))
+    d0 = g["dspec2"] - g["dspec2"].mean()
+    CS = TO.conjugate_spectrum(d0, int(g["npad"]), 0.0)
+    cs32 = np.ascontiguousarray(CS.astype(np.complex64))
+    tau, fd = g["tau"], g["fd"]
+    e1, e2 = t["edges"], t["arc"]
+    th1 = np.ascontiguousarray((e1[1:] + e1[:-1]) / 2)
+    th2 = np.ascontiguousarray((e2[1:] + e2[:-1]) / 2)
+    sel = [2, 8, 15]
+    etas = np.ascontiguousarray(t["etas"][sel])
+    neta = len(sel)
+    sv = np.zeros(neta)
+    status = np.zeros(neta, np.int32)
+    n1r = np.zeros(neta, np.int32)
+    n2r = np.zeros(neta, np.int32)
+    iters = np.zeros(neta, np.int32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    c_ll, c_d, c_i, vp = ctypes.c_longlong, ctypes.c_double, ctypes.c_int, ctypes.c_void_p
+    lib.emu_thin_sweep.argtypes = [vp, c_ll, c_ll, c_d, c_d, c_d, c_d, c_d, vp, c_i, vp, c_i, c_d,
+                                   c_i, vp, vp, c_i, c_d, c_i, vp, vp, vp, vp, vp]
+    rc = lib.emu_thin_sweep(P(cs32), CS.shape[0], CS.shape[1], float(tau[1]),
+                            float(np.diff(tau).mean()), float(tau.max()), float(fd[1]),
+                            float(np.diff(fd).mean()), P(th1), len(th1), P(th2), len(th2),
+                            float(t["cut"]), 0, P(etas), P(etas), neta, 2e-5, 0, P(sv), P(status),
+                            P(n1r), P(n2r), P(iters))
+    assert rc == 0
+    assert (status == 0).all(), status
+    ref = t["sv"][sel]
+    assert (np.abs(sv - ref) / ref).max() < 1e-5, (sv, ref)
