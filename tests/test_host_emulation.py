@@ -252,3 +252,56 @@ def test_thin_kernels_on_host(golden_dir):
     assert (status == 0).all(), status
     ref = t["sv"][sel]
     assert (np.abs(sv - ref) / ref).max() < 1e-5, (sv, ref)
+
+
+@pytest.mark.parametrize("nedge,half,coherent,mixed", [(42, 0, 1, 0), (72, 1, 1, 0), (34, 0, 0, 0),
+                                                      (66, 1, 1, 1)])
+def test_default_sweep_kernels_on_host_random(nedge, half, coherent, mixed):
+    """Random small spectra through the emulated sweep kernels: full and
+    Hermitian-half CS layouts, incoherent mode, odd / cropped theta grids,
+    curvatures that fail (NaN) -- against the numpy oracle."""
+    from oracle import thth_oracle as TO
+    lib = _build("sweep_emu")
+    rng = np.random.default_rng(nedge)
+    nf, nt, npad = 16, 64, 1
+    d = rng.normal(size=(nf, nt))
+    d -= d.mean()
+    t = np.arange(nt) * 10.0
+    f = 1400 + 0.2 * np.arange(nf)
+    fd = TO.fft_axis(t, "mHz", npad)
+    tau = TO.fft_axis(f, "us", npad)
+    CS = TO.conjugate_spectrum(d, npad, 0.0)
+    src = CS if coherent else np.abs(CS)
+    edges = np.linspace(-22, 22, nedge)
+    etas = np.ascontiguousarray(np.array([0.002, 0.006, 0.02, 5.0]))
+    ref = TO.eta_sweep(src, tau, fd, etas, edges)
+    if half:        # unshifted fd >= 0 columns of the fftshifted array, like DeviceCS
+        nfd = CS.shape[1]
+        cols = np.fft.ifftshift(CS, axes=1)[:, :nfd // 2 + 1]
+        pitch = nfd // 2 + 16
+        buf = np.zeros((CS.shape[0], pitch), np.complex64)
+        buf[:, :nfd // 2 + 1] = cols
+    else:
+        pitch = CS.shape[1]
+        buf = np.ascontiguousarray(CS.astype(np.complex64))
+    th = TO.theta_centres(edges)
+    neta = len(etas)
+    eigs = np.zeros(neta)
+    status = np.zeros(neta, np.int32)
+    nred = np.zeros(neta, np.int32)
+    iters = np.zeros(neta, np.int32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    c_ll, c_d, c_i, vp = ctypes.c_longlong, ctypes.c_double, ctypes.c_int, ctypes.c_void_p
+    lib.emu_eta_sweep.argtypes = [vp, c_ll, c_ll, c_ll, c_i, c_d, c_d, c_d, c_d, c_d, c_d, vp, c_i,
+                                  c_i, vp, c_i, c_d, c_i, c_i, vp, vp, vp, vp]
+    rc = lib.emu_eta_sweep(P(buf), CS.shape[0], CS.shape[1], pitch, half, float(tau[0]),
+                           float(np.diff(tau).mean()), float(abs(tau.max())), float(fd[0]),
+                           float(np.diff(fd).mean()), float(abs(fd.max()) / 2), P(th), len(th),
+                           coherent, P(etas), neta, 2e-5, 0, mixed, P(eigs), P(status), P(nred),
+                           P(iters))
+    assert rc == 0
+    want_n = [int(TO.th_points(tau, fd, e, edges).sum()) for e in etas]
+    assert list(nred) == want_n
+    assert np.array_equal(np.isnan(eigs), np.isnan(ref)), (eigs, ref, status)
+    ok = ~np.isnan(ref)
+    assert (np.abs(eigs[ok] - ref[ok]) / ref[ok]).max() < 1e-5, (eigs, ref)
