@@ -8,7 +8,9 @@
 #include <math.h>
 #include <stdlib.h>
 
+#ifndef SB_HOST_EMU            // tests/host_emu runs the scatter / eigenpair kernels on the CPU
 #include "fft_generic.cuh"
+#endif
 #include "lanczos.cuh"
 
 namespace sb {
@@ -101,6 +103,7 @@ __global__ void rev_finalise_kernel(RevGeom g, float2* __restrict__ acc,
     }
 }
 
+#ifndef SB_HOST_EMU
 int rev_map(const float2* thth, int n, const double* th_dev, double eta, double tau0,
             double dtau, int ntau, double fd0, double dfd, int nfd, int hermitian,
             float2* recov, cudaStream_t st) {
@@ -126,6 +129,8 @@ int rev_map(const float2* thth, int n, const double* th_dev, double eta, double 
     SB_LAUNCH_CHECK();
     return SB_OK;
 }
+
+#endif  // SB_HOST_EMU
 
 // --------------------------------------------------------------------------
 // Top eigenpair (largest algebraic) of one full Hermitian complex matrix:
@@ -303,6 +308,7 @@ herm_eigvec_kernel(const float2* __restrict__ A, int n, int ld, float2* __restri
     }
 }
 
+#ifndef SB_HOST_EMU
 int herm_eigvec(const float2* A, int n, int ld, double tol, int max_iter, double* w_dev,
                 float2* V_dev, int* info_dev, cudaStream_t st) {
     if (!(tol > 0.0)) tol = 1e-7;
@@ -499,5 +505,7 @@ int gerchberg_saxton(float2* W, const float* amp, const unsigned char* rowmask, 
     }
     return SB_OK;
 }
+
+#endif  // SB_HOST_EMU
 
 }  // namespace sb

@@ -305,3 +305,38 @@ def test_default_sweep_kernels_on_host_random(nedge, half, coherent, mixed):
     assert np.array_equal(np.isnan(eigs), np.isnan(ref)), (eigs, ref, status)
     ok = ~np.isnan(ref)
     assert (np.abs(eigs[ok] - ref[ok]) / ref[ok]).max() < 1e-5, (eigs, ref)
+
+
+def test_retrieval_kernels_on_host(golden_dir):
+    """csrc/retrieval.cu under the SIMT emulator: the histogram2d scatter
+    (bit-exact bins) and the top-eigenpair kernel against the reference's
+    rev_map / modeler outputs (tests/golden/retrieval_64x128.npz)."""
+    from oracle import thth_oracle as TO
+    lib = _build("retrieval_emu")
+    g = np.load(os.path.join(golden_dir, "retrieval_64x128.npz"))
+    tau, fd, eta = g["tau"], g["fd"], float(g["eta"])
+    th = TO.theta_centres(g["edges_red"])
+    n = len(th)
+    rng = np.random.default_rng(int(g["tt_seed"]))
+    tt = (rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))).astype(np.complex64)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    c_d, c_i, vp = ctypes.c_double, ctypes.c_int, ctypes.c_void_p
+    lib.emu_rev_map.argtypes = [vp, c_i, vp, c_d, c_d, c_d, c_i, c_d, c_d, c_i, c_i, vp]
+    for herm, key in ((1, "rv_h"), (0, "rv_n")):
+        out = np.zeros((len(tau), len(fd)), np.complex64)
+        lib.emu_rev_map(P(np.ascontiguousarray(tt)), n, P(th), eta, float(tau[0]),
+                        float(tau[1] - tau[0]), len(tau), float(fd[0]), float(fd[1] - fd[0]),
+                        len(fd), herm, P(out))
+        ref = g[key]
+        assert np.array_equal(out == 0, ref == 0)
+        assert np.abs(out - ref).max() < 1e-5 * np.abs(ref).max()
+    A = np.ascontiguousarray(g["thth_red"].astype(np.complex64))
+    w = np.zeros(1)
+    V = np.zeros(n, np.complex64)
+    info = np.zeros(2, np.int32)
+    lib.emu_herm_eigvec.argtypes = [vp, c_i, c_i, c_d, c_i, vp, vp, vp]
+    lib.emu_herm_eigvec(P(A), n, n, 1e-7, 96, P(w), P(V), P(info))
+    assert w[0] == pytest.approx(float(g["w"]), rel=1e-5)
+    Vr = g["V"].astype(complex)
+    z = np.vdot(V, Vr)
+    assert np.abs(V * (z / abs(z)) - Vr).max() < 3e-5 * np.abs(Vr).max()
