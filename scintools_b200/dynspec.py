@@ -551,10 +551,13 @@ class Dynspec:
         self.ththeta = A / self.fref ** 2
         self.ththetaerr = A_err / self.fref ** 2
 
-    def thetatheta_chunks(self, verbose=False, pool=None, memmap=False):
+    def thetatheta_chunks(self, verbose=False, pool=None, memmap=False, group=None):
         """Phase retrieval on every half-overlapping retrieval chunk
         (reference dynspec.py:1765-1828) -> self.chunks [ncf_ret][nct_ret][cwf][cwt].
-        ``pool`` must be None (see fit_thetatheta); memmap is not supported."""
+        ``pool`` must be None (see fit_thetatheta); memmap is not supported.
+        Under torch.distributed (one process per GPU) the chunks are
+        block-partitioned over the ranks of ``group`` and all-gathered, the
+        counterpart of the reference's ``pool.map`` over chunks (:1815-1828)."""
         if pool is not None:
             raise ValueError("thetatheta_chunks on the B200 path takes pool=None "
                              "(CUDA is not fork-safe)")
@@ -562,8 +565,8 @@ class Dynspec:
             raise NotImplementedError("memmap chunk storage is outside the B200 path")
         if not hasattr(self, "ththeta"):
             self.fit_thetatheta(verbose=verbose)
-        self.chunks = np.zeros((self.ncf_ret, self.nct_ret, self.cwf, self.cwt),
-                               dtype=complex)
+        from . import sharding
+        pars = []
         for cf in range(self.ncf_ret):
             fs = slice(cf * (self.cwf // 2), cf * (self.cwf // 2) + self.cwf)
             freq2 = np.copy(self.freqs[fs]).astype(np.float64)
@@ -575,10 +578,17 @@ class Dynspec:
                 dspec2 = np.copy(self.dyn[fs, ts]).astype(np.float64)
                 dspec2 -= np.nanmean(dspec2)
                 dspec2 = np.nan_to_num(dspec2)
-                res = thth.single_chunk_retrieval(
-                    (dspec2, self.edges * (freq / self.fref), time2, freq2, eta, ct, cf,
-                     self.npad, self.thth_tau_mask, verbose))
-                self.chunks[cf, ct, :, :] = res[0]
+                pars.append((dspec2, self.edges * (freq / self.fref), time2, freq2, eta, ct, cf,
+                             self.npad, self.thth_tau_mask, verbose))
+
+        def one(p):
+            e = thth.single_chunk_retrieval(p)[0]
+            return np.concatenate((e.real.ravel(), e.imag.ravel()))
+
+        L = self.cwf * self.cwt
+        flat = sharding.sharded_map(one, pars, 2 * L, group)
+        self.chunks = (flat[:, :L] + 1j * flat[:, L:]).reshape(
+            self.ncf_ret, self.nct_ret, self.cwf, self.cwt)
 
     def calc_wavefield(self, verbose=False, pool=None, gs=False, memmap=False,
                        niter=1):

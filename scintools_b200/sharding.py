@@ -67,3 +67,34 @@ def sharded_items(items, group=None):
     rank, world = world_info(group)
     lo, hi = block_range(len(items), rank, world)
     return list(items[lo:hi])
+
+
+def sharded_map(fn, items, width, group=None, device=None):
+    """Apply ``fn(item) -> float64 array of length width`` to this rank's block
+    of ``items`` and all-gather the rows: every rank gets the [len(items)][width]
+    array.  Used for the independent retrieval chunks of
+    Dynspec.thetatheta_chunks (the reference's pool.map over chunks,
+    scintools/dynspec.py:1815-1828); one collective, rows padded to whole blocks."""
+    import torch
+    import torch.distributed as dist
+    rank, world = world_info(group)
+    n = len(items)
+    lo, hi = block_range(n, rank, world)
+    local = np.full((hi - lo, width), np.nan)
+    for k, i in enumerate(range(lo, hi)):
+        local[k] = np.asarray(fn(items[i]), dtype=np.float64).reshape(width)
+    if world == 1:
+        return local
+    rows = -(-n // world)
+    buf = torch.full((rows, width), float("nan"), dtype=torch.float64)
+    buf[:hi - lo] = torch.from_numpy(local)
+    if device is not None:
+        buf = buf.to(device)
+    out = torch.empty((world * rows, width), dtype=torch.float64, device=buf.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    out = out.cpu().numpy().reshape(world, rows, width)
+    parts = []
+    for r in range(world):
+        a, b = block_range(n, r, world)
+        parts.append(out[r, :b - a])
+    return np.concatenate(parts, axis=0)

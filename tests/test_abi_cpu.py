@@ -149,3 +149,40 @@ def test_spline_tables_match_scipy(golden_dir):
     lamdyn = np.flipud(out)
     assert lamdyn.shape == g["lamdyn"].shape
     assert np.abs(lamdyn - g["lamdyn"]).max() < 1e-12 * np.abs(g["lamdyn"]).max()
+
+
+def test_thetatheta_chunks_plumbing(monkeypatch):
+    """Host logic of Dynspec.thetatheta_chunks / calc_wavefield with the device
+    call replaced: chunk order, slices, curvature scaling, mosaic shape."""
+    import numpy as np
+    import scintools_b200 as sb
+    from scintools_b200 import ththmod
+    rng = np.random.default_rng(0)
+    nf, nt = 64, 128
+    dyn = rng.exponential(1.0, (nf, nt))
+    t = np.arange(nt) * 20.0
+    f = 1400.0 + np.arange(nf) * 0.05
+    ds = sb.Dynspec(dyn=sb.BasicDyn(dyn, times=t, freqs=f, dt=20.0, df=0.05), verbose=False)
+    ds.prep_thetatheta(cwf=32, cwt=64, eta_min=15.0, eta_max=60.0, nedge=96, edges_lim=8.0,
+                       fw=0.2, npad=3)
+    ds.ththeta = 30.0
+    seen = []
+
+    def fake(params):
+        d2, edges, time2, freq2, eta, idx_t, idx_f, npad, mask, verbose = params
+        seen.append((idx_f, idx_t, float(eta), float(freq2.mean()), float(time2[0])))
+        return (np.full(d2.shape, idx_f + 10 * idx_t + 1j * d2[0, 0]), idx_f, idx_t)
+
+    monkeypatch.setattr(ththmod, "single_chunk_retrieval", fake)
+    ds.calc_wavefield()
+    assert ds.chunks.shape == (3, 3, 32, 64)
+    assert [(s[0], s[1]) for s in seen] == [(cf, ct) for cf in range(3) for ct in range(3)]
+    for cf in range(3):
+        for ct in range(3):
+            fs = slice(cf * 16, cf * 16 + 32)
+            ts = slice(ct * 32, ct * 32 + 64)
+            d2 = dyn[fs, ts] - dyn[fs, ts].mean()
+            assert ds.chunks[cf, ct, 0, 0] == cf + 10 * ct + 1j * d2[0, 0]
+    fm = f[16:48].mean()
+    assert seen[3][2] == 30.0 * (ds.fref / fm) ** 2 and seen[3][3] == fm
+    assert ds.wavefield.shape == (64, 128)

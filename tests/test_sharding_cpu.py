@@ -33,7 +33,8 @@ def _worker(rank, world, port, n, q):
 
     full = sharding.sharded_eta_sweep(fake_sweep, etas)
     seeds = sharding.sharded_items(list(range(7)))
-    q.put((rank, full, calls, seeds))
+    rows = sharding.sharded_map(lambda i: np.arange(6) + 10.0 * i, list(range(5)), 6)
+    q.put((rank, full, calls, seeds, rows))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,7 +65,9 @@ def test_sharded_sweep_world2_matches_single():
     want = np.sqrt(etas) * 3.0
     want[etas > 9.0] = np.nan
     seeds_all = []
-    for rank, full, calls, seeds in sorted(res, key=lambda t: t[0]):
+    want_rows = np.arange(6)[None, :] + 10.0 * np.arange(5)[:, None]
+    for rank, full, calls, seeds, rows in sorted(res, key=lambda t: t[0]):
+        assert np.array_equal(rows, want_rows)       # retrieval-chunk style gather: 3 + 2 rows
         assert np.array_equal(np.isnan(full), np.isnan(want))
         assert np.allclose(full[~np.isnan(want)], want[~np.isnan(want)], rtol=0, atol=0)
         assert calls == [51] if rank == 0 else calls == [50]
