@@ -18,6 +18,11 @@
 // n = 511 (bf16 Ritz value alone: 1.7e-4), same step counts.  Traffic per
 // curvature: m * 0.52 MB + 1.04 MB instead of m * 1.04 MB (m ~ 18).
 //
+// Two variants (template), to be A/B-timed in round 2:
+//   <2, false>  SB_EIG_MIXED=1: 2 bf16 stages per warp, basis (24 x fp16) in shared memory
+//   <4, true>   SB_EIG_MIXED=2: 4 bf16 stages per warp (as many bytes in flight as the
+//               fp32 kernel, twice the elements), basis (64 slots) in global memory (L2)
+//
 // Kernel = the generic TMA row loop of thth_eig_kernel with
 //   * 2 x 2 KB bf16 stages per warp (bulk copies from column (a+1) & ~3),
 //     the same 4 KB re-used as ONE fp32 stage for the final pass;
@@ -46,30 +51,38 @@ constexpr int EM_THREADS = 256;
 constexpr int EM_NW = EM_THREADS / 32;
 #ifdef SB_EM_NB
 constexpr int EM_NB = SB_EM_NB;      // tests/host_emu: few slots to exercise the fp32 restart
+constexpr int EM_NBG = SB_EM_NB;
 #else
-constexpr int EM_NB = 24;            // basis slots
+constexpr int EM_NB = 24;            // basis slots in shared memory
+constexpr int EM_NBG = 64;           // basis slots in global memory
 #endif
 
+template <int NSB, bool BG>
 __global__ void __launch_bounds__(EM_THREADS)
 thth_eig_mixed_kernel(const float2* __restrict__ Mbase, const unsigned* __restrict__ Mbbase,
                       int ld, const int* __restrict__ nred, int eta0,
                       double* __restrict__ eigs, int* __restrict__ status,
-                      int* __restrict__ iters, double tol, double etol, int max_iter) {
+                      int* __restrict__ iters, double tol, double etol, int max_iter,
+                      __half2* __restrict__ gbasis) {
+    constexpr int NSF = NSB / 2;               // fp32 stages of 4 KB in the same ring
+    constexpr int NB = BG ? EM_NBG : EM_NB;    // basis slots
+    constexpr int RING = NSB * 2048;           // ring bytes per warp
     extern __shared__ __align__(128) unsigned char smem_raw[];
     LanczosShared& S = *reinterpret_cast<LanczosShared*>(smem_raw);
     float2* v = reinterpret_cast<float2*>(smem_raw + sizeof(LanczosShared));
     float2* vp = v + ld;
     float2* w = vp + ld;          // row sums, then the new Lanczos vector
     float2* u = w + ld;           // column sums
-    unsigned char* ring = reinterpret_cast<unsigned char*>(u + ld);     // [NW][4096]
-    float2* part = reinterpret_cast<float2*>(ring);                      // [NW][512] scratch
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ring + (size_t)EM_NW * 4096);
-    __half2* basis = reinterpret_cast<__half2*>(mbar + 2 * EM_NW + 2);   // [EM_NB][ld]
+    unsigned char* ring = reinterpret_cast<unsigned char*>(u + ld);     // [NW][RING]
+    float2* part = reinterpret_cast<float2*>(ring);                      // [NW][512] scratch (RING >= 4096)
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ring + (size_t)EM_NW * RING);
+    __half2* sbasis = reinterpret_cast<__half2*>(mbar + NSB * EM_NW + 2);   // [EM_NB][ld] if !BG
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int e = blockIdx.x;
     const int n = nred[eta0 + e];
     const float2* M = Mbase + (size_t)e * ld * ld;
     const unsigned* Mb = Mbbase + (size_t)e * ld * ld;
+    __half2* basis = BG ? gbasis + (size_t)e * NB * ld : sbasis;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
     if (status[eta0 + e] & EM_ST_INDEX_ERROR) {
@@ -84,21 +97,21 @@ thth_eig_mixed_kernel(const float2* __restrict__ Mbase, const unsigned* __restri
         return;
     }
     if (tid == 0) {
-        for (int i = 0; i < 2 * EM_NW; ++i) mbar_init(mbar + i, 1);
+        for (int i = 0; i < NSB * EM_NW; ++i) mbar_init(mbar + i, 1);
         fence_mbarrier_init();
     }
     __syncthreads();
     const int ncol4 = (n + 1) >> 1;            // float4 / uint2 groups = two complex columns
     const int ncolq = ((n + 3) >> 2) << 2;     // bf16 rows are fetched in multiples of 4 columns
-    unsigned char* mystage = ring + (size_t)warp * 4096;
-    unsigned long long* mybar = mbar + 2 * warp;
-    unsigned ph0 = 0, ph1 = 0;                 // phase parity of this warp's two barriers
+    unsigned char* mystage = ring + (size_t)warp * RING;
+    unsigned long long* mybar = mbar + NSB * warp;
+    unsigned phbits = 0;                       // bit s: phase parity of this warp's barrier s
 
     // ---- y = A x for the strict upper triangle (row sums into w, column sums
-    // into u); BF = true: bf16 rows, two 2 KB stages; false: fp32 rows, one 4 KB stage
+    // into u); BF = true: bf16 rows, NSB stages of 2 KB; false: fp32 rows, NSB/2 stages of 4 KB
     auto matvec = [&](auto bfc) {
         constexpr bool BF = decltype(bfc)::value;
-        constexpr int NSTG = BF ? 2 : 1;
+        constexpr int NSTG = BF ? NSB : NSF;
         for (int c = tid; c < ld; c += EM_THREADS) w[c] = make_float2(0.f, 0.f);
         __syncthreads();
         float4 yc[8];
@@ -107,7 +120,7 @@ thth_eig_mixed_kernel(const float2* __restrict__ Mbase, const unsigned* __restri
         const int K = (n - 2 >= warp) ? (n - 2 - warp) / EM_NW + 1 : 0;
         auto issue = [&](int k) {
             const int a2 = warp + EM_NW * k;
-            const int st = BF ? (k & 1) : 0;
+            const int st = k % NSTG;
             if (BF) {
                 const int c_lo = (a2 + 1) & ~3;
                 const unsigned bytes = (unsigned)(ncolq - c_lo) * 4u;
@@ -118,7 +131,8 @@ thth_eig_mixed_kernel(const float2* __restrict__ Mbase, const unsigned* __restri
                 const int c_lo = (a2 + 1) & ~1;
                 const unsigned bytes = (unsigned)(2 * ncol4 - c_lo) * 8u;
                 mbar_expect_tx(mybar + st, bytes);
-                bulk_g2s(mystage + c_lo * 8, M + (size_t)a2 * ld + c_lo, bytes, mybar + st);
+                bulk_g2s(mystage + st * 4096 + c_lo * 8, M + (size_t)a2 * ld + c_lo, bytes,
+                         mybar + st);
             }
         };
         if (lane == 0)
@@ -127,9 +141,9 @@ thth_eig_mixed_kernel(const float2* __restrict__ Mbase, const unsigned* __restri
             const int a = warp + EM_NW * k;
             const int first4 = (a + 1) >> 1;
             const float2 xa = v[a];
-            const int st = BF ? (k & 1) : 0;
-            if (st == 0) { while (!mbar_try_wait(mybar, ph0)) {} ph0 ^= 1u; }
-            else { while (!mbar_try_wait(mybar + 1, ph1)) {} ph1 ^= 1u; }
+            const int st = k % NSTG;
+            while (!mbar_try_wait(mybar + st, (phbits >> st) & 1u)) {}
+            phbits ^= 1u << st;
             float4 mm[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -143,7 +157,7 @@ thth_eig_mixed_kernel(const float2* __restrict__ Mbase, const unsigned* __restri
                         q.z = __uint_as_float(r.y << 16);
                         q.w = __uint_as_float(r.y & 0xffff0000u);
                     } else {
-                        q = reinterpret_cast<const float4*>(mystage)[c4];
+                        q = reinterpret_cast<const float4*>(mystage + st * 4096)[c4];
                     }
                 }
                 mm[j] = q;
@@ -232,7 +246,7 @@ thth_eig_mixed_kernel(const float2* __restrict__ Mbase, const unsigned* __restri
         m = 0;
         for (int it = 0; it < max_iter; ++it) {
             if (mode == 0) {
-                if (it >= EM_NB) { overflow = true; break; }
+                if (it >= NB) { overflow = true; break; }
                 for (int c = tid; c < ld; c += EM_THREADS)
                     basis[(size_t)it * ld + c] = __floats2half2_rn(v[c].x, v[c].y);
                 matvec(std::true_type{});
@@ -362,7 +376,8 @@ int eig_mixed_launch(const float2* d_M, int ld, const int* d_nred, int e0, int n
                      double* d_eigs, int* d_status, int* d_iters, double tol, double etol,
                      int max_iter, cudaStream_t st) {
     const char* ev = getenv("SB_EIG_MIXED");
-    if (!ev || atoi(ev) <= 0 || ld > 512) return 0;
+    const int variant = ev ? atoi(ev) : 0;
+    if (variant <= 0 || ld > 512) return 0;
     const size_t count = (size_t)nb * ld * ld;
     unsigned* d_Mb = (unsigned*)workspace(6, count * sizeof(unsigned));
     if (!d_Mb) return SB_ERR_NOMEM;
@@ -370,13 +385,24 @@ int eig_mixed_launch(const float2* d_M, int ld, const int* d_nred, int e0, int n
     if (blocks > 148 * 32) blocks = 148 * 32;
     thth_pack_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_M, d_Mb, count);
     SB_LAUNCH_CHECK();
-    const size_t smem = sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2) +
-                        (size_t)EM_NW * 4096 + (2 * EM_NW + 2) * sizeof(unsigned long long) +
-                        (size_t)EM_NB * ld * sizeof(__half2);
-    SB_CUDA(cudaFuncSetAttribute(thth_eig_mixed_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    thth_eig_mixed_kernel<<<nb, EM_THREADS, smem, st>>>(d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status,
-                                                        d_iters, tol, etol, max_iter);
+    const size_t base = sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2);
+    if (variant >= 2) {
+        // 4 stages, basis in global memory (L2-resident: 128 KB per curvature)
+        __half2* d_basis = (__half2*)workspace(7, (size_t)nb * EM_NBG * ld * sizeof(__half2));
+        if (!d_basis) return SB_ERR_NOMEM;
+        const size_t smem = base + (size_t)EM_NW * 4 * 2048 + (4 * EM_NW + 2) * sizeof(unsigned long long);
+        SB_CUDA(cudaFuncSetAttribute(thth_eig_mixed_kernel<4, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        thth_eig_mixed_kernel<4, true><<<nb, EM_THREADS, smem, st>>>(
+            d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, etol, max_iter, d_basis);
+    } else {
+        const size_t smem = base + (size_t)EM_NW * 2 * 2048 + (2 * EM_NW + 2) * sizeof(unsigned long long) +
+                            (size_t)EM_NB * ld * sizeof(__half2);
+        SB_CUDA(cudaFuncSetAttribute(thth_eig_mixed_kernel<2, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        thth_eig_mixed_kernel<2, false><<<nb, EM_THREADS, smem, st>>>(
+            d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, etol, max_iter, nullptr);
+    }
     SB_LAUNCH_CHECK();
     return 1;
 }

@@ -16,7 +16,8 @@ alignas(128) unsigned char smem_raw[256 * 1024];
 #include "../../scintools_b200/csrc/eig_mixed.cu"
 
 extern "C" int emu_eig_mixed(const float* M, int ld, const int* nred, int nb, double* eigs,
-                             int* status, int* iters, double tol, double etol, int max_iter) {
+                             int* status, int* iters, double tol, double etol, int max_iter,
+                             int variant) {
     const size_t count = (size_t)nb * ld * ld;
     std::vector<unsigned> Mb(count);
     // pack kernel: no rendezvous, one "thread" covers everything through its grid stride
@@ -28,11 +29,18 @@ extern "C" int emu_eig_mixed(const float* M, int ld, const int* nred, int nb, do
             }
         }
     });
+    std::vector<__half2> gbasis((size_t)nb * sb::EM_NBG * ld);
     for (int e = 0; e < nb; ++e) {
         std::memset(sb::smem_raw, 0xa5, sizeof(sb::smem_raw));     // garbage, like real shared memory
         emu::run_block(sb::EM_THREADS, (unsigned)e, [&]() {
-            sb::thth_eig_mixed_kernel(reinterpret_cast<const float2*>(M), Mb.data(), ld, nred, 0,
-                                      eigs, status, iters, tol, etol, max_iter);
+            if (variant >= 2)
+                sb::thth_eig_mixed_kernel<4, true>(reinterpret_cast<const float2*>(M), Mb.data(), ld,
+                                                   nred, 0, eigs, status, iters, tol, etol, max_iter,
+                                                   gbasis.data());
+            else
+                sb::thth_eig_mixed_kernel<2, false>(reinterpret_cast<const float2*>(M), Mb.data(), ld,
+                                                    nred, 0, eigs, status, iters, tol, etol, max_iter,
+                                                    nullptr);
         });
     }
     return 0;

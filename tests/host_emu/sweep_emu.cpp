@@ -57,12 +57,19 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
     if (max_iter <= 0 || max_iter > SB_LANCZOS_MAXIT) max_iter = SB_LANCZOS_MAXIT;
     if (mixed) {
         std::vector<unsigned> Mb(M.size());
+        std::vector<__half2> gbasis((size_t)neta * EM_NBG * ld);
         for (size_t i = 0; i < M.size(); ++i) Mb[i] = bf16_bits(M[i].x) | (bf16_bits(M[i].y) << 16);
         for (int e = 0; e < neta; ++e)
             emu::run_block(emu::Dim3{(unsigned)EM_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
                            emu::Dim3{(unsigned)neta, 1, 1}, [&]() {
-                               thth_eig_mixed_kernel(M.data(), Mb.data(), ld, nred, 0, eigs, status,
-                                                     iters, tol, 2e-7, max_iter);
+                               if (mixed >= 2)
+                                   thth_eig_mixed_kernel<4, true>(M.data(), Mb.data(), ld, nred, 0,
+                                                                  eigs, status, iters, tol, 2e-7,
+                                                                  max_iter, gbasis.data());
+                               else
+                                   thth_eig_mixed_kernel<2, false>(M.data(), Mb.data(), ld, nred, 0,
+                                                                   eigs, status, iters, tol, 2e-7,
+                                                                   max_iter, nullptr);
                            });
     } else {
         for (int e = 0; e < neta; ++e)

@@ -531,10 +531,11 @@ def test_search_batch_matches_single_search(sb, golden_dir):
 @pytest.mark.skipif(not os.environ.get("SB_TEST_UNVERIFIED"),
                     reason="eig_mixed.cu was written after the round-1 GPU budget ran out; "
                            "opt in with SB_TEST_UNVERIFIED=1 (first item of round 2)")
-def test_eta_sweep_mixed_precision_solver(sb, sample, monkeypatch):
-    """SB_EIG_MIXED=1: bf16 Lanczos iteration + fp32 Rayleigh quotient."""
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_eta_sweep_mixed_precision_solver(sb, sample, monkeypatch, variant):
+    """SB_EIG_MIXED=1/2: bf16 Lanczos iteration + fp32 Rayleigh quotient."""
     g, CS = sample
-    monkeypatch.setenv("SB_EIG_MIXED", "1")
+    monkeypatch.setenv("SB_EIG_MIXED", variant)
     eigs, info = sb.ththmod.eta_sweep(CS, g["tau"], g["fd"], g["etas"], g["edges"],
                                       return_info=True)
     assert (np.abs(eigs - g["eigs"]) / g["eigs"]).max() < RTOL

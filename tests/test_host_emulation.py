@@ -140,8 +140,8 @@ def _triangles(golden_dir, etas_idx):
     return g, M, nred, ld
 
 
-@pytest.mark.parametrize("slots", [24, 3])
-def test_eig_mixed_kernel_on_host(golden_dir, slots):
+@pytest.mark.parametrize("slots,variant", [(24, 1), (3, 1), (24, 2), (3, 2)])
+def test_eig_mixed_kernel_on_host(golden_dir, slots, variant):
     """csrc/eig_mixed.cu under the SIMT emulator (tests/host_emu/simt.h): the
     bf16 Lanczos iteration + fp32 Rayleigh quotient (slots=24) and the fp32
     restart taken when the basis slots run out (slots=3) both reproduce the
@@ -161,16 +161,17 @@ def test_eig_mixed_kernel_on_host(golden_dir, slots):
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     lib.emu_eig_mixed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                  ctypes.c_double, ctypes.c_double, ctypes.c_int]
+                                  ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int]
     Mc = np.ascontiguousarray(M)
-    lib.emu_eig_mixed(P(Mc), ld, P(nred), nb, P(eigs), P(status), P(iters), 2e-5, 2e-7, 256)
+    lib.emu_eig_mixed(P(Mc), ld, P(nred), nb, P(eigs), P(status), P(iters), 2e-5, 2e-7, 256,
+                      variant)
     ref = g["eigs"][idx]
     assert (status == 0).all(), status
     assert (np.abs(eigs - ref) / ref).max() < 1e-5, (eigs, ref, iters)
     assert iters.max() < 64
 
 
-@pytest.mark.parametrize("mixed", [0, 1])
+@pytest.mark.parametrize("mixed", [0, 1, 2])
 def test_default_sweep_kernels_on_host(golden_dir, mixed):
     """The DEFAULT device code of the curvature sweep (csrc/thth.cu:
     thth_prep_kernel, thth_indexerr_kernel, thth_build_kernel,
@@ -255,7 +256,7 @@ def test_thin_kernels_on_host(golden_dir):
 
 
 @pytest.mark.parametrize("nedge,half,coherent,mixed", [(42, 0, 1, 0), (72, 1, 1, 0), (34, 0, 0, 0),
-                                                      (66, 1, 1, 1)])
+                                                      (66, 1, 1, 1), (50, 1, 1, 2)])
 def test_default_sweep_kernels_on_host_random(nedge, half, coherent, mixed):
     """Random small spectra through the emulated sweep kernels: full and
     Hermitian-half CS layouts, incoherent mode, odd / cropped theta grids,
