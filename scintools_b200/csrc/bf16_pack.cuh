@@ -13,8 +13,9 @@ __device__ __forceinline__ unsigned bf16_bits(float x) {
     return r >> 16;
 }
 
-// Mb[i] = bf16(re) | bf16(im) << 16
-__global__ void thth_pack_bf16_kernel(const float2* __restrict__ M, unsigned* __restrict__ Mb,
+// Mb[i] = bf16(re) | bf16(im) << 16   (stand-alone converter; the sweep packs inside
+// thth_build_kernel<true>; kept for tests/host_emu and ad-hoc use)
+static __global__ void thth_pack_bf16_kernel(const float2* __restrict__ M, unsigned* __restrict__ Mb,
                                       size_t count) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count;
          i += (size_t)gridDim.x * blockDim.x) {

@@ -23,6 +23,9 @@
 //   <4, true>   SB_EIG_MIXED=2: 4 bf16 stages per warp (as many bytes in flight as the
 //               fp32 kernel, twice the elements), basis (64 slots) in global memory (L2)
 //
+// The bf16 copy is written by thth_build_kernel<true> (thth.cu) next to the fp32
+// triangle (+0.5 GB of writes per 1024-eta sweep, no extra pass).
+//
 // Kernel = the generic TMA row loop of thth_eig_kernel with
 //   * 2 x 2 KB bf16 stages per warp (bulk copies from column (a+1) & ~3),
 //     the same 4 KB re-used as ONE fp32 stage for the final pass;
@@ -370,21 +373,17 @@ thth_eig_mixed_kernel(const float2* __restrict__ Mbase, const unsigned* __restri
 }
 
 #ifndef SB_HOST_EMU
-// Returns 1 when the mixed-precision solver ran, 0 when it is not enabled /
-// not applicable (caller falls back), < 0 on error.
-int eig_mixed_launch(const float2* d_M, int ld, const int* d_nred, int e0, int nb,
-                     double* d_eigs, int* d_status, int* d_iters, double tol, double etol,
-                     int max_iter, cudaStream_t st) {
+// 0: disabled (default); 1 / 2: the variant selected by SB_EIG_MIXED
+int eig_mixed_variant(int ld) {
     const char* ev = getenv("SB_EIG_MIXED");
     const int variant = ev ? atoi(ev) : 0;
-    if (variant <= 0 || ld > 512) return 0;
-    const size_t count = (size_t)nb * ld * ld;
-    unsigned* d_Mb = (unsigned*)workspace(6, count * sizeof(unsigned));
-    if (!d_Mb) return SB_ERR_NOMEM;
-    size_t blocks = (count + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    thth_pack_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_M, d_Mb, count);
-    SB_LAUNCH_CHECK();
+    return (variant > 0 && ld <= 512) ? (variant >= 2 ? 2 : 1) : 0;
+}
+
+// d_Mb: the bf16 copy of d_M written by thth_build_kernel<true>.  Returns 1.
+int eig_mixed_launch(const float2* d_M, const unsigned* d_Mb, int variant, int ld,
+                     const int* d_nred, int e0, int nb, double* d_eigs, int* d_status,
+                     int* d_iters, double tol, double etol, int max_iter, cudaStream_t st) {
     const size_t base = sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2);
     if (variant >= 2) {
         // 4 stages, basis in global memory (L2-resident: 128 KB per curvature)

@@ -13,6 +13,7 @@
 
 #include <type_traits>
 
+#include "bf16_pack.cuh"
 #include "lanczos.cuh"
 #include "thth.cuh"
 #include "tma.cuh"
@@ -26,9 +27,10 @@ int eig_cluster_launch(const float2* d_M, int ld, int n_max, const int* d_nred, 
                        double etol, int max_iter, cudaStream_t st);
 
 // eig_mixed.cu: bf16 iteration + fp32 Rayleigh quotient (SB_EIG_MIXED=1, unverified)
-int eig_mixed_launch(const float2* d_M, int ld, const int* d_nred, int e0, int nb,
-                     double* d_eigs, int* d_status, int* d_iters, double tol, double etol,
-                     int max_iter, cudaStream_t st);
+int eig_mixed_variant(int ld);      // 0: off (default), 1 / 2: SB_EIG_MIXED
+int eig_mixed_launch(const float2* d_M, const unsigned* d_Mb, int variant, int ld,
+                     const int* d_nred, int e0, int nb, double* d_eigs, int* d_status,
+                     int* d_iters, double tol, double etol, int max_iter, cudaStream_t st);
 
 #endif  // SB_HOST_EMU
 
@@ -92,10 +94,13 @@ __global__ void thth_indexerr_kernel(ThthGeom g, const double* __restrict__ etas
 // columns >= nred and the diagonal are zero, the lower triangle is not touched.
 // --------------------------------------------------------------------------
 #define SB_BUILD_EB 4
+// PACK: also write the bf16 copy Mb (re | im << 16) that eig_mixed.cu iterates on
+template <bool PACK>
 __global__ void __launch_bounds__(256)
 thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nbatch,
                   int ld, const int* __restrict__ idx,
-                  const int* __restrict__ nred, float2* __restrict__ M) {
+                  const int* __restrict__ nred, float2* __restrict__ M,
+                  unsigned* __restrict__ Mb) {
     SB_SHARED int ia[32], ib[32];
     SB_SHARED double ta_[32], tb_[32];
     // eta is the FAST grid index: CTAs resident at the same time work on the
@@ -139,6 +144,9 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
             v.y = nan_to_num(v.y);
         }
         Me[(size_t)(ta * 32 + la) * ld + tb * 32 + lb] = v;
+        if (PACK)
+            Mb[(size_t)e * ld * ld + (size_t)(ta * 32 + la) * ld + tb * 32 + lb] =
+                bf16_bits(v.x) | (bf16_bits(v.y) << 16);
     }
   }
 }
@@ -599,6 +607,13 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
     if (batch > neta) batch = neta;
     float2* d_M = (float2*)workspace(2, per * batch);
     if (!d_M) return SB_ERR_NOMEM;
+    // round-2 candidate (SB_EIG_MIXED, off by default): bf16 copy written by the build kernel
+    const int mixed = eig_mixed_variant(ld);
+    unsigned* d_Mb = nullptr;
+    if (mixed) {
+        d_Mb = (unsigned*)workspace(6, per / 2 * batch);
+        if (!d_Mb) return SB_ERR_NOMEM;
+    }
     const int T = ld / 32;
     const int npairs = T * (T + 1) / 2;
     // TMA ring variant (ld <= 512): 256 threads, 2 stages -> 2 CTAs per SM so
@@ -629,13 +644,19 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
         int nb = neta - e0 < batch ? neta - e0 : batch;
         dim3 grid((nb + SB_BUILD_EB - 1) / SB_BUILD_EB, npairs), block(32, 8);
         prof_begin(PROF_THTH_BUILD, st);
-        thth_build_kernel<<<grid, block, 0, st>>>(g, d_etas, e0, nb, ld, d_idx, d_nred, d_M);
+        if (mixed)
+            thth_build_kernel<true><<<grid, block, 0, st>>>(g, d_etas, e0, nb, ld, d_idx, d_nred,
+                                                            d_M, d_Mb);
+        else
+            thth_build_kernel<false><<<grid, block, 0, st>>>(g, d_etas, e0, nb, ld, d_idx, d_nred,
+                                                             d_M, nullptr);
         prof_end(PROF_THTH_BUILD, st);
         SB_LAUNCH_CHECK();
         prof_begin(PROF_THTH_EIG, st);
         // experimental solvers, each enabled by its own environment variable
-        int rc = eig_mixed_launch(d_M, ld, d_nred, e0, nb, d_eigs, d_status, d_iters, tol,
-                                  2e-7, max_iter, st);
+        int rc = mixed ? eig_mixed_launch(d_M, d_Mb, mixed, ld, d_nred, e0, nb, d_eigs, d_status,
+                                          d_iters, tol, 2e-7, max_iter, st)
+                       : 0;
         if (rc == 0)
             rc = eig_cluster_launch(d_M, ld, g.n, d_nred, e0, nb, d_eigs, d_status, d_iters,
                                     tol, 2e-7, max_iter, st);

@@ -38,6 +38,7 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
     std::vector<int> idx((size_t)neta * ld, 0);
     std::vector<float2> M((size_t)neta * ld * ld);
     std::memset(M.data(), 0xff, M.size() * sizeof(float2));          // NaN junk, like a fresh slab
+    std::vector<unsigned> Mb(mixed ? M.size() : 0, 0xffffffffu);      // written by the build kernel
     for (int e = 0; e < neta; ++e) status[e] = 0;
     for (int e = 0; e < neta; ++e)
         emu::run_block(emu::Dim3{32, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
@@ -53,12 +54,17 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
     for (unsigned bx = 0; bx < gx; ++bx)
         for (unsigned by = 0; by < (unsigned)npairs; ++by)
             emu::run_block(emu::Dim3{32, 8, 1}, emu::Dim3{bx, by, 0}, emu::Dim3{gx, (unsigned)npairs, 1},
-                           [&]() { thth_build_kernel(g, etas, 0, neta, ld, idx.data(), nred, M.data()); });
+                           [&]() {
+                               if (mixed)
+                                   thth_build_kernel<true>(g, etas, 0, neta, ld, idx.data(), nred,
+                                                           M.data(), Mb.data());
+                               else
+                                   thth_build_kernel<false>(g, etas, 0, neta, ld, idx.data(), nred,
+                                                            M.data(), nullptr);
+                           });
     if (max_iter <= 0 || max_iter > SB_LANCZOS_MAXIT) max_iter = SB_LANCZOS_MAXIT;
     if (mixed) {
-        std::vector<unsigned> Mb(M.size());
         std::vector<__half2> gbasis((size_t)neta * EM_NBG * ld);
-        for (size_t i = 0; i < M.size(); ++i) Mb[i] = bf16_bits(M[i].x) | (bf16_bits(M[i].y) << 16);
         for (int e = 0; e < neta; ++e)
             emu::run_block(emu::Dim3{(unsigned)EM_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
                            emu::Dim3{(unsigned)neta, 1, 1}, [&]() {
