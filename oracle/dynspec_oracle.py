@@ -132,3 +132,54 @@ def scale_dyn_lambda(dyn, freqs, spacing="auto"):
     # solve with nt right-hand sides
     arout = interp1d(freqs, arin, kind="cubic", axis=0)(feq)
     return np.flipud(arout), np.flipud(lam_eq), dlam
+
+
+def norm_sspec(sspec, fdop, tdel, eta, freq, delmax=None, startbin=1, maxnormfac=5, cutmid=0,
+               ref_freq=1400, numsteps=None, weighted=True):
+    """Dynspec.norm_sspec (dynspec.py:1920-2183) for lamsteps=False, an explicit
+    eta, linear steps, no artefact subtraction / NaN interpolation / spectrum fit:
+    every delay row of the secondary spectrum is resampled (np.interp) on the
+    normalised Doppler axis fdop / sqrt(tdel / eta).  Returns (normsspec masked
+    array, normsspecavg, fdopnew, tdel_cut, powerspectrum).
+    ORACLE ONLY in round 1: groundwork for the arc-fit row."""
+    sspec = np.array(sspec, dtype=np.float64)
+    fdop = np.asarray(fdop, dtype=np.float64)
+    yaxis = np.asarray(tdel, dtype=np.float64)
+    delmax = np.max(yaxis) if delmax is None else delmax
+    c = 299792458.0
+    eta = eta / (freq / ref_freq) ** 2 * (c * 1e6 / ((ref_freq * 10 ** 6) ** 2))
+    ind = np.argmin(abs(yaxis - delmax))
+    sspec = sspec[startbin:ind, :]
+    nr, nc = sspec.shape
+    sspec[:, int(nc / 2 - np.floor(cutmid / 2)):int(nc / 2 + np.floor(cutmid / 2))] = np.nan
+    td = yaxis[startbin:ind]
+    maxfdop = maxnormfac * np.sqrt(td[-1] / eta)
+    if maxfdop > max(fdop):
+        maxfdop = max(fdop)
+    nfdop = 2 * len(fdop[abs(fdop) <= maxfdop]) if numsteps is None else numsteps
+    if nfdop % 2 != 0:
+        nfdop += 1
+    fdopnew = np.linspace(-maxnormfac, maxnormfac, nfdop)
+    rows, mask = [], []
+    for ii in range(len(td)):
+        s = np.sqrt(td[ii] / eta)
+        sel = abs(fdop) <= maxnormfac * s
+        ifdop = fdop[sel] / s
+        rows.append(np.interp(fdopnew, ifdop, sspec[ii, sel]))
+        mask.append(np.abs(fdopnew) > np.max(np.abs(ifdop)))
+    mask = np.array(mask).squeeze()
+    norm = np.array(rows).squeeze()
+    mask = mask + np.isnan(norm)
+    norm = np.ma.array(norm, mask=mask)
+    power = np.ma.mean(np.power(10, norm / 10), axis=1)
+    xdata = np.sqrt(td)
+    ydata = np.sqrt(td) * power
+    xdata = xdata[~np.isnan(xdata)]
+    ydata = ydata[~np.isnan(ydata)]
+    alpha = -11 / 3
+    index = np.argmin(np.abs(xdata - 10))
+    amp = ydata[index] * xdata[index] ** -alpha
+    arc = amp * xdata ** alpha
+    weights = 10 * np.log10(arc) if weighted else np.ones(np.shape(arc))
+    avg = np.ma.average(norm, axis=0, weights=np.squeeze(weights)).squeeze()
+    return norm, avg, fdopnew, td, power

@@ -273,6 +273,28 @@ def golden_scale_dyn(pkg):
     print("scale_dyn: lamdyn", ds.lamdyn.shape, "dlam %.3e" % ds.dlam)
 
 
+def golden_norm_sspec(pkg):
+    """Dynspec.norm_sspec of the reference with an explicit curvature (oracle pin
+    for SURVEY 8f rank 2; no CUDA row yet)."""
+    rng = np.random.default_rng(29)
+    nf, nt, dt, df = 64, 96, 10.0, 0.1
+    dyn = rng.exponential(1.0, (nf, nt))
+    ds = _ref_dynspec(pkg, dyn.copy(), dt, df)
+    ds.calc_sspec()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ds.norm_sspec(eta=0.4, lamsteps=False, plot=False, cutmid=2, startbin=2)
+    np.savez_compressed(os.path.join(GOLD, "norm_sspec_64x96.npz"), dyn=dyn, dt=dt, df=df,
+                        eta=0.4, cutmid=2, startbin=2, freq=float(ds.freq),
+                        sspec=ds.sspec, fdop=ds.fdop, tdel=ds.tdel,
+                        normsspec=np.ma.filled(ds.normsspec, np.nan),
+                        mask=np.ma.getmaskarray(ds.normsspec),
+                        normsspecavg=np.ma.filled(ds.normsspecavg, np.nan),
+                        normsspec_fdop=ds.normsspec_fdop, normsspec_tdel=ds.normsspec_tdel,
+                        powerspectrum=np.ma.filled(ds.powerspectrum, np.nan))
+    print("norm_sspec:", np.shape(ds.normsspec))
+
+
 def golden_sim(pkg):
     """scint_sim.Simulation at 64^2 / 32x96, seeded (legacy MT19937)."""
     Sim = pkg.scint_sim.Simulation
@@ -317,6 +339,8 @@ def main():
         golden_wavefield(pkg)
     if not only or "scale" in only:
         golden_scale_dyn(pkg)
+    if not only or "norm" in only:
+        golden_norm_sspec(pkg)
     if not only or "sim" in only:
         golden_sim(pkg)
     for fn in sorted(os.listdir(GOLD)):
