@@ -57,7 +57,14 @@ using std::isfinite;
 
 namespace emu {
 struct Dim3 { unsigned x, y, z; };
-struct Fiber { ucontext_t ctx; std::vector<char> stack; bool done = false; };
+struct Fiber { ucontext_t ctx; char* stack = nullptr; bool done = false; };
+constexpr size_t STACK_BYTES = 192 * 1024;
+// stacks are allocated once and reused by every emulated block (no zero-fill)
+inline char* stack_of(int i) {
+    static std::vector<char*> pool;
+    while ((int)pool.size() <= i) pool.push_back((char*)std::malloc(STACK_BYTES));
+    return pool[i];
+}
 struct Warp {
     unsigned long long slot[32];
     int arrive = 0, arrive2 = 0;
@@ -106,10 +113,10 @@ inline void run_block(Dim3 bdim, Dim3 bidx, Dim3 gdim, std::function<void()> bod
     B() = &blk;
     for (int i = 0; i < nthreads; ++i) {
         Fiber& f = blk.th[i];
-        f.stack.resize(512 * 1024);
+        f.stack = stack_of(i);
         getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = f.stack.data();
-        f.ctx.uc_stack.ss_size = f.stack.size();
+        f.ctx.uc_stack.ss_sp = f.stack;
+        f.ctx.uc_stack.ss_size = STACK_BYTES;
         f.ctx.uc_link = nullptr;
         makecontext(&f.ctx, (void (*)())trampoline, 0);
     }
