@@ -168,7 +168,7 @@ int sb_gerchberg_saxton_f32(void* wavefield, const float* amp, const uint8_t* ro
 
 /* ---- Dynspec 2-D FFT paths ---------------------------------------------- */
 
-/* UNVERIFIED ON GPU (round-2 candidate).  Dynspec.scale_dyn(scale='lambda')
+/* Dynspec.scale_dyn(scale='lambda')
  * (scintools/dynspec.py:3926-3957): not-a-knot cubic spline of every time
  * column of dyn [nf][nt] at nlam query frequencies, written flipped
  * (out [nlam][nt], wavelength ascending).  The column-independent tables are

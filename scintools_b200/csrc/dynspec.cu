@@ -684,8 +684,6 @@ static int conj_spectrum_bluestein(const float* dyn, int nf, int nt, int NF, int
 // out[:crop0, :crop1] = scale * ifft2(ifftshift(in)) for ANY sizes (phase
 // retrieval on the tutorial's 256 x 600 conjugate spectrum), by the same
 // chirp-z machinery: ifft2(X) = conj(fft2(conj X)) / (N0 N1).
-//   STATUS: round-2 candidate, NOT yet run on a GPU (written after the round-1
-//   GPU budget was spent); reached only with SB_ENABLE_UNVERIFIED=1.
 // ------------------------------------------------------------------------
 // conj_in != 0: returns ifft2(conj(in)) = conj(fft2(in)) / (n0 n1) (used for the
 // forward transform of the Gerchberg-Saxton loop)

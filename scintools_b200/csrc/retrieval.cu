@@ -358,13 +358,13 @@ struct CropStore {        // out[k][c], k = k1 + R1 k2
     }
 };
 
-// dynspec.cu: chirp-z variant for arbitrary sizes (round-2 candidate, unverified)
+// dynspec.cu: chirp-z variant for arbitrary sizes
 int ifft2_c2c_any(const float2* in, int n0, int n1, int centred, int crop0, int crop1,
                   double scale, int real_only, void* out, cudaStream_t st, int conj_in);
 
 int ifft2_c2c(const float2* in, int n0, int n1, int centred, int crop0, int crop1,
               double scale, int real_only, void* out, cudaStream_t st) {
-    if (((n0 & (n0 - 1)) || (n1 & (n1 - 1))) && getenv("SB_ENABLE_UNVERIFIED"))
+    if ((n0 & (n0 - 1)) || (n1 & (n1 - 1)))
         return ifft2_c2c_any(in, n0, n1, centred, crop0, crop1, scale, real_only, out, st, 0);
     if (n0 < 8 || n1 < 8 || (n0 & (n0 - 1)) || (n1 & (n1 - 1)) || n0 > 65536 || n1 > 32768) {
         set_error("ifft2: sizes %d x %d must be powers of two (8..65536 x 8..32768)", n0, n1);
@@ -473,7 +473,7 @@ static int gerchberg_saxton_any(float2* W, const float* amp, const unsigned char
 
 int gerchberg_saxton(float2* W, const float* amp, const unsigned char* rowmask, int n0, int n1,
                      int niter, cudaStream_t st) {
-    if (((n0 & (n0 - 1)) || (n1 & (n1 - 1))) && getenv("SB_ENABLE_UNVERIFIED"))
+    if ((n0 & (n0 - 1)) || (n1 & (n1 - 1)))
         return gerchberg_saxton_any(W, amp, rowmask, n0, n1, niter, st);
     if (n0 < 8 || n1 < 8 || (n0 & (n0 - 1)) || (n1 & (n1 - 1)) || n0 > 65536 || n1 > 32768) {
         set_error("gerchberg_saxton: wavefield %d x %d must have power-of-two sizes", n0, n1);

@@ -2,12 +2,9 @@
 // every time column from the frequency grid to equal wavelength steps with a
 // not-a-knot cubic spline (scipy interp1d(kind='cubic')).
 //
-//   STATUS: ROUND-2 CANDIDATE.  The algorithm (second-derivative form, Thomas
-//   factors shared by all columns, 4 weights per output row) is verified on
-//   the CPU against scipy (1e-16 in fp64, 1e-7 emulated in fp32) and the host
-//   tables are built by the Python mirror with numpy; this kernel is a direct
-//   transcription that has NOT run on a GPU yet (written after the round-1 GPU
-//   budget was spent).  Python side gated by SB_ENABLE_UNVERIFIED=1.
+// Algorithm: second-derivative form, Thomas factors shared by all columns,
+// 4 weights per output row; host tables built by the Python mirror in fp64.
+// GPU parity vs the reference: tests/test_gpu_parity.py::test_scale_dyn_lambda.
 //
 // The knots are the same for every column, so the tridiagonal system for the
 // second derivatives M has column-independent factors (host, fp64):

@@ -250,19 +250,11 @@ class Dynspec:
     def scale_dyn(self, scale='lambda', spacing='auto', **kwargs):
         """Resample the dynamic spectrum to equal wavelength steps (reference
         dynspec.py:3872-3957, scale='lambda' only) -> self.lamdyn, self.lam,
-        self.nlam, self.dlam.
-
-        NOT YET VALIDATED ON A GPU (written after the round-1 GPU budget was
-        spent): refuses to run unless SB_ENABLE_UNVERIFIED=1."""
-        import os
+        self.nlam, self.dlam."""
         import torch
         from scipy.constants import c as c_light
         if not (('lambda' in scale) or ('wavelength' in scale)):
             raise NotImplementedError("only scale='lambda' is on the B200 path")
-        if not os.environ.get("SB_ENABLE_UNVERIFIED"):
-            raise NotImplementedError(
-                "scale_dyn is a round-2 candidate that has not run on a GPU yet; "
-                "set SB_ENABLE_UNVERIFIED=1 to try it")
         freqs = np.array(self.freqs, dtype=np.float64)
         nf, nt = self.dyn.shape
         lams = np.divide(c_light, freqs * 10 ** 6)

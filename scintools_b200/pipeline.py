@@ -50,9 +50,11 @@ def batch_arc_pipeline(dyns, freqs, times, etas, edges, group=None, device=None,
     lo, hi = sharding.block_range(n, rank, world)
     fit = np.full(hi - lo, np.nan)
     sig = np.full(hi - lo, np.nan)
+    want_sspec = kw.pop("want_sspec", True)
+    want_acf = kw.pop("want_acf", True)
     for k, i in enumerate(range(lo, hi)):
-        r = arc_pipeline(dyns[i], freqs, times, etas, edges, want_sspec=True,
-                         want_acf=True, **kw)
+        r = arc_pipeline(dyns[i], freqs, times, etas, edges, want_sspec=want_sspec,
+                         want_acf=want_acf, **kw)
         fit[k], sig[k] = r["eta_fit"], r["eta_sig"]
     return (sharding.all_gather_blocks(fit, n, group, device),
             sharding.all_gather_blocks(sig, n, group, device))

@@ -27,6 +27,19 @@ def world_info(group=None):
     return 0, 1
 
 
+def _gather_device(group=None, device=None):
+    """Device of the all-gather buffers: NCCL has no CPU backend, so under
+    one-process-per-GPU the buffers must be CUDA tensors; gloo takes CPU."""
+    import torch.distributed as dist
+    if device is not None:
+        return device
+    backend = str(dist.get_backend(group)).lower()
+    if "nccl" in backend:
+        from . import _device as D
+        return D.device()
+    return None
+
+
 def all_gather_blocks(local, n_total, group=None, device=None):
     """All-gather variable-length float64 blocks (block_range layout) into one
     array of length n_total on every rank.  One collective."""
@@ -39,6 +52,7 @@ def all_gather_blocks(local, n_total, group=None, device=None):
     width = -(-n_total // world)
     buf = torch.full((width,), float("nan"), dtype=torch.float64)
     buf[:local.shape[0]] = torch.from_numpy(local)
+    device = _gather_device(group, device)
     if device is not None:
         buf = buf.to(device)
     out = torch.empty((world * width,), dtype=torch.float64, device=buf.device)
@@ -88,6 +102,7 @@ def sharded_map(fn, items, width, group=None, device=None):
     rows = -(-n // world)
     buf = torch.full((rows, width), float("nan"), dtype=torch.float64)
     buf[:hi - lo] = torch.from_numpy(local)
+    device = _gather_device(group, device)
     if device is not None:
         buf = buf.to(device)
     out = torch.empty((world * rows, width), dtype=torch.float64, device=buf.device)

@@ -175,8 +175,12 @@ def eta_sweep(CS, tau, fd, etas, edges, coher=True, tol=DEFAULT_TOL,
                                      status.data_ptr(), nred.data_ptr(),
                                      iters.data_ptr(), D.stream_ptr()))
     out = eigs.cpu().numpy()
+    st = status.cpu().numpy()
+    # iteration cap hit without convergence: ARPACK raises ArpackNoConvergence in
+    # the reference and the eta loop stores NaN (ththmod.py:795-799)
+    out[(st & 8) != 0] = np.nan
     if return_info:
-        return out, dict(status=status.cpu().numpy(), nred=nred.cpu().numpy(),
+        return out, dict(status=st, nred=nred.cpu().numpy(),
                          iters=iters.cpu().numpy())
     return out
 
@@ -633,14 +637,17 @@ def _top_eigenpair(thth_red):
     wv = float(w.cpu()[0])
     if not np.isfinite(wv):
         raise np.linalg.LinAlgError("theta-theta matrix has a zero start vector / no eigenpair")
+    if int(info.cpu()[1]) & 8:
+        # iteration cap without convergence: ARPACK raises ArpackNoConvergence here
+        raise np.linalg.LinAlgError("top eigenpair did not converge")
     return wv, _c64(V), V
 
 
 def modeler(CS, tau, fd, eta, edges, hermetian=True):
     """Model theta-theta, conjugate spectrum and dynamic spectrum from the top
     eigenpair (ththmod.py:261-327).  Returns (thth_red, thth2_red, recov, model,
-    edges_red, w, V).  The padded CS must have power-of-two sizes (the inverse
-    2-D FFT of this version); V has an arbitrary global phase, like ARPACK's."""
+    edges_red, w, V).  Any padded CS size (powers of two take the radix path, other
+    sizes the chirp-z inverse); V has an arbitrary global phase, like ARPACK's."""
     import torch
     if not hermetian:
         raise NotImplementedError(
@@ -689,7 +696,11 @@ def single_chunk_retrieval(params):
         model_E = _c64(out)
         if verbose:
             print("Chunk %s-%s success" % (idx_f, idx_t), flush=True)
-    except Exception as e:          # same catch-all as ththmod.py:1470-1475
+    except _lib.SbError:
+        # a library error (unsupported size, CUDA failure) is not a data failure:
+        # never turn it into a silent all-zero chunk
+        raise
+    except Exception as e:          # data failures, as in ththmod.py:1470-1475
         print(e, flush=True)
         model_E = np.zeros(dspec2.shape, dtype=complex)
     return (model_E, idx_f, idx_t)

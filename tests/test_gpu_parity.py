@@ -528,9 +528,6 @@ def test_search_batch_matches_single_search(sb, golden_dir):
         assert x[0] == pytest.approx(y[0], rel=1e-6)
 
 
-@pytest.mark.skipif(not os.environ.get("SB_TEST_UNVERIFIED"),
-                    reason="eig_mixed.cu was written after the round-1 GPU budget ran out; "
-                           "opt in with SB_TEST_UNVERIFIED=1 (first item of round 2)")
 @pytest.mark.parametrize("variant", ["1", "2"])
 def test_eta_sweep_mixed_precision_solver(sb, sample, monkeypatch, variant):
     """SB_EIG_MIXED=1/2: bf16 Lanczos iteration + fp32 Rayleigh quotient."""
@@ -551,11 +548,7 @@ def test_eta_sweep_mixed_precision_solver(sb, sample, monkeypatch, variant):
     assert np.isnan(z).all()
 
 
-@pytest.mark.skipif(not os.environ.get("SB_TEST_UNVERIFIED"),
-                    reason="scale_dyn.cu was written after the round-1 GPU budget ran out; "
-                           "opt in with SB_TEST_UNVERIFIED=1 (round 2)")
 def test_scale_dyn_lambda(sb, golden_dir, monkeypatch):
-    monkeypatch.setenv("SB_ENABLE_UNVERIFIED", "1")
     g = np.load(os.path.join(golden_dir, "scale_dyn_40x24.npz"))
     dyn = g["dyn"]
     nf, nt = dyn.shape
