@@ -6,8 +6,9 @@ One *step* = one pass of the hot path over one dynamic spectrum:
   conjugate spectrum of the 4096x8192 chunk (npad=3 -> 16384x32768 c64, 4.3 GB)
   + dominant-eigenvalue sweep over 1024 curvatures on a 512-point theta grid
   (+ one all-gather of the per-eta eigenvalues when N > 1).
-Weak scaling: every rank sweeps its own block of 1024 etas of a global
-N x 1024 log grid (the CS is recomputed per rank; no data-path collective).
+Weak scaling: every rank sweeps 1024 etas of a global N x 1024 log grid,
+interleaved over the ranks (the CS is recomputed per rank; no data-path
+collective); a strong-scaling leg over a fixed 8192-eta grid is reported too.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
@@ -37,6 +38,8 @@ ETA_TRUE = 0.08          # s^3
 DT, DF = 10.0, 0.03125   # s, MHz
 EDGE_LIM = 10.0          # mHz
 FW = 0.1
+WORKLOAD = ("C3 eta-sweep: 4096x8192 dynspec (1-D screen, 64 images, eta_true=0.08 s^3), "
+            "npad=3 -> CS 16384x32768, 512-pt theta grid, 1024 etas per GPU")
 
 
 def make_dynspec(seed=3, nf=NF, nt=NT):
@@ -62,14 +65,6 @@ def make_dynspec(seed=3, nf=NF, nt=NT):
 
 def eta_grid(n_total):
     return np.logspace(np.log10(ETA_TRUE / 2), np.log10(2 * ETA_TRUE), n_total)
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
-# `ncu --set full` capture of this same command (profiles/
-# r1_ncu_full_summary_final.csv); bench.py cannot run ncu on itself.
-NCU_TRAFFIC_BYTES = {"thth_eig": 19.325e9 + 0.004e9, "thth_build": 1.368e9 + 1.042e9,
-                     "cs_rows": 0.134e9 + 0.164e9, "cs_colA": 0.215e9 + 0.800e9,
-                     "cs_colB": 0.858e9 + 0.810e9}
 
 
 def peak_hbm():
@@ -149,34 +144,71 @@ class ClockSampler:
 _G = {}
 
 
+def _pool_init():
+    """One BLAS/OpenMP thread per pool worker (no oversubscription)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        _G["limited"] = threadpool_limits(1)
+    except Exception:
+        _G["limited"] = True
+
+
 def _eval_one(eta):
     from oracle import thth_oracle as TO
-    if _G.get("procs", 1) > 1 and not _G.get("limited"):
-        try:    # one BLAS thread per pool worker: no oversubscription
-            from threadpoolctl import threadpool_limits
-            _G["limited"] = threadpool_limits(1)
-        except Exception:
-            _G["limited"] = True
     try:
         return TO.Eval_calc(_G["CS"], _G["tau"], _G["fd"], eta, _G["edges"])
     except Exception:
         return float("nan")
 
 
-def cpu_sample(CS, tau, fd, edges, etas, procs):
-    """Time len(etas) eta-trials of the oracle; returns (seconds, eigs)."""
-    _G.update(CS=CS, tau=tau, fd=fd, edges=edges, procs=procs)
-    t0 = time.perf_counter()
-    if procs <= 1:
-        eigs = [_eval_one(e) for e in etas]
-    else:
-        import multiprocessing as mp
-        with mp.get_context("fork").Pool(procs) as pool:
-            eigs = pool.map(_eval_one, list(etas), chunksize=1)
-    return time.perf_counter() - t0, np.array(eigs)
+class CpuSweep:
+    """The reference's eta loop (ththmod.py:789-799) on the host cores.
+
+    procs == 1: the as-shipped serial loop, one BLAS thread (numpy.fft and the
+    eta loop of the reference are single-threaded).  procs > 1: the reference's
+    own parallel mode, a process pool (dynspec.py:1715-1719 maps chunks over a
+    pool; here the pool maps the eta-trials of one chunk).  The pool is created
+    ONCE (fork: the workers share the CS copy-on-write) and re-used by every
+    timed step; workers run one BLAS thread each."""
+
+    def __init__(self, CS, tau, fd, edges, procs):
+        _G.update(CS=CS, tau=tau, fd=fd, edges=edges)
+        self.procs = procs
+        self.pool = None
+        self.limit = None
+        if procs > 1:
+            import multiprocessing as mp
+            self.pool = mp.get_context("fork").Pool(procs, initializer=_pool_init)
+        else:
+            try:
+                from threadpoolctl import threadpool_limits
+                self.limit = threadpool_limits(1)
+            except Exception:
+                self.limit = None
+
+    def run(self, etas):
+        """Returns (seconds, eigs) for len(etas) eta-trials."""
+        t0 = time.perf_counter()
+        if self.pool is None:
+            eigs = [_eval_one(e) for e in etas]
+        else:
+            eigs = self.pool.map(_eval_one, list(etas), chunksize=1)
+        return time.perf_counter() - t0, np.array(eigs)
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+        if self.limit is not None and hasattr(self.limit, "restore_original_limits"):
+            self.limit.restore_original_limits()
 
 
 def reference_arm(args):
+    """`--impl reference`: the reference's CPU algorithm (oracle port: numpy gather +
+    scipy ARPACK eigsh, scipy pocketfft CS) on all host cores.  One step = a
+    bounded sample of the C3 workload: `per_worker` eta-trials per pool worker,
+    drawn from the same eta grid; the CS FFT (once per 1024 etas in the real
+    workload) is timed once and charged pro rata to every step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -187,40 +219,53 @@ def reference_arm(args):
     fd = TO.fft_axis(t, "mHz", NPAD)
     tau = TO.fft_axis(freq, "us", NPAD)
     edges = np.linspace(-EDGE_LIM, EDGE_LIM, NEDGE)
-    t0 = time.perf_counter()
     pad = np.zeros(((NPAD + 1) * NF, (NPAD + 1) * NT), dtype=np.float32)
     pad[:NF, :NT] = dyn
+    sfft.fft2(pad[:256, :256], workers=cores)               # thread-pool warm-up
+    t0 = time.perf_counter()
     CS = sfft.fftshift(sfft.fft2(pad, workers=cores))       # pocketfft, c64
-    del pad
     t_cs = time.perf_counter() - t0
+    del pad
     etas = eta_grid(NETA * args.gpus)
-    nsamp = max(cores, 4)
-    times = []
+    per_worker = 8
+    nsamp = per_worker * cores
     rng = np.random.default_rng(0)
-    for it in range(args.warmup + args.steps):
-        sel = np.sort(rng.choice(len(etas), nsamp, replace=False))
-        dt_, _ = cpu_sample(CS, tau, fd, edges, etas[sel], cores)
-        if it >= args.warmup:
+    sweep = CpuSweep(CS, tau, fd, edges, cores)
+    times = []
+    for it in range(max(1, args.warmup) + args.steps):      # >= 1 warm-up step (page-in, BLAS init)
+        sel = np.sort(rng.choice(len(etas), nsamp, replace=len(etas) < nsamp))
+        dt_, _ = sweep.run(etas[sel])
+        if it >= max(1, args.warmup):
             times.append(dt_)
-    per_step = float(np.mean(times))
+    sweep.close()
+    # as-shipped single process (serial eta loop), same grid
+    one = CpuSweep(CS, tau, fd, edges, 1)
+    one.run(etas[:1])
+    sel1 = np.linspace(0, len(etas) - 1, 8).astype(int)
+    t_one, _ = one.run(etas[sel1])
+    one.close()
+    cs_share = t_cs * nsamp / NETA                           # one CS per 1024 eta-trials
+    per_step = float(np.mean(times)) + cs_share
     value = nsamp / per_step
+    sample = ("%d eta-trials per step (%d per worker) over a persistent %d-process fork pool, "
+              "1 BLAS thread each, on the full-size CS; + %.3f s per step = the CS FFT "
+              "(scipy pocketfft c64, %d threads: %.1f s per 1024 etas) pro rata"
+              % (nsamp, per_worker, cores, cs_share, cores, t_cs))
     line = {
         "impl": "reference", "metric": METRIC, "value": value,
         "unit": "eta-trials/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "warmup": max(1, args.warmup), "ms_per_step": per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C3 eta-sweep: 4096x8192 dynspec, npad=3, "
-                               "512-pt theta grid, %d etas" % NETA,
+        "config": {"workload": WORKLOAD,
                    "note": "reference algorithm (numpy gather + scipy ARPACK "
                            "eigsh) via the oracle port; astropy unavailable"},
         "cpu_baseline": {"value": value, "unit": "eta-trials/s", "cores": cores,
-                         "kind": "port",
-                         "sample": "%d eta-trials per step over a %d-process "
-                                   "fork pool on the full-size CS; the CS "
-                                   "(scipy pocketfft c64, %d threads) took "
-                                   "%.1f s once and is NOT counted"
-                                   % (nsamp, cores, cores, t_cs)},
+                         "kind": "port", "sample": sample,
+                         "step_spread": [float(min(times)), float(max(times))],
+                         "single_process": {"value": len(sel1) / t_one, "cores": 1,
+                                            "sample": "8 eta-trials, serial loop, 1 BLAS "
+                                                      "thread (as shipped), CS FFT not counted"}},
         "e2e": {"value": value, "unit": "eta-trials/s",
                 "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -231,6 +276,32 @@ def reference_arm(args):
 # --------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------
+PROF_NAMES = ["cs_rows", "cs_colA", "cs_colB", "thth_prep", "thth_build",
+              "thth_eig", "sspec", "acf", "sim_screen", "sim_freq"]
+NETA_STRONG = 8192       # fixed global grid of the strong-scaling leg
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, read at
+    run time from the committed summary of the `ncu --set full` capture of this
+    same command (profiles/r2_ncu_traffic.json, written by profiles/ncu_traffic.py
+    from the .ncu-rep).  None when the capture does not list the kernel."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        return d["kernels"][kernel]["dram_bytes"], "profiles/r2_ncu_traffic.json (%s)" % d.get("source", "")
+    except Exception:
+        return None, "no committed ncu capture lists this kernel"
+
+
+def collect_prof(L, _lib):
+    ms = np.zeros(16)
+    cnt = np.zeros(16, dtype=np.int32)
+    _lib.check(L.sb_profile_collect(ms.ctypes.data, cnt.ctypes.data, 16))
+    return ms, cnt
+
+
 def b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -251,8 +322,11 @@ def b200_arm(args):
     fd = np.asarray(thth.fft_axis(t, "mHz", NPAD))
     tau = np.asarray(thth.fft_axis(freq, "us", NPAD))
     edges = np.linspace(-EDGE_LIM, EDGE_LIM, NEDGE)
+    # weak scaling: a global grid of world x 1024 curvatures, INTERLEAVED over the
+    # ranks (rank r sweeps etas_all[r::world]) so that every rank gets the same mix
+    # of easy (near the peak) and hard curvatures
     etas_all = eta_grid(NETA * world)
-    etas = np.ascontiguousarray(etas_all[rank * NETA:(rank + 1) * NETA])
+    etas = np.ascontiguousarray(etas_all[rank::world])
 
     # device-resident inputs
     d_dyn = D.upload(dyn)
@@ -264,141 +338,163 @@ def b200_arm(args):
     keep = thth.needed_fd_columns(fd, edges) or 0
     cs = thth.DeviceCS(d_cs, nfd=nfd, ncols_valid=keep or None)
     geom = thth._Geom(cs, tau, fd, edges, True)
-    d_etas = D.upload(etas)
-    d_eigs = D.empty((NETA,), torch.float64)
-    d_stat = D.empty((NETA,), torch.int32)
-    d_nred = D.empty((NETA,), torch.int32)
-    d_iter = D.empty((NETA,), torch.int32)
-    gathered = D.empty((world * NETA,), torch.float64) if world > 1 else None
     stream = D.stream_ptr()
     L = _lib.lib
-
-    def step():
-        _lib.check(L.sb_cs_f32(d_dyn.data_ptr(), NF, NT, NPAD, 0.0, 0, 1, pitch, keep,
-                               d_cs.data_ptr(), stream))
-        _lib.check(L.sb_eta_sweep(geom.ref, d_etas.data_ptr(), NETA, thth.DEFAULT_TOL,
-                                  0, d_eigs.data_ptr(), d_stat.data_ptr(),
-                                  d_nred.data_ptr(), d_iter.data_ptr(), stream))
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, d_eigs)
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    sync_all()
-    launches0 = L.sb_launch_count()
-    L.sb_profile_enable(1)
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    sync_all()
-    wall0 = time.time()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    sync_all()
-    wall1 = time.time()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    launches = int(L.sb_launch_count() - launches0)
-    prof_ms = (np.zeros(16), np.zeros(16, dtype=np.int32))
-    _lib.check(L.sb_profile_collect(prof_ms[0].ctypes.data, prof_ms[1].ctypes.data, 16))
-    L.sb_profile_enable(0)
+    def make_leg(etas_local):
+        n = len(etas_local)
+        buf = dict(n=n, etas=D.upload(np.ascontiguousarray(etas_local)),
+                   eigs=D.empty((n,), torch.float64), stat=D.empty((n,), torch.int32),
+                   nred=D.empty((n,), torch.int32), iters=D.empty((n,), torch.int32),
+                   gathered=D.empty((world * n,), torch.float64) if world > 1 else None)
+
+        def step():
+            _lib.check(L.sb_cs_f32(d_dyn.data_ptr(), NF, NT, NPAD, 0.0, 0, 1, pitch, keep,
+                                   d_cs.data_ptr(), stream))
+            _lib.check(L.sb_eta_sweep(geom.ref, buf["etas"].data_ptr(), n, thth.DEFAULT_TOL,
+                                      0, buf["eigs"].data_ptr(), buf["stat"].data_ptr(),
+                                      buf["nred"].data_ptr(), buf["iters"].data_ptr(), stream))
+            if world > 1:
+                dist.all_gather_into_tensor(buf["gathered"], buf["eigs"])
+        return buf, step
+
+    def timed(step, warmup, steps):
+        """W warm-up steps, then K steps between barrier + synchronize; device time by
+        CUDA events, max over ranks; per-kernel CUDA-event times, max over ranks."""
+        for _ in range(warmup):
+            step()
+        sync_all()
+        launches0 = L.sb_launch_count()
+        L.sb_profile_enable(1)
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        sync_all()
+        wall0 = time.time()
+        ev0.record()
+        for _ in range(steps):
+            step()
+        ev1.record()
+        sync_all()
+        wall1 = time.time()
+        launches = int(L.sb_launch_count() - launches0)
+        pm, pc = collect_prof(L, _lib)
+        L.sb_profile_enable(0)
+        per = torch.tensor(np.concatenate(([ev0.elapsed_time(ev1)], pm / np.maximum(pc, 1))),
+                           device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(per, op=dist.ReduceOp.MAX)
+        per = per.cpu().numpy()
+        kern = {n_: float(per[1 + i]) for i, n_ in enumerate(PROF_NAMES) if pc[i]}
+        return float(per[0]) / steps, kern, launches, (wall0, wall1)
+
+    # ---- headline (weak) leg ------------------------------------------------
+    wbuf, wstep = make_leg(etas)
+    ms_step, kern, launches, (wall0, wall1) = timed(wstep, args.warmup, args.steps)
     clk = clocks.stop(wall0, wall1)
-
-    eigs = d_eigs.cpu().numpy()
-    nred = d_nred.cpu().numpy().astype(np.int64)
-    iters = d_iter.cpu().numpy()
-    status = d_stat.cpu().numpy()
-    ms_step = ms_total / args.steps
     value = world * NETA / (ms_step * 1e-3)
+    eigs = wbuf["eigs"].cpu().numpy()
+    nred = wbuf["nred"].cpu().numpy().astype(np.int64)
+    iters = wbuf["iters"].cpu().numpy()
+    status = wbuf["stat"].cpu().numpy()
 
-    names = ["cs_rows", "cs_colA", "cs_colB", "thth_prep", "thth_build",
-             "thth_eig", "sspec", "acf", "sim_screen", "sim_freq"]
-    kern = {n: (prof_ms[0][i] / max(1, prof_ms[1][i]))
-            for i, n in enumerate(names) if prof_ms[1][i]}
     # algorithmic bytes of one launch of the sweep kernels: one c64 gather of the
     # strict upper triangle + one f64 eigenvalue per eta (SURVEY.md 8d)
     alg_bytes = float(np.sum(8 * nred * (nred - 1) // 2 + 8))
     dom = max((k for k in kern if k.startswith("thth")), key=lambda k: kern[k])
     peak, peak_src = peak_hbm()
     ach = alg_bytes / (kern[dom] * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak,
-                "traffic": NCU_TRAFFIC_BYTES.get(dom),
-                "traffic_source": "profiles/r1_ncu_full_summary_final.csv (bytes per launch)",
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "iterative solver: the 1 MB triangle is streamed once per Lanczos step "
-                        "(~18 steps) = `traffic`; the on-chip variant that reads it once "
-                        "(eig_cluster.cu, traffic 1.10 GB) measured slower, see DESIGN.md",
+                "note": "iterative solver: every Lanczos step streams the triangle once "
+                        "(bf16 copy, 0.52 MB at N=511, ~18 steps) + one fp32 pass for the "
+                        "Rayleigh quotient = `traffic`; kernel_ms = CUDA events on the launching "
+                        "stream, max over ranks",
                 "kernel_ms": kern}
 
+    # ---- strong-scaling leg: fixed 8192-eta grid split over the ranks ----------
+    strong = None
+    if not args.no_strong:
+        es_all = eta_grid(NETA_STRONG)
+        sbuf, sstep = make_leg(es_all[rank::world])
+        s_ms, s_kern, _, _ = timed(sstep, 2, max(2, args.steps // 2))
+        strong = {"etas_total": NETA_STRONG, "etas_per_gpu": sbuf["n"], "ms_per_step": s_ms,
+                  "value": NETA_STRONG / (s_ms * 1e-3), "unit": "eta-trials/s",
+                  "scaling": "strong", "kernel_ms": s_kern,
+                  "note": "same step (CS recomputed on every rank + sweep + all-gather) over a "
+                          "FIXED grid of 8192 curvatures interleaved over the ranks"}
+        del sbuf
+
     # ---- end to end through the public API, pinned host input ----------
-    h_dyn = torch.from_numpy(dyn).pin_memory()
-    params = [h_dyn.numpy(), freq, t, etas, edges, None, False, FW, NPAD, True,
-              0.0, False]
-    res = None
-    for _ in range(min(2, args.warmup)):
-        res = thth.single_search(params)
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = thth.single_search(params)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_val = world * NETA / (float(e2e_t.item()) / args.steps)
+    def e2e_leg(h_dyn):
+        """ththmod.search_batch over `steps` chunks: every chunk's dynamic spectrum is
+        copied from pinned host memory inside the timed region (the copy of chunk i+1
+        overlaps the sweep of chunk i), eigenvalues come back to the host, the
+        parabola fit runs on the host."""
+        params = [h_dyn, freq, t, etas, edges, None, False, FW, NPAD, True, 0.0, False]
+        thth.search_batch([params] * 2)
+        sync_all()
+        t0 = time.perf_counter()
+        res = thth.search_batch([params] * args.steps)
+        torch.cuda.synchronize()
+        dt_ = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
+        return world * NETA / (float(dt_.item()) / args.steps), res[-1]
+
+    h32 = torch.from_numpy(dyn).pin_memory()
+    e2e_val, res = e2e_leg(h32.numpy())
     e2e = {"value": e2e_val, "unit": "eta-trials/s",
            "h2d_bytes_per_step": int(dyn.nbytes + etas.nbytes + 8 * (NEDGE - 1)),
            "d2h_bytes_per_step": int(8 * NETA),
-           "api": "scintools_b200.ththmod.single_search(params) incl. host "
-                  "parabola fit; dyn float32 in pinned host memory",
-           "eta_fit": float(res[0]) if res is not None else None}
+           "api": "scintools_b200.ththmod.search_batch([params] * steps) (the loop of "
+                  "Dynspec.fit_thetatheta) incl. host parabola fit; dyn float32 in pinned "
+                  "host memory",
+           "eta_fit": float(res[0])}
+    e2e_f64 = None
+    if not args.no_extra:
+        h64 = torch.from_numpy(dyn.astype(np.float64)).pin_memory()
+        v64, _ = e2e_leg(h64.numpy())
+        e2e_f64 = {"value": v64, "unit": "eta-trials/s",
+                   "h2d_bytes_per_step": int(8 * dyn.size + etas.nbytes + 8 * (NEDGE - 1)),
+                   "d2h_bytes_per_step": int(8 * NETA),
+                   "note": "same call with the reference's dtype: float64 host dynamic "
+                           "spectrum (narrowed to fp32 on the device)"}
+        del h64
+    del h32
 
     line = None
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
-            from oracle import thth_oracle as TO   # checker / CPU baseline only
-            full = thth.conjugate_spectrum(dyn, NPAD, 0.0)      # all columns, for the CPU leg
-            CS_host = full.numpy().astype(np.complex64)
-            del full
-            sel = np.linspace(0, NETA - 1, 8).astype(int)
-            secs, ref = cpu_sample(CS_host, tau, fd, edges, etas[sel], 1)
-            rel = np.abs(eigs[sel] - ref) / np.abs(ref)
-            cpu = {"value": len(sel) / secs, "unit": "eta-trials/s", "cores": 1,
-                   "kind": "port",
-                   "sample": "8 of 1024 eta-trials (oracle Eval_calc: numpy "
-                             "gather + scipy ARPACK) on the GPU-built 16384x32768 "
-                             "CS; the CPU fft2 of the CS is not counted",
-                   "max_rel_err_vs_gpu": float(np.nanmax(rel))}
+            cpu = cpu_baseline_leg(thth, dyn, tau, fd, edges, etas, eigs)
+        extra = None
+        if world == 1 and not args.no_extra:
+            extra = other_configs(peak)
         line = {
             "metric": METRIC, "value": value, "unit": "eta-trials/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3 eta-sweep: 4096x8192 dynspec (1-D screen, "
-                                   "64 images, eta_true=0.08 s^3), npad=3 -> CS "
-                                   "16384x32768 (fd>=0 half stored, 2.15 GB c64) recomputed every step, "
-                                   "512-pt theta grid, 1024 etas per GPU",
+            "config": {"workload": WORKLOAD,
                        "etas_total": world * NETA,
-                       "cs_columns": "%d of %d fd>=0 columns computed (those the "
-                                     "512-pt theta grid can reach)" % (keep or nfd // 2 + 1,
-                                                                      nfd // 2 + 1),
-                       "l2": "inputs larger than L2 (CS half-plane 2.15 GB, matrices 1.07 GB)",
+                       "cs": "fd>=0 half stored (2.15 GB c64), recomputed every step; "
+                             "%d of %d fd>=0 columns computed (those the 512-pt theta grid "
+                             "can reach)" % (keep or nfd // 2 + 1, nfd // 2 + 1),
+                       "l2": "inputs larger than L2 (CS half-plane 2.15 GB, matrices 1.6 GB)",
                        "tol": thth.DEFAULT_TOL,
-                       "parallelism": "eta blocks per rank, CS replicated, one "
-                                      "NCCL all-gather of eigenvalues per step"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                       "parallelism": "global eta grid interleaved over the ranks, CS "
+                                      "replicated, one NCCL all-gather of eigenvalues per step"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_f64": e2e_f64,
+            "strong": strong, "extra": extra,
             "gpu_launches": launches, "clocks": clk,
             "sweep": {"nred_min": int(nred.min()), "nred_max": int(nred.max()),
                       "iters_mean": float(iters.mean()), "iters_max": int(iters.max()),
@@ -412,6 +508,81 @@ def b200_arm(args):
     return 0
 
 
+def cpu_baseline_leg(thth, dyn, tau, fd, edges, etas, eigs):
+    """cpu_baseline of the b200 arm: the oracle port on ONE host core (the
+    as-shipped serial eta loop), 1 warm-up + 24 eta-trials (about 10-20 s)."""
+    full = thth.conjugate_spectrum(dyn, NPAD, 0.0)      # all columns, for the CPU leg
+    CS_host = full.numpy().astype(np.complex64)
+    del full
+    one = CpuSweep(CS_host, tau, fd, edges, 1)
+    one.run(etas[:1])
+    sel = np.linspace(0, NETA - 1, 24).astype(int)
+    secs, ref = one.run(etas[sel])
+    one.close()
+    rel = np.abs(eigs[sel] - ref) / np.abs(ref)
+    return {"value": len(sel) / secs, "unit": "eta-trials/s", "cores": 1, "kind": "port",
+            "sample": "24 of 1024 eta-trials after 1 warm-up trial (oracle Eval_calc: numpy "
+                      "gather + scipy ARPACK, 1 BLAS thread) on the GPU-built 16384x32768 "
+                      "CS; the CPU fft2 of the CS is not counted",
+            "max_rel_err_vs_gpu": float(np.nanmax(rel))}
+
+
+def other_configs(peak):
+    """BASELINE.json configs 2 and 4 in the same process (rank 0, one GPU):
+    C2 calc_sspec / calc_acf on a 4096x8192 dynamic spectrum, C4 one 8192^2
+    Simulation realisation (8 frequencies timed).  Device ms = CUDA events of the
+    library call (sb_profile); e2e ms = the public API call from pinned host
+    float32 memory to the host result; frac = algorithmic bytes
+    / device time / measured HBM peak."""
+    import torch
+    from scintools_b200 import _lib, BasicDyn, Dynspec
+    from scintools_b200.scint_sim import Simulation
+    L = _lib.lib
+    rng = np.random.default_rng(2)
+    dyn = torch.from_numpy(rng.exponential(1.0, (NF, NT)).astype(np.float32)).pin_memory().numpy()
+    ds = Dynspec(dyn=BasicDyn(dyn, times=10.0 * np.arange(NT), freqs=1400 + DF * np.arange(NF),
+                              dt=10.0, df=DF), verbose=False)
+
+    def prof(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        L.sb_profile_enable(1)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / reps
+        ms, cnt = collect_prof(L, _lib)
+        L.sb_profile_enable(0)
+        return wall, ms, cnt
+
+    out = {}
+    w, ms, cnt = prof(lambda: ds.calc_sspec(dtype=np.float32), 3)
+    tms = ms[6] / cnt[6]
+    alg = 4 * NF * NT + 4 * NF * 2 * NT
+    out["c2_sspec"] = {"device_ms": tms, "e2e_ms": w * 1e3, "algorithmic_bytes": alg,
+                       "achieved_GBs": alg / tms / 1e6, "frac": alg / tms / 1e6 / peak}
+    w, ms, cnt = prof(lambda: ds.calc_acf(dtype=np.float32), 3)
+    tms = ms[7] / cnt[7]
+    alg = 4 * NF * NT + 4 * 2 * NF * 2 * NT
+    out["c2_acf"] = {"device_ms": tms, "e2e_ms": w * 1e3, "algorithmic_bytes": alg,
+                     "achieved_GBs": alg / tms / 1e6, "frac": alg / tms / 1e6 / peak}
+    del ds, dyn
+    nfreq, n = 8, 8192
+    w, ms, cnt = prof(lambda: Simulation(mb2=2, ns=n, nf=nfreq, dlam=0.25, seed=1,
+                                         device_rng=True), 1)
+    per_f = ms[9] / cnt[9]
+    out["c4_sim"] = {"ns": n, "nf_timed": nfreq, "screen_ms": ms[8] / cnt[8],
+                     "per_freq_ms": per_f, "e2e_s": w,
+                     "per_freq_algorithmic_bytes": 52 * n * n,
+                     "achieved_GBs": 52 * n * n / per_f / 1e6,
+                     "frac": 52 * n * n / per_f / 1e6 / peak,
+                     "realisation_nf256_est_s": (ms[8] / cnt[8] + 256 * per_f) / 1e3,
+                     "note": "the library reads 20 n^2 B per frequency (collapsed inverse, "
+                             "DESIGN.md); frac is quoted against the faithful plan's 52 n^2"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -420,6 +591,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true",
                     help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-strong", action="store_true",
+                    help="skip the strong-scaling leg (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip e2e_f64 and the C2/C4 extra configs (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -1,0 +1,562 @@
+// Mixed-precision streaming Lanczos for the theta-theta eigenvalue
+// (ththmod.Eval_calc, scintools/ththmod.py:371-401): the DEFAULT solver of
+// sb::eta_sweep for ld <= 512.
+//
+// Why: the fp32 streaming solver (thth_eig_kernel, thth.cu) re-reads the 1 MB
+// fp32 triangle on every Lanczos step (19.3 GB per 1024-eta sweep) and spends
+// ~32 thread-instructions per matrix element (masks, shared-memory loads of
+// the vector, per-row reductions).  This kernel
+//   * iterates on the bf16 copy of the triangle written by
+//     thth_build_kernel<true> (4 B per complex element: half the bytes),
+//   * keeps the lane's 16 vector elements and 16 column accumulators in
+//     registers for the whole mat-vec and does the complex multiply-adds with
+//     PACKED fp32 FMAs (Blackwell FFMA2, fma.rn.f32x2, scalar operand broadcast):
+//     one LDS.128 + 4 shifts + 16 FFMA2 per four complex elements; no masks
+//     except on the diagonal group,
+//   * fetches TWO adjacent rows per mbarrier phase (two cp.async.bulk on one
+//     barrier) and reduces their four row sums with six shuffles,
+//   * keeps the Lanczos vectors (fp32) in global memory, forms the Ritz vector
+//     y and reports the Rayleigh quotient <y, A y> / <y, y> with the FP32
+//     triangle in one extra pass.  The Rayleigh quotient is second order in
+//     the vector error (CPU study profiles/probe_mixed_precision.py: <= 5e-7
+//     at n = 511 while the bf16 Ritz value alone is off by 1.7e-4).
+//   * Safety net: the same fp32 pass yields the true residual
+//     ||A y - rho y|| / |rho|; if it exceeds rtol_r (2e-3) the solve continues
+//     as a plain fp32 Lanczos started from y with the stopping rule of
+//     thth_eig_kernel, and reports its Ritz value.
+// Failure modes / status bits as thth_eig_kernel (NaN where the reference's
+// try/except stores NaN).
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "lanczos.cuh"
+#include "tma.cuh"
+
+namespace sb {
+
+enum { EB_ST_INDEX_ERROR = 1, EB_ST_ZERO_START = 2, EB_ST_TOO_SMALL = 4,
+       EB_ST_NOT_CONVERGED = 8 };
+
+constexpr int EB_THREADS = 256;
+constexpr int EB_NW = EB_THREADS / 32;
+constexpr int EB_NST = 2;             // ring stages per warp, 4 KB each
+#ifdef SB_EB_SLOTS
+constexpr int EB_SLOTS = SB_EB_SLOTS; // tests/host_emu: few slots to exercise the fp32 restart
+#else
+constexpr int EB_SLOTS = 48;          // Lanczos vectors kept for the Ritz vector
+#endif
+
+// acc += a * (b, b): one packed fp32 FMA (Blackwell FFMA2; ptxas folds the
+// duplicated scalar into the .F32 broadcast operand form)
+__device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float b) {
+#ifdef SB_HOST_EMU
+    acc.x = fmaf(a.x, b, acc.x);
+    acc.y = fmaf(a.y, b, acc.y);
+#else
+    unsigned long long ra, rb, rc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(rb) : "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(acc.x), "f"(acc.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(rc));
+#endif
+}
+
+// packed element of the bf16 triangle (thth.cu: pack_bf16x2): the low half is
+// bf16(re); the WHOLE word read as a float is the stored im (the packer picks the
+// high half so that this value is the nearest one to im), so only re needs a shift
+__device__ __forceinline__ float2 unpack_bf16x2(const unsigned p) {
+    return make_float2(__uint_as_float(p << 16), __uint_as_float(p));
+}
+
+// shared-memory bytes of one CTA (host + device agree through this)
+__host__ __device__ inline size_t eig_bf16_smem(int ld) {
+    return sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2) +
+           (size_t)EB_NW * EB_NST * 4096 + (size_t)EB_NW * EB_NST * 8 + 16;
+}
+
+__global__ void __launch_bounds__(EB_THREADS, 2)
+thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restrict__ Mbbase,
+                     int ld, const int* __restrict__ nred, int eta0,
+                     double* __restrict__ eigs, int* __restrict__ status,
+                     int* __restrict__ iters, double tol, double etol, double rtol_r,
+                     int max_iter, float2* __restrict__ gbasis) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    LanczosShared& S = *reinterpret_cast<LanczosShared*>(smem_raw);
+    float2* v = reinterpret_cast<float2*>(smem_raw + sizeof(LanczosShared));
+    float2* vp = v + ld;
+    float2* w = vp + ld;          // row sums, then the new Lanczos vector
+    float2* u = w + ld;           // column sums
+    unsigned char* ring = reinterpret_cast<unsigned char*>(u + ld);     // [NW][NST][4096]
+    float2* part = reinterpret_cast<float2*>(ring);                      // [NW][512] scratch (aliases the ring)
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ring + (size_t)EB_NW * EB_NST * 4096);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int e = blockIdx.x;
+    const int n = nred[eta0 + e];
+    const float2* M = Mbase + (size_t)e * ld * ld;
+    const unsigned* Mb = Mbbase + (size_t)e * ld * ld;
+    float2* basis = gbasis + (size_t)e * EB_SLOTS * ld;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    if (status[eta0 + e] & EB_ST_INDEX_ERROR) {
+        if (tid == 0) { eigs[eta0 + e] = qnan; iters[eta0 + e] = 0; }
+        return;
+    }
+    if (n < 3) {
+        if (tid == 0) {
+            eigs[eta0 + e] = qnan; iters[eta0 + e] = 0;
+            status[eta0 + e] |= EB_ST_TOO_SMALL;
+        }
+        return;
+    }
+    // The ring starts out as zeros: positions a row's copy does not cover keep
+    // older (finite) data, which only ever meets vector elements that are zero.
+    for (int i = tid; i < EB_NW * EB_NST * 256; i += EB_THREADS)
+        reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) {
+        for (int i = 0; i < EB_NW * EB_NST; ++i) mbar_init(mbar + i, 1);
+        fence_mbarrier_init();
+    }
+    fence_proxy_async();
+    __syncthreads();
+    const int ncol4 = (n + 1) >> 1;            // fp32 rows: float4 groups = two complex columns
+    const int ncolq = ((n + 3) >> 2) << 2;     // bf16 rows are fetched in multiples of 4 columns
+    unsigned char* mystage = ring + (size_t)warp * EB_NST * 4096;
+    unsigned long long* mybar = mbar + EB_NST * warp;
+    unsigned phbits = 0;                       // bit s: phase parity of this warp's barrier s
+
+    // ------------------------------------------------------------------
+    // bf16 mat-vec: w = (strict upper triangle) v row sums, u = column sums.
+    // Warp `warp` owns the row pairs p = warp + NW k, rows (2p, 2p+1); a lane
+    // owns the columns 4 (lane + 32 j) + i, j < 4, i < 4, of every row.
+    // ------------------------------------------------------------------
+    auto matvec_b = [&]() {
+        for (int c = tid; c < ld; c += EB_THREADS) w[c] = make_float2(0.f, 0.f);
+        float xr[4][8];                        // v at the lane's columns (re, im interleaved)
+        float2 yc[4][4];                       // column accumulators
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c0 = 4 * (lane + 32 * j);
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (c0 < ld) {
+                a = *reinterpret_cast<const float4*>(v + c0);
+                b = *reinterpret_cast<const float4*>(v + c0 + 2);
+            }
+            xr[j][0] = a.x; xr[j][1] = a.y; xr[j][2] = a.z; xr[j][3] = a.w;
+            xr[j][4] = b.x; xr[j][5] = b.y; xr[j][6] = b.z; xr[j][7] = b.w;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) yc[j][i] = make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+        const int npair = n >> 1;              // rows 0 .. n-2  ->  pairs 0 .. (n-2)/2
+        const int K = (npair - 1 >= warp) ? (npair - 1 - warp) / EB_NW + 1 : 0;
+        // Row pair k of this warp: rows a0 = 2 warp + 16 k and a0 + 1.  Their copies start
+        // at the columns c0 = a0 & ~3 and c0 + dc (dc = 0 / 4 by the parity of warp), so the
+        // global offset, the shared offset and the byte counts are all LINEAR in k: the
+        // issuing lane only adds constants.
+        const int dc = (2 * warp) & 2 ? 4 : 0;
+        auto issue = [&](int k) {
+            const int a0 = 2 * warp + 16 * k;
+            const int c0 = ((2 * warp) & ~3) + 16 * k;
+            const unsigned b0 = (unsigned)(ncolq - c0) * 4u;
+            const bool has1 = a0 + 1 <= n - 2;
+            const unsigned b1 = has1 ? b0 - 4u * dc : 0u;
+            unsigned char* dst = mystage + (k % EB_NST) * 4096 + c0 * 4;
+            const unsigned* src = Mb + (unsigned)(a0 * ld + c0);
+            mbar_expect_tx(mybar + k % EB_NST, b0 + b1);
+            bulk_g2s(dst, src, b0, mybar + k % EB_NST);
+            if (has1) bulk_g2s(dst + 2048 + 4 * dc, src + ld + dc, b1, mybar + k % EB_NST);
+        };
+        if (lane == 0)
+            for (int k = 0; k < EB_NST && k < K; ++k) issue(k);
+        float* wflat = reinterpret_cast<float*>(w);
+        for (int k = 0; k < K; ++k) {
+            const int a0 = 2 * warp + 16 * k;
+            const bool has1 = a0 + 1 <= n - 2;
+            float4 xa = *reinterpret_cast<const float4*>(v + a0);     // v[a0], v[a0 + 1]
+            if (!has1) { xa.z = 0.f; xa.w = 0.f; }
+            // column part: yc += conj(A[a][c]) v[a] = (xa.x, xa.y) q.re + (xa.y, -xa.x) q.im
+            const float2 XA0 = make_float2(xa.x, xa.y), XB0 = make_float2(xa.y, -xa.x);
+            const float2 XA1 = make_float2(xa.z, xa.w), XB1 = make_float2(xa.w, -xa.z);
+            const int st = k % EB_NST;
+            while (!mbar_try_wait(mybar + st, (phbits >> st) & 1u)) {}
+            phbits ^= 1u << st;
+            const uint4* s0 = reinterpret_cast<const uint4*>(mystage + st * 4096);
+            const uint4* s1 = s0 + 128;
+            const int JS = (a0 + 1) >> 7;       // column groups entirely left of the diagonal
+            // row part: P += (q.re, q.im) v.re, R += (q.re, q.im) v.im;
+            // row sum = (P.x - R.y, P.y + R.x)
+            float2 P0 = make_float2(0.f, 0.f), R0 = P0, P1 = P0, R1 = P0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < JS) continue;           // warp-uniform
+                const int c16 = lane + 32 * j;
+                uint4 q0 = s0[c16], q1 = s1[c16];
+                if (j == JS) {                  // the group the diagonal crosses
+                    const int rel0 = a0 + 1 - 4 * c16, rel1 = rel0 + 1;
+                    if (rel0 > 0) q0.x = 0u;
+                    if (rel0 > 1) q0.y = 0u;
+                    if (rel0 > 2) q0.z = 0u;
+                    if (rel0 > 3) q0.w = 0u;
+                    if (rel1 > 0) q1.x = 0u;
+                    if (rel1 > 1) q1.y = 0u;
+                    if (rel1 > 2) q1.z = 0u;
+                    if (rel1 > 3) q1.w = 0u;
+                }
+                const unsigned p0[4] = {q0.x, q0.y, q0.z, q0.w};
+                const unsigned p1[4] = {q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xre = xr[j][2 * i], xim = xr[j][2 * i + 1];
+                    const float2 Q0 = unpack_bf16x2(p0[i]);
+                    ffma2(P0, Q0, xre);
+                    ffma2(R0, Q0, xim);
+                    ffma2(yc[j][i], XA0, Q0.x);
+                    ffma2(yc[j][i], XB0, Q0.y);
+                    const float2 Q1 = unpack_bf16x2(p1[i]);
+                    ffma2(P1, Q1, xre);
+                    ffma2(R1, Q1, xim);
+                    ffma2(yc[j][i], XA1, Q1.x);
+                    ffma2(yc[j][i], XB1, Q1.y);
+                }
+            }
+            __syncwarp();                       // every lane is done reading the stage
+            if (lane == 0 && k + EB_NST < K) issue(k + EB_NST);
+            // four row sums (re0, im0, re1, im1) with six shuffles: lanes 0-15 keep
+            // row 0, lanes 16-31 row 1; then bit 3 splits re / im
+            const float r0x = P0.x - R0.y, r0y = P0.y + R0.x;
+            const float r1x = P1.x - R1.y, r1y = P1.y + R1.x;
+            const bool h16 = lane & 16;
+            float kx = h16 ? r1x : r0x, ky = h16 ? r1y : r0y;
+            kx += __shfl_xor_sync(0xffffffffu, h16 ? r0x : r1x, 16);
+            ky += __shfl_xor_sync(0xffffffffu, h16 ? r0y : r1y, 16);
+            const bool h8 = lane & 8;
+            float kk = h8 ? ky : kx;
+            kk += __shfl_xor_sync(0xffffffffu, h8 ? kx : ky, 8);
+            kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+            kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+            kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+            // lanes 0 / 8 / 16 / 24 hold re0, im0, re1, im1 = 4 consecutive floats of w
+            if ((lane & 7) == 0 && (has1 || lane < 16)) wflat[2 * a0 + (lane >> 3)] = kk;
+        }
+        __syncthreads();                        // every warp is done with its stages
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4* dst = reinterpret_cast<float4*>(part + warp * 512 + 4 * (lane + 32 * j));
+            dst[0] = make_float4(yc[j][0].x, yc[j][0].y, yc[j][1].x, yc[j][1].y);
+            dst[1] = make_float4(yc[j][2].x, yc[j][2].y, yc[j][3].x, yc[j][3].y);
+        }
+        __syncthreads();
+        for (int c = tid; c < 512; c += EB_THREADS) {
+            float sx = 0.f, sy = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < EB_NW; ++kk) { sx += part[kk * 512 + c].x; sy += part[kk * 512 + c].y; }
+            if (c < ld) u[c] = make_float2(sx, sy);
+        }
+        __syncthreads();
+        // the scratch aliased the ring: back to zeros (finite, harmless under a
+        // zero vector element), ordered before the next bulk copies (async proxy)
+        for (int i = tid; i < EB_NW * 256; i += EB_THREADS)
+            reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fence_proxy_async();
+        __syncthreads();
+    };
+
+    // ------------------------------------------------------------------
+    // fp32 mat-vec (final Rayleigh quotient, fp32 continuation): one 4 KB row
+    // per stage, generic masks.  The ring may hold bf16 data interpreted as
+    // fp32 (finite: bf16 pairs never have an all-ones exponent in the high
+    // half, see bf16_bits) and vice versa it is re-zeroed afterwards.
+    // ------------------------------------------------------------------
+    auto matvec_f = [&]() {
+        for (int c = tid; c < ld; c += EB_THREADS) w[c] = make_float2(0.f, 0.f);
+        __syncthreads();
+        float4 yc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int K = (n - 2 >= warp) ? (n - 2 - warp) / EB_NW + 1 : 0;
+        auto issue = [&](int k) {
+            const int a2 = warp + EB_NW * k;
+            const int st = k % EB_NST;
+            const int c_lo = (a2 + 1) & ~1;
+            const unsigned bytes = (unsigned)(2 * ncol4 - c_lo) * 8u;
+            mbar_expect_tx(mybar + st, bytes);
+            bulk_g2s(mystage + st * 4096 + c_lo * 8, M + (size_t)a2 * ld + c_lo, bytes, mybar + st);
+        };
+        if (lane == 0)
+            for (int k = 0; k < EB_NST && k < K; ++k) issue(k);
+        for (int k = 0; k < K; ++k) {
+            const int a = warp + EB_NW * k;
+            const int first4 = (a + 1) >> 1;
+            const float2 xa = v[a];
+            const int st = k % EB_NST;
+            while (!mbar_try_wait(mybar + st, (phbits >> st) & 1u)) {}
+            phbits ^= 1u << st;
+            const float4* sg = reinterpret_cast<const float4*>(mystage + st * 4096);
+            float rx = 0.f, ry = 0.f;
+            const int jskip = first4 >> 5;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < jskip) continue;
+                const int c4 = lane + 32 * j;
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c4 >= first4 && c4 < ncol4) q = sg[c4];
+                const float4 x = (2 * c4 < ld) ? *reinterpret_cast<const float4*>(v + 2 * c4)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                rx = fmaf(q.x, x.x, rx); rx = fmaf(-q.y, x.y, rx);
+                rx = fmaf(q.z, x.z, rx); rx = fmaf(-q.w, x.w, rx);
+                ry = fmaf(q.x, x.y, ry); ry = fmaf(q.y, x.x, ry);
+                ry = fmaf(q.z, x.w, ry); ry = fmaf(q.w, x.z, ry);
+                yc[j].x = fmaf(q.x, xa.x, yc[j].x); yc[j].x = fmaf(q.y, xa.y, yc[j].x);
+                yc[j].y = fmaf(q.x, xa.y, yc[j].y); yc[j].y = fmaf(-q.y, xa.x, yc[j].y);
+                yc[j].z = fmaf(q.z, xa.x, yc[j].z); yc[j].z = fmaf(q.w, xa.y, yc[j].z);
+                yc[j].w = fmaf(q.z, xa.y, yc[j].w); yc[j].w = fmaf(-q.w, xa.x, yc[j].w);
+            }
+            __syncwarp();
+            if (lane == 0 && k + EB_NST < K) issue(k + EB_NST);
+            rx = warp_sum(rx);
+            ry = warp_sum(ry);
+            if (lane == 0) w[a] = make_float2(rx, ry);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(part + warp * 512 + 2 * (lane + 32 * j)) = yc[j];
+        __syncthreads();
+        for (int c = tid; c < 512; c += EB_THREADS) {
+            float sx = 0.f, sy = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < EB_NW; ++kk) { sx += part[kk * 512 + c].x; sy += part[kk * 512 + c].y; }
+            if (c < ld) u[c] = make_float2(sx, sy);
+        }
+        __syncthreads();
+        // fp32 rows may leave any bit pattern behind: the bf16 passes need zeros
+        for (int i = tid; i < EB_NW * EB_NST * 256; i += EB_THREADS)
+            reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fence_proxy_async();
+        __syncthreads();
+    };
+
+    // ------------------------------------------------------------------
+    // Lanczos from the normalised vector in v (vp = 0).  BF: iterate on the
+    // bf16 triangle and keep the basis; returns false if the basis slots ran
+    // out.  S.done / S.theta / m describe the outcome.
+    // ------------------------------------------------------------------
+    int m = 0;
+    auto lanczos = [&](bool BF, double et) -> bool {
+        if (tid == 0) {
+            S.done = 0; S.lo = 0.0; S.theta = 0.0; S.res = 0.0; S.m_lo2 = 0; S.lo2 = 0.0;
+            S.next_check = 1; S.beta2[0] = 0.0;
+        }
+        __syncthreads();
+        float beta_prev = 0.f;
+        m = 0;
+        for (int it = 0; it < max_iter; ++it) {
+            if (BF) {
+                if (it >= EB_SLOTS) return false;
+                for (int c = tid; c < ld; c += EB_THREADS) basis[(size_t)it * ld + c] = v[c];
+                matvec_b();
+            } else {
+                matvec_f();
+            }
+            // ---- alpha = Re <v, A v>
+            double apart = 0.0;
+            for (int c = tid; c < n; c += EB_THREADS) {
+                float2 x = w[c];
+                x.x += u[c].x;
+                x.y += u[c].y;
+                w[c] = x;
+                apart += (double)(v[c].x * x.x + v[c].y * x.y);
+            }
+            apart = warp_sum(apart);
+            if (lane == 0) S.red[0][warp] = apart;
+            __syncthreads();
+            double alpha = 0.0;
+            for (int k = 0; k < EB_NW; ++k) alpha += S.red[0][k];
+            // ---- w -= alpha v + beta_prev vp ; beta = ||w||
+            const float af = (float)alpha;
+            double bpart = 0.0;
+            for (int c = tid; c < n; c += EB_THREADS) {
+                float2 x = w[c];
+                x.x -= af * v[c].x + beta_prev * vp[c].x;
+                x.y -= af * v[c].y + beta_prev * vp[c].y;
+                w[c] = x;
+                bpart += (double)x.x * x.x + (double)x.y * x.y;
+            }
+            bpart = warp_sum(bpart);
+            if (lane == 0) S.red[1][warp] = bpart;
+            __syncthreads();
+            double b2 = 0.0;
+            for (int k = 0; k < EB_NW; ++k) b2 += S.red[1][k];
+            const double beta = sqrt(b2);
+            m = it + 1;
+            if (tid == 0) { S.alpha[it] = alpha; S.beta[m] = beta; S.beta2[m] = b2; }
+            __syncthreads();
+            const bool last = (it + 1 == max_iter);
+            if (warp == 0 && (m >= S.next_check || last || !(beta > 0.0)))
+                lanczos_check(S, m, tol, et);
+            __syncthreads();
+            if (S.done || !isfinite(alpha)) break;
+            // ---- rotate: vp = v, v = w / beta
+            const float ib = (float)(1.0 / beta);
+            for (int c = tid; c < n; c += EB_THREADS) {
+                const float2 x = w[c];
+                vp[c] = v[c];
+                v[c] = make_float2(x.x * ib, x.y * ib);
+            }
+            beta_prev = (float)beta;
+            __syncthreads();
+        }
+        return true;
+    };
+
+    // v0 = row n//2 of the Hermitian matrix (ththmod.py:398-399), from the fp32 triangle
+    auto start_vector = [&]() -> bool {
+        const int h = n / 2;
+        double part0 = 0.0;
+        for (int c = tid; c < ld; c += EB_THREADS) {
+            float2 x = make_float2(0.f, 0.f);
+            if (c < n && c > h) x = M[(size_t)h * ld + c];
+            else if (c < h) { x = M[(size_t)c * ld + h]; x.y = -x.y; }
+            v[c] = x;
+            vp[c] = make_float2(0.f, 0.f);
+            part0 += (double)x.x * x.x + (double)x.y * x.y;
+        }
+        part0 = warp_sum(part0);
+        __syncthreads();
+        if (lane == 0) S.red[0][warp] = part0;
+        __syncthreads();
+        double nrm2 = 0.0;
+        for (int k = 0; k < EB_NW; ++k) nrm2 += S.red[0][k];
+        if (!(nrm2 > 0.0) || !isfinite(nrm2)) return false;
+        const float s = (float)(1.0 / sqrt(nrm2));
+        for (int c = tid; c < ld; c += EB_THREADS) { v[c].x *= s; v[c].y *= s; }
+        __syncthreads();
+        return true;
+    };
+
+    if (!start_vector()) {
+        if (tid == 0) {
+            eigs[eta0 + e] = qnan; iters[eta0 + e] = 0;
+            status[eta0 + e] |= EB_ST_ZERO_START;
+        }
+        return;
+    }
+    int steps = 0;
+    const bool fits = lanczos(true, etol);
+    steps = m;
+    bool plain = !fits || !S.done;              // report the fp32 Ritz value instead
+    if (!fits) {                                // more steps than basis slots: redo in fp32
+        start_vector();
+        lanczos(false, etol);
+        steps += m;
+    } else if (S.done) {
+        // ---- Ritz vector of T_m at theta (backward recurrence, grows towards s_0),
+        // y = sum_j s_j q_j, eigenvalue = Rayleigh quotient with the fp32 triangle
+        if (tid == 0) {
+            const double theta = S.theta;
+            double* s = S.piv;
+            s[m - 1] = 1.0;
+            if (m >= 2) s[m - 2] = (S.beta[m - 1] != 0.0) ? (theta - S.alpha[m - 1]) / S.beta[m - 1] : 0.0;
+            for (int i = m - 2; i >= 1; --i) {
+                const double t = (theta - S.alpha[i]) * s[i] - S.beta[i + 1] * s[i + 1];
+                s[i - 1] = (S.beta[i] != 0.0) ? t / S.beta[i] : 0.0;
+                if (fabs(s[i - 1]) > 1e150)
+                    for (int k = i - 1; k < m; ++k) s[k] *= 1e-150;
+            }
+            double nn = 0.0;
+            for (int i = 0; i < m; ++i) nn += s[i] * s[i];
+            nn = 1.0 / sqrt(nn);
+            for (int i = 0; i < m; ++i) s[i] *= nn;
+        }
+        __syncthreads();
+        for (int c = tid; c < ld; c += EB_THREADS) {
+            float sx = 0.f, sy = 0.f;
+            if (c < n) {
+                for (int j = 0; j < m; ++j) {
+                    const float2 q = basis[(size_t)j * ld + c];
+                    const float sj = (float)S.piv[j];
+                    sx = fmaf(sj, q.x, sx);
+                    sy = fmaf(sj, q.y, sy);
+                }
+            }
+            v[c] = make_float2(sx, sy);
+            vp[c] = make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+        matvec_f();
+        double num = 0.0, den = 0.0;
+        for (int c = tid; c < n; c += EB_THREADS) {
+            const float2 y = v[c];
+            float2 ay = w[c];
+            ay.x += u[c].x;
+            ay.y += u[c].y;
+            w[c] = ay;
+            num += (double)y.x * ay.x + (double)y.y * ay.y;
+            den += (double)y.x * y.x + (double)y.y * y.y;
+        }
+        num = warp_sum(num);
+        den = warp_sum(den);
+        if (lane == 0) { S.red[0][warp] = num; S.red[1][warp] = den; }
+        __syncthreads();
+        double sn = 0.0, sd = 0.0;
+        for (int k = 0; k < EB_NW; ++k) { sn += S.red[0][k]; sd += S.red[1][k]; }
+        const double rho = (sd > 0.0) ? sn / sd : 0.0;
+        __syncthreads();
+        double rpart = 0.0;
+        for (int c = tid; c < n; c += EB_THREADS) {
+            const double rx = (double)w[c].x - rho * v[c].x, ry = (double)w[c].y - rho * v[c].y;
+            rpart += rx * rx + ry * ry;
+        }
+        rpart = warp_sum(rpart);
+        if (lane == 0) S.red[0][warp] = rpart;
+        __syncthreads();
+        double r2 = 0.0;
+        for (int k = 0; k < EB_NW; ++k) r2 += S.red[0][k];
+        const bool accept = (sd > 0.0) && isfinite(rho) &&
+                            (r2 <= rtol_r * rtol_r * rho * rho * sd);
+        __syncthreads();
+        if (accept) {
+            if (tid == 0) { eigs[eta0 + e] = fabs(rho); iters[eta0 + e] = steps + 1; }
+            return;
+        }
+        // fp32 continuation from y
+        const float s = (sd > 0.0) ? (float)(1.0 / sqrt(sd)) : 0.f;
+        for (int c = tid; c < ld; c += EB_THREADS) { v[c].x *= s; v[c].y *= s; }
+        __syncthreads();
+        if (!(sd > 0.0)) start_vector();
+        lanczos(false, etol);
+        steps += 1 + m;
+        plain = true;
+    } else {
+        // iteration cap on the bf16 matrix: report what thth_eig_kernel would
+    }
+    if (plain && tid == 0) {
+        eigs[eta0 + e] = fabs(S.theta);
+        iters[eta0 + e] = steps;
+        if (!S.done) status[eta0 + e] |= EB_ST_NOT_CONVERGED;
+    }
+}
+
+#ifndef SB_HOST_EMU
+// d_Mb: the bf16 copy of d_M written by thth_build_kernel<true>.
+int eig_bf16_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* d_nred, int e0,
+                    int nb, double* d_eigs, int* d_status, int* d_iters, double tol, double etol,
+                    int max_iter, cudaStream_t st) {
+    float2* d_basis = (float2*)workspace(7, (size_t)nb * EB_SLOTS * ld * sizeof(float2));
+    if (!d_basis) return SB_ERR_NOMEM;
+    const size_t smem = eig_bf16_smem(ld);
+    double rtol_r = 2e-3;
+    if (const char* ev = getenv("SB_EIG_RTOL_R")) rtol_r = atof(ev);
+    if (const char* ev = getenv("SB_EIG_ETOL_B")) etol = atof(ev);
+    SB_CUDA(cudaFuncSetAttribute(thth_eig_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    thth_eig_bf16_kernel<<<nb, EB_THREADS, smem, st>>>(d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status,
+                                                       d_iters, tol, etol, rtol_r, max_iter, d_basis);
+    SB_LAUNCH_CHECK();
+    return 1;
+}
+#endif  // SB_HOST_EMU
+
+}  // namespace sb

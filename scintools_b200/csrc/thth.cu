@@ -26,11 +26,10 @@ int eig_cluster_launch(const float2* d_M, int ld, int n_max, const int* d_nred, 
                        int nb, double* d_eigs, int* d_status, int* d_iters, double tol,
                        double etol, int max_iter, cudaStream_t st);
 
-// eig_mixed.cu: bf16 iteration + fp32 Rayleigh quotient (SB_EIG_MIXED=1, unverified)
-int eig_mixed_variant(int ld);      // 0: off (default), 1 / 2: SB_EIG_MIXED
-int eig_mixed_launch(const float2* d_M, const unsigned* d_Mb, int variant, int ld,
-                     const int* d_nred, int e0, int nb, double* d_eigs, int* d_status,
-                     int* d_iters, double tol, double etol, int max_iter, cudaStream_t st);
+// eig_bf16.cu: bf16 iteration + fp32 Rayleigh quotient (default for ld <= 512)
+int eig_bf16_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* d_nred, int e0,
+                    int nb, double* d_eigs, int* d_status, int* d_iters, double tol, double etol,
+                    int max_iter, cudaStream_t st);
 
 #endif  // SB_HOST_EMU
 
@@ -93,18 +92,41 @@ __global__ void thth_indexerr_kernel(ThthGeom g, const double* __restrict__ etas
 // block = 32 x 8.  M[e] is [ld][ld] float2; inside the active 32x32 tiles
 // columns >= nred and the diagonal are zero, the lower triangle is not touched.
 // --------------------------------------------------------------------------
-#define SB_BUILD_EB 4
-// PACK: also write the bf16 copy Mb (re | im << 16) that eig_mixed.cu iterates on
+#define SB_BUILD_EB 8
+
+// fp32 pair -> one 32-bit word for eig_bf16.cu: low half = bf16(re) (round to
+// nearest even, no overflow to inf); high half h chosen so that the WHOLE word
+// (h << 16 | low) read as a float is as close to im as any h allows (error <= half
+// a bf16 ulp, like a plain bf16 rounding) -- the solver then uses the word itself as
+// im and only shifts for re.
+__device__ __forceinline__ unsigned pack_bf16x2(float2 v) {
+    const float big = 3.3895313892515355e38f;          // largest finite bf16
+    const unsigned lo = bf16_bits(fminf(fmaxf(v.x, -big), big));
+    const unsigned u = __float_as_uint(fminf(fmaxf(v.y, -big), big));
+    const unsigned m = u & 0x7fffffffu;
+    const unsigned t = m + 0x8000u;
+    const unsigned h = t >= lo ? (t - lo) >> 16 : 0u;
+    return (u & 0x80000000u) | (h << 16) | lo;
+}
+
+// PACK: also write the bf16 copy Mb (re | im << 16) that eig_bf16.cu iterates on.
+//
+// Everything of thth_map's index math that does not depend on eta is computed
+// once per (row, column) pair and kept in registers while the CTA walks its
+// SB_BUILD_EB curvatures: d = theta1^2 - theta2^2, fd_inv with its Hermitian
+// half-plane column / conjugation flag, sqrt|theta2 - theta1|.  Per curvature
+// only tau_inv = floor((eta d - tau0 + dtau/2) / dtau) (same fp64 operations in
+// the same order as thth_point, so the bins stay bit-exact), one gather and the
+// Jacobian remain.  The cached pair is re-derived whenever the crop of the next
+// curvature moves the pair (idx differs).
 template <bool PACK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nbatch,
                   int ld, const int* __restrict__ idx,
                   const int* __restrict__ nred, float2* __restrict__ M,
                   unsigned* __restrict__ Mb) {
-    SB_SHARED int ia[32], ib[32];
-    SB_SHARED double ta_[32], tb_[32];
     // eta is the FAST grid index: CTAs resident at the same time work on the
-    // same 32x32 tile for ~900 neighbouring curvatures, whose gathers fall on
+    // same 32x32 tile for neighbouring curvatures, whose gathers fall on
     // the same / adjacent CS rows for small |theta1^2 - theta2^2| (L2 reuse)
     // pair index -> (ta <= tb)
     int p = blockIdx.y, ta = 0;
@@ -112,43 +134,86 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
     while (p >= T - ta) { p -= T - ta; ++ta; }
     const int tb = ta + p;
     const int tx = threadIdx.x, ty = threadIdx.y;
-  // EB consecutive curvatures per CTA, back to back: their gathers hit the
-  // same or neighbouring CS rows
-  for (int e = blockIdx.x * SB_BUILD_EB; e < min(nbatch, (int)(blockIdx.x + 1) * SB_BUILD_EB); ++e) {
-    const int n = nred[eta0 + e];
-    if (tb * 32 >= n) continue;  // never read by the eigen kernel
-    const double eta = etas[eta0 + e];
-    const int* id = idx + (size_t)(eta0 + e) * ld;
-    __syncthreads();
-    if (ty == 0) {
-        int a = ta * 32 + tx;
-        ia[tx] = a < n ? id[a] : -1;
-        ta_[tx] = a < n ? g.th[id[a]] : 0.0;
-    } else if (ty == 1) {
-        int b = tb * 32 + tx;
-        ib[tx] = b < n ? id[b] : -1;
-        tb_[tx] = b < n ? g.th[id[b]] : 0.0;
-    }
-    __syncthreads();
-    float2* Me = M + (size_t)e * ld * ld;
+    const int b = tb * 32 + tx;
+    const double ntau_d = (double)g.ntau;
+    const long long hfd = g.nfd / 2;
+    // cached eta-independent state of this thread's column and its 4 rows
+    int cj = -2;
+    double thj = 0.0;
+    int ci[4] = {-2, -2, -2, -2};
+    double dk[4];
+    long long col[4];       // CS column to gather; < 0: never a valid point
+    bool conj[4];
+    float wk[4];
+    const int e_end = min(nbatch, (int)(blockIdx.x + 1) * SB_BUILD_EB);
+    for (int e = blockIdx.x * SB_BUILD_EB; e < e_end; ++e) {
+        const int n = nred[eta0 + e];
+        if (tb * 32 >= n) continue;  // never read by the eigen kernel
+        const double eta = etas[eta0 + e];
+        const int* id = idx + (size_t)(eta0 + e) * ld;
+        const int j = b < n ? id[b] : -1;
+        if (j != cj) {
+            cj = j;
+            thj = j >= 0 ? g.th[j] : 0.0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int la = ty + 8 * k, lb = tx;
-        if (ta == tb && lb < la) continue;      // lower triangle: not stored
-        const int i = ia[la], j = ib[lb];
-        float2 v = make_float2(0.f, 0.f);
-        if (i >= 0 && j > i && i + j != g.n - 1) {
-            ThthPoint pt = thth_point(g, eta, tb_[lb], ta_[la]);
-            v = thth_value(g, eta, tb_[lb], ta_[la], pt);
-            v.x = nan_to_num(v.x);
-            v.y = nan_to_num(v.y);
+            for (int k = 0; k < 4; ++k) ci[k] = -2;
         }
-        Me[(size_t)(ta * 32 + la) * ld + tb * 32 + lb] = v;
-        if (PACK)
-            Mb[(size_t)e * ld * ld + (size_t)(ta * 32 + la) * ld + tb * 32 + lb] =
-                bf16_bits(v.x) | (bf16_bits(v.y) << 16);
+        const float seta = sqrtf((float)(2.0 * eta));
+        float2* Me = M + (size_t)e * ld * ld;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int la = ty + 8 * k;
+            if (ta == tb && tx < la) continue;      // lower triangle: not stored
+            const int a = ta * 32 + la;
+            const int i = a < n ? id[a] : -1;
+            if (i != ci[k]) {
+                ci[k] = i;
+                col[k] = -1;
+                conj[k] = false;
+                wk[k] = 0.f;
+                dk[k] = 0.0;
+                if (i >= 0 && j > i && i + j != g.n - 1) {
+                    // th1 = theta of the column, th2 = theta of the row (ththmod.py:86-87)
+                    const double th1 = thj, th2 = g.th[i];
+                    dk[k] = __dsub_rn(__dmul_rn(th1, th1), __dmul_rn(th2, th2));
+                    const double bb = __dadd_rn(__dsub_rn(__dsub_rn(th1, th2), g.fd0), g.half_dfd);
+                    const double fqd = floor_div_fast(bb, g.dfd, g.inv_dfd);
+                    const long long fq = (fqd == fqd && fabs(fqd) < 9.0e18) ? (long long)fqd : LLONG_MIN;
+                    wk[k] = sqrtf((float)fabs(th2 - th1));
+                    if (fq < g.nfd && !(fq < -g.nfd)) {     // pnts mask / IndexError (thth_point)
+                        const long long fi = fq < 0 ? fq + g.nfd : fq;
+                        if (!g.cs_half) col[k] = fi;
+                        else if (fi >= hfd) col[k] = fi - hfd;
+                        else if (fi == 0) col[k] = hfd;
+                        else { col[k] = hfd - fi; conj[k] = true; }   // CS[-tau,-fd] = conj(CS[tau,fd])
+                    }
+                }
+            }
+            float2 v = make_float2(0.f, 0.f);
+            if (col[k] >= 0) {
+                const double aa = __dadd_rn(__dsub_rn(__dmul_rn(eta, dk[k]), g.tau0), g.half_dtau);
+                const double tqd = floor_div_fast(aa, g.dtau, g.inv_dtau);
+                if (tqd > 0.0 && tqd < ntau_d) {            // tau_inv > 0 and < ntau (ththmod.py:100)
+                    const long long tq = (long long)tqd;
+                    const long long r = conj[k] ? g.ntau - tq : tq;
+                    v = __ldg(g.cs + (size_t)r * (size_t)g.cs_pitch + (size_t)col[k]);
+                    if (conj[k]) v.y = -v.y;
+                    if (!g.coherent) v = make_float2(hypotf(v.x, v.y), 0.f);
+                }
+                // Jacobian sqrt|2 eta (th2 - th1)| (ththmod.py:107)
+                const float wf = seta * wk[k];
+                v.x *= wf;
+                v.y *= wf;
+                if (!(fabsf(v.x) <= 3.402823466e+38f) || !(fabsf(v.y) <= 3.402823466e+38f)) {
+                    v.x = nan_to_num(v.x);
+                    v.y = nan_to_num(v.y);
+                }
+            }
+            const size_t o = (size_t)a * ld + b;
+            Me[o] = v;
+            if (PACK) Mb[(size_t)e * ld * ld + o] = pack_bf16x2(v);
+        }
     }
-  }
 }
 
 // --------------------------------------------------------------------------
@@ -607,8 +672,10 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
     if (batch > neta) batch = neta;
     float2* d_M = (float2*)workspace(2, per * batch);
     if (!d_M) return SB_ERR_NOMEM;
-    // round-2 candidate (SB_EIG_MIXED, off by default): bf16 copy written by the build kernel
-    const int mixed = eig_mixed_variant(ld);
+    // default solver for ld <= 512 (eig_bf16.cu): iterates on the bf16 copy written by the
+    // build kernel; SB_EIG_FP32=1 selects the fp32 streaming solver below instead
+    const bool mixed = (ld <= 512) && !getenv("SB_EIG_FP32") && !getenv("SB_EIG_CLUSTER") &&
+                       !getenv("SB_EIG_PERSIST") && !getenv("SB_EIG_NO_TMA");
     unsigned* d_Mb = nullptr;
     if (mixed) {
         d_Mb = (unsigned*)workspace(6, per / 2 * batch);
@@ -654,15 +721,15 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
         SB_LAUNCH_CHECK();
         prof_begin(PROF_THTH_EIG, st);
         // experimental solvers, each enabled by its own environment variable
-        int rc = mixed ? eig_mixed_launch(d_M, d_Mb, mixed, ld, d_nred, e0, nb, d_eigs, d_status,
-                                          d_iters, tol, 2e-7, max_iter, st)
+        int rc = mixed ? eig_bf16_launch(d_M, d_Mb, ld, d_nred, e0, nb, d_eigs, d_status,
+                                         d_iters, tol, 2e-7, max_iter, st)
                        : 0;
         if (rc == 0)
             rc = eig_cluster_launch(d_M, ld, g.n, d_nred, e0, nb, d_eigs, d_status, d_iters,
                                     tol, 2e-7, max_iter, st);
         if (rc < 0) return rc;
         if (rc > 0) {
-            // handled by eig_mixed.cu / eig_cluster.cu
+            // handled by eig_bf16.cu / eig_cluster.cu
         } else if (use_tma && persist > 0)
             thth_eig_kernel<TT, true, PS, true><<<persist < nb ? persist : nb, TT, smem_p, st>>>(
                 d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter, nb);

@@ -2,14 +2,18 @@
 #pragma once
 
 #ifdef SB_HOST_EMU
-// tests/host_emu/simt.h: bulk copies complete synchronously, the 8-byte barrier
-// word holds the phase parity
+// tests/host_emu/simt.h: bulk copies complete synchronously; the 8-byte barrier
+// word holds the phase parity (bit 0) and the pending transaction bytes (bits 8+),
+// so that several copies can complete one phase
 namespace sb {
 inline void mbar_init(unsigned long long* bar, int) { *bar = 0; }
-inline void mbar_expect_tx(unsigned long long*, unsigned) {}
+inline void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    *bar += (unsigned long long)bytes << 8;
+}
 inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
     std::memcpy(dst, src, bytes);
-    *bar ^= 1ull;
+    *bar -= (unsigned long long)bytes << 8;
+    if ((*bar >> 8) == 0) *bar ^= 1ull;
 }
 inline bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
     if ((unsigned)(*bar & 1ull) != parity) return true;

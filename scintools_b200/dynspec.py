@@ -522,7 +522,7 @@ class Dynspec:
         if self.thetatheta_proc == 'thin':
             results = [thth.single_search_thin(p) for p in pars]
         else:
-            results = [thth.single_search(p) for p in pars]
+            results = thth.search_batch(pars)
         for (cf, ct), res in zip(where, results):
             self.eta_evo[cf, ct] = U.value(res[0], "s3")
             self.eta_evo_err[cf, ct] = U.value(res[1], "s3")

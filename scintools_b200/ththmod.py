@@ -153,6 +153,58 @@ class _Geom:
         return ctypes.byref(self.g)
 
 
+class _SweepJob:
+    """An eta sweep in flight on the current stream: device outputs, pinned host
+    mirrors (asynchronous device->host copies) and the event that marks them
+    complete.  ``finish()`` waits for the event only -- the stream keeps running
+    whatever was enqueued after the sweep."""
+
+    def __init__(self, cs, geom, d_etas, neta, tol, max_iter, pinned):
+        import torch
+        self.keep = (cs, geom, d_etas)           # referenced until the kernels ran
+        self.eigs = D.empty((neta,), torch.float64)
+        self.status = D.empty((neta,), torch.int32)
+        self.nred = D.empty((neta,), torch.int32)
+        self.iters = D.empty((neta,), torch.int32)
+        _lib.check(_lib.lib.sb_eta_sweep(geom.ref, d_etas.data_ptr(), neta, tol,
+                                         max_iter, self.eigs.data_ptr(),
+                                         self.status.data_ptr(), self.nred.data_ptr(),
+                                         self.iters.data_ptr(), D.stream_ptr()))
+        self.host = None
+        if pinned:
+            self.host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                         for t in (self.eigs, self.status, self.nred, self.iters)]
+            for h, t in zip(self.host, (self.eigs, self.status, self.nred, self.iters)):
+                h.copy_(t, non_blocking=True)
+            self.event = torch.cuda.Event()
+            self.event.record()
+
+    def finish(self, return_info=False):
+        if self.host is not None:
+            self.event.synchronize()
+            out, st, nred, iters = [h.numpy().copy() for h in self.host]
+        else:
+            out = self.eigs.cpu().numpy()
+            st = self.status.cpu().numpy()
+            nred = self.nred.cpu().numpy()
+            iters = self.iters.cpu().numpy()
+        self.keep = None
+        # iteration cap hit without convergence: ARPACK raises ArpackNoConvergence in
+        # the reference and the eta loop stores NaN (ththmod.py:795-799)
+        out[(st & 8) != 0] = np.nan
+        if return_info:
+            return out, dict(status=st, nred=nred, iters=iters)
+        return out
+
+
+def _sweep_launch(CS, tau, fd, etas, edges, coher=True, tol=DEFAULT_TOL, max_iter=0,
+                  pinned=False):
+    cs = _as_device_cs(CS)
+    geom = _Geom(cs, tau, fd, edges, coher)
+    ev = np.ascontiguousarray(np.atleast_1d(U.value(etas, "s3")))
+    return _SweepJob(cs, geom, D.upload(ev), ev.shape[0], tol, max_iter, pinned)
+
+
 def eta_sweep(CS, tau, fd, etas, edges, coher=True, tol=DEFAULT_TOL,
               max_iter=0, return_info=False):
     """Largest-eigenvalue curve over ``etas`` (float64 array, NaN where the
@@ -160,29 +212,7 @@ def eta_sweep(CS, tau, fd, etas, edges, coher=True, tol=DEFAULT_TOL,
 
     One launch sequence for the whole sweep: crop masks, gather + Hermitian
     fill, Lanczos; one eta per thread block."""
-    import torch
-    cs = _as_device_cs(CS)
-    geom = _Geom(cs, tau, fd, edges, coher)
-    ev = np.ascontiguousarray(np.atleast_1d(U.value(etas, "s3")))
-    neta = ev.shape[0]
-    d_etas = D.upload(ev)
-    eigs = D.empty((neta,), torch.float64)
-    status = D.empty((neta,), torch.int32)
-    nred = D.empty((neta,), torch.int32)
-    iters = D.empty((neta,), torch.int32)
-    _lib.check(_lib.lib.sb_eta_sweep(geom.ref, d_etas.data_ptr(), neta, tol,
-                                     max_iter, eigs.data_ptr(),
-                                     status.data_ptr(), nred.data_ptr(),
-                                     iters.data_ptr(), D.stream_ptr()))
-    out = eigs.cpu().numpy()
-    st = status.cpu().numpy()
-    # iteration cap hit without convergence: ARPACK raises ArpackNoConvergence in
-    # the reference and the eta loop stores NaN (ththmod.py:795-799)
-    out[(st & 8) != 0] = np.nan
-    if return_info:
-        return out, dict(status=st, nred=nred.cpu().numpy(),
-                         iters=iters.cpu().numpy())
-    return out
+    return _sweep_launch(CS, tau, fd, etas, edges, coher, tol, max_iter).finish(return_info)
 
 
 def Eval_calc(CS, tau, fd, eta, edges):
@@ -361,10 +391,12 @@ def single_search(params):
     [dspec2, freq, time, etas, edges, name, plot, fw, npad, coher, tauMask,
     verbose]; returns (eta_fit, eta_sig, freq.mean(), time.mean(), eigs).
     Plotting is not part of the hot path: ``plot=True`` raises."""
-    return _single_search(params, None)
+    return _search_finish(_search_launch(params, None))
 
 
-def _single_search(params, staged):
+def _search_launch(params, staged, pinned=False):
+    """Enqueue the device work of one single_search (CS + sweep) on the current
+    stream; nothing here waits for the GPU."""
     (dspec2, freq, time, etas, edges, name, plot, fw, npad, coher, tauMask,
      verbose) = params
     if plot:
@@ -380,7 +412,15 @@ def _single_search(params, staged):
     tau = U.value(fft_axis(freq_v, "us", npad), "us")
     cs = conjugate_spectrum(dspec2, npad, None, tau, tauMask,
                             ncols_keep=needed_fd_columns(fd, edges))
-    eigs = eta_sweep(cs, tau, fd, etas_v, edges, bool(coher))
+    job = _sweep_launch(cs, tau, fd, etas_v, edges, bool(coher), pinned=pinned)
+    return job, params, time_v, freq_v, etas_v
+
+
+def _search_finish(launched):
+    """Wait for the eigenvalues of a launched search and fit the peak on the host."""
+    job, params, time_v, freq_v, etas_v = launched
+    (_, freq, time, etas, _, _, _, fw, _, _, _, verbose) = params
+    eigs = job.finish()
     eta_fit, eta_sig, _ = peak_fit(etas_v, eigs, fw)
     if verbose:
         print("Chunk completed (eta = %s +- %s at %s)" %
@@ -390,32 +430,39 @@ def _single_search(params, staged):
             U.wrap(time_v.mean(), "s", like=time), eigs)
 
 
+_copy_stream = {}
+
+
 def search_batch(params_list):
     """single_search over a sequence of chunks -- the loop of
     Dynspec.fit_thetatheta (dynspec.py:1680-1712) / ``pool.map(single_search,
-    pars)`` (:1715-1719) -- with the host->device copy of chunk i+1 running on
-    a copy stream while chunk i is swept.  The copy is asynchronous when the
-    dynamic spectra sit in pinned host memory; otherwise it is merely issued
-    early.  Returns the list of single_search results, in order.
+    pars)`` (:1715-1719) -- as a two-deep software pipeline:
 
-    EXPERIMENTAL: results are verified (GPU parity tests), but the one timing
-    taken so far (5 x 134 MB dynspecs, no warm-up of the copy stream) was
-    slower than calling single_search in a loop, so neither fit_thetatheta nor
-    bench.py use it yet."""
+      * the host->device copy of chunk i+1 runs on a persistent copy stream
+        while chunk i is swept (asynchronous when the dynamic spectra sit in
+        pinned host memory; float64 input is narrowed on the device);
+      * the device work of chunk i+1 (CS + sweep + asynchronous read-back of
+        the eigenvalues into pinned memory) is enqueued BEFORE the host waits
+        for chunk i and fits its parabola, so the GPU never idles behind the
+        host-side scipy fit.
+
+    Returns the list of single_search results, in order."""
     import torch
     params_list = list(params_list)
     if not params_list:
         return []
-    D.device()
+    dev = D.device()
     main = torch.cuda.current_stream()
-    side = torch.cuda.Stream()
+    side = _copy_stream.get(dev)
+    if side is None:
+        side = _copy_stream[dev] = torch.cuda.Stream()
 
     def stage(p):
         a = np.asarray(p[0])
         if a.dtype not in (np.float32, np.float64):
             a = a.astype(np.float64)
         with torch.cuda.stream(side):
-            t = torch.from_numpy(np.ascontiguousarray(a)).to(D.device(), non_blocking=True)
+            t = torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
             if t.dtype != torch.float32:
                 t32 = torch.empty(t.shape, dtype=torch.float32, device=t.device)
                 _lib.check(_lib.lib.sb_convert_f64_f32(t.data_ptr(), t32.data_ptr(), t.numel(),
@@ -427,12 +474,17 @@ def search_batch(params_list):
         return t, ev
 
     out = []
-    nxt = stage(params_list[0])
+    staged = stage(params_list[0])
+    prev = None
     for i, p in enumerate(params_list):
-        t, ev = nxt
+        t, ev = staged
         main.wait_event(ev)
-        nxt = stage(params_list[i + 1]) if i + 1 < len(params_list) else None
-        out.append(_single_search(p, t))
+        launched = _search_launch(p, t, pinned=True)
+        staged = stage(params_list[i + 1]) if i + 1 < len(params_list) else None
+        if prev is not None:
+            out.append(_search_finish(prev))
+        prev = launched
+    out.append(_search_finish(prev))
     return out
 
 

@@ -2,8 +2,9 @@
 // SIMT emulator: thth_prep_kernel (crop mask + compaction), thth_indexerr_kernel,
 // thth_build_kernel (gather into the strict upper triangle) and
 // thth_eig_kernel<256, TMA, 2> (bulk-copy ring + Lanczos), sources unchanged,
-// launch geometry as in sb::eta_sweep.  Optionally the triangle goes through
-// csrc/eig_mixed.cu instead of thth_eig_kernel (mixed != 0).
+// launch geometry as in sb::eta_sweep.  mixed != 0: the default solver
+// csrc/eig_bf16.cu (bf16 iteration + fp32 Rayleigh quotient) instead of the fp32
+// thth_eig_kernel; -DSB_EB_SLOTS=3 exercises its fp32 restart.
 // TEST INFRASTRUCTURE (tests/test_host_emulation.py).
 #define SB_HOST_EMU 1
 #include "simt.h"
@@ -17,13 +18,14 @@ namespace sb {
 alignas(128) unsigned char smem_raw[256 * 1024];
 }
 #include "../../scintools_b200/csrc/thth.cu"
-#include "../../scintools_b200/csrc/eig_mixed.cu"
+#include "../../scintools_b200/csrc/eig_bf16.cu"
 
 extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, long long cs_pitch,
                              int cs_half, double tau0, double dtau, double tau_absmax, double fd0,
                              double dfd, double fd_half, const double* th, int n_th, int coherent,
                              const double* etas, int neta, double tol, int max_iter, int mixed,
-                             double* eigs, int* status, int* nred, int* iters) {
+                             double* eigs, int* status, int* nred, int* iters,
+                             float* M_out) {
     using namespace sb;
     ThthGeom g;
     g.cs = reinterpret_cast<const float2*>(cs);
@@ -62,21 +64,21 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
                                    thth_build_kernel<false>(g, etas, 0, neta, ld, idx.data(), nred,
                                                             M.data(), nullptr);
                            });
+    if (M_out) std::memcpy(M_out, M.data(), M.size() * sizeof(float2));   // [neta][ld][ld] triangle
     if (max_iter <= 0 || max_iter > SB_LANCZOS_MAXIT) max_iter = SB_LANCZOS_MAXIT;
     if (mixed) {
-        std::vector<__half2> gbasis((size_t)neta * EM_NBG * ld);
-        for (int e = 0; e < neta; ++e)
-            emu::run_block(emu::Dim3{(unsigned)EM_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
+        // mixed = 1: default thresholds; 2: residual threshold 0 -> every curvature takes
+        // the fp32 continuation from the Ritz vector
+        std::vector<float2> gbasis((size_t)neta * EB_SLOTS * ld);
+        for (int e = 0; e < neta; ++e) {
+            std::memset(smem_raw, 0xa5, sizeof(smem_raw));     // garbage, like real shared memory
+            emu::run_block(emu::Dim3{(unsigned)EB_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
                            emu::Dim3{(unsigned)neta, 1, 1}, [&]() {
-                               if (mixed >= 2)
-                                   thth_eig_mixed_kernel<4, true>(M.data(), Mb.data(), ld, nred, 0,
-                                                                  eigs, status, iters, tol, 2e-7,
-                                                                  max_iter, gbasis.data());
-                               else
-                                   thth_eig_mixed_kernel<2, false>(M.data(), Mb.data(), ld, nred, 0,
-                                                                   eigs, status, iters, tol, 2e-7,
-                                                                   max_iter, nullptr);
+                               thth_eig_bf16_kernel(M.data(), Mb.data(), ld, nred, 0, eigs, status,
+                                                    iters, tol, 2e-7, mixed >= 2 ? 0.0 : 2e-3,
+                                                    max_iter, gbasis.data());
                            });
+        }
     } else {
         for (int e = 0; e < neta; ++e)
             emu::run_block(emu::Dim3{256, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},

@@ -528,16 +528,19 @@ def test_search_batch_matches_single_search(sb, golden_dir):
         assert x[0] == pytest.approx(y[0], rel=1e-6)
 
 
-@pytest.mark.parametrize("variant", ["1", "2"])
-def test_eta_sweep_mixed_precision_solver(sb, sample, monkeypatch, variant):
-    """SB_EIG_MIXED=1/2: bf16 Lanczos iteration + fp32 Rayleigh quotient."""
+@pytest.mark.parametrize("env", [{}, {"SB_EIG_FP32": "1"}, {"SB_EIG_RTOL_R": "0"}])
+def test_eta_sweep_mixed_precision_solver(sb, sample, monkeypatch, env):
+    """Default solver (eig_bf16.cu: bf16 Lanczos iteration + fp32 Rayleigh
+    quotient), the fp32 streaming solver (SB_EIG_FP32=1) and the default solver
+    with its fp32 continuation forced on every curvature (SB_EIG_RTOL_R=0)."""
     g, CS = sample
-    monkeypatch.setenv("SB_EIG_MIXED", variant)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     eigs, info = sb.ththmod.eta_sweep(CS, g["tau"], g["fd"], g["etas"], g["edges"],
                                       return_info=True)
     assert (np.abs(eigs - g["eigs"]) / g["eigs"]).max() < RTOL
     assert (info["status"] == 0).all()
-    # slowly converging random spectrum: more steps than basis slots -> fp32 restart
+    # slowly converging random spectrum (small gaps, many steps)
     rng = np.random.default_rng(77)
     R = rng.normal(size=CS.shape) + 1j * rng.normal(size=CS.shape)
     etas = g["etas"][::16]

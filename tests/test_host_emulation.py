@@ -140,54 +140,33 @@ def _triangles(golden_dir, etas_idx):
     return g, M, nred, ld
 
 
-@pytest.mark.parametrize("slots,variant", [(24, 1), (3, 1), (24, 2), (3, 2)])
-def test_eig_mixed_kernel_on_host(golden_dir, slots, variant):
-    """csrc/eig_mixed.cu under the SIMT emulator (tests/host_emu/simt.h): the
-    bf16 Lanczos iteration + fp32 Rayleigh quotient (slots=24) and the fp32
-    restart taken when the basis slots run out (slots=3) both reproduce the
-    reference eigenvalues of the tutorial chunk."""
-    src = os.path.join(EMU, "eig_mixed_emu.cpp")
-    out = os.path.join(EMU, "_build", "eig_mixed_emu_%d.so" % slots)
-    os.makedirs(os.path.dirname(out), exist_ok=True)
-    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DSB_EM_NB=%d" % slots,
-                    "-x", "c++", src, "-o", out], check=True)
-    lib = ctypes.CDLL(out)
-    idx = [5, 37, 60]
-    g, M, nred, ld = _triangles(golden_dir, idx)
-    nb = len(idx)
-    eigs = np.zeros(nb)
-    status = np.zeros(nb, np.int32)
-    iters = np.zeros(nb, np.int32)
-    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    lib.emu_eig_mixed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
-                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                  ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int]
-    Mc = np.ascontiguousarray(M)
-    lib.emu_eig_mixed(P(Mc), ld, P(nred), nb, P(eigs), P(status), P(iters), 2e-5, 2e-7, 256,
-                      variant)
-    ref = g["eigs"][idx]
-    assert (status == 0).all(), status
-    assert (np.abs(eigs - ref) / ref).max() < 1e-5, (eigs, ref, iters)
-    assert iters.max() < 64
-
-
-@pytest.mark.parametrize("mixed", [0, 1, 2])
-def test_default_sweep_kernels_on_host(golden_dir, mixed):
-    """The DEFAULT device code of the curvature sweep (csrc/thth.cu:
-    thth_prep_kernel, thth_indexerr_kernel, thth_build_kernel,
-    thth_eig_kernel<256, TMA, 2>) under the SIMT emulator, launch geometry as in
-    sb::eta_sweep, against the reference: cropped sizes bit-exact, eigenvalues to
-    1e-5.  mixed=1 routes the same triangle through csrc/eig_mixed.cu."""
-    from oracle import thth_oracle as TO
+def _sweep_emu_lib(slots=0):
+    """tests/host_emu/sweep_emu.cpp compiled for the CPU; slots > 0 shrinks the
+    Lanczos-basis capacity of eig_bf16.cu so that its fp32 restart is taken."""
     src = os.path.join(EMU, "sweep_emu.cpp")
-    out = os.path.join(EMU, "_build", "sweep_emu.so")
+    out = os.path.join(EMU, "_build", "sweep_emu%s.so" % ("_s%d" % slots if slots else ""))
     os.makedirs(os.path.dirname(out), exist_ok=True)
     csrc = os.path.join(ROOT, "scintools_b200", "csrc")
     newest = max(os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc))
+    newest = max(newest, os.path.getmtime(os.path.join(EMU, "simt.h")))
     if not os.path.exists(out) or os.path.getmtime(out) < max(newest, os.path.getmtime(src)):
-        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC",
-                        "-x", "c++", src, "-o", out], check=True)
-    lib = ctypes.CDLL(out)
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC"] +
+                       (["-DSB_EB_SLOTS=%d" % slots] if slots else []) +
+                       ["-x", "c++", src, "-o", out], check=True)
+    return ctypes.CDLL(out)
+
+
+@pytest.mark.parametrize("mixed,slots", [(0, 0), (1, 0), (2, 0), (1, 3)])
+def test_default_sweep_kernels_on_host(golden_dir, mixed, slots):
+    """The device code of the curvature sweep (csrc/thth.cu: thth_prep_kernel,
+    thth_indexerr_kernel, thth_build_kernel; csrc/eig_bf16.cu) under the SIMT
+    emulator, launch geometry as in sb::eta_sweep, against the reference: cropped
+    sizes bit-exact, eigenvalues to 1e-5.  mixed=0: the fp32 streaming solver
+    thth_eig_kernel<256, TMA, 2> (SB_EIG_FP32=1); mixed=1: the default solver
+    (bf16 iteration + fp32 Rayleigh quotient); mixed=2: its fp32 continuation
+    forced on every curvature; slots=3: its fp32 restart (basis slots exhausted)."""
+    from oracle import thth_oracle as TO
+    lib = _sweep_emu_lib(slots)
     g = np.load(os.path.join(golden_dir, "thth_sample_64x150.npz"))
     d0 = g["dspec2"] - g["dspec2"].mean()
     CS = TO.conjugate_spectrum(d0, int(g["npad"]), 0.0)
@@ -204,15 +183,27 @@ def test_default_sweep_kernels_on_host(golden_dir, mixed):
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     c_ll, c_d, c_i, vp = ctypes.c_longlong, ctypes.c_double, ctypes.c_int, ctypes.c_void_p
     lib.emu_eta_sweep.argtypes = [vp, c_ll, c_ll, c_ll, c_i, c_d, c_d, c_d, c_d, c_d, c_d, vp, c_i,
-                                  c_i, vp, c_i, c_d, c_i, c_i, vp, vp, vp, vp]
+                                  c_i, vp, c_i, c_d, c_i, c_i, vp, vp, vp, vp, vp]
+    ld = 32 * ((len(th) + 31) // 32)
+    Mout = np.zeros((neta, ld, ld), np.complex64)
     rc = lib.emu_eta_sweep(P(cs32), CS.shape[0], CS.shape[1], CS.shape[1], 0, float(tau[0]),
                            float(np.diff(tau).mean()), float(abs(tau.max())), float(fd[0]),
                            float(np.diff(fd).mean()), float(abs(fd.max()) / 2), P(th), len(th), 1,
-                           P(etas), neta, 2e-5, 0, mixed, P(eigs), P(status), P(nred), P(iters))
+                           P(etas), neta, 2e-5, 0, mixed, P(eigs), P(status), P(nred), P(iters),
+                           P(Mout))
     assert rc == 0
     want_n = [int(TO.th_points(tau, fd, e, g["edges"]).sum()) for e in etas]
     assert list(nred) == want_n
     assert (status == 0).all()
+    # the triangle written by thth_build_kernel against the reference's thth_redmap:
+    # same gathered bins (any wrong bin is an O(1) error), fp32 rounding only
+    for e in range(neta):
+        A = TO.thth_redmap(CS, tau, fd, etas[e], g["edges"])[0]
+        n = A.shape[0]
+        up = np.triu(A, 1)
+        got = np.triu(Mout[e, :n, :n], 1)
+        assert np.abs(got - up).max() <= 1e-6 * np.abs(up).max()
+        assert np.all(Mout[e, :n, :n][np.diag_indices(n)] == 0)
     ref = g["eigs"][sel]
     assert (np.abs(eigs - ref) / ref).max() < 1e-5, (eigs, ref)
 
@@ -294,13 +285,26 @@ def test_default_sweep_kernels_on_host_random(nedge, half, coherent, mixed):
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     c_ll, c_d, c_i, vp = ctypes.c_longlong, ctypes.c_double, ctypes.c_int, ctypes.c_void_p
     lib.emu_eta_sweep.argtypes = [vp, c_ll, c_ll, c_ll, c_i, c_d, c_d, c_d, c_d, c_d, c_d, vp, c_i,
-                                  c_i, vp, c_i, c_d, c_i, c_i, vp, vp, vp, vp]
+                                  c_i, vp, c_i, c_d, c_i, c_i, vp, vp, vp, vp, vp]
+    ld = 32 * ((len(th) + 31) // 32)
+    Mout = np.zeros((neta, ld, ld), np.complex64)
     rc = lib.emu_eta_sweep(P(buf), CS.shape[0], CS.shape[1], pitch, half, float(tau[0]),
                            float(np.diff(tau).mean()), float(abs(tau.max())), float(fd[0]),
                            float(np.diff(fd).mean()), float(abs(fd.max()) / 2), P(th), len(th),
                            coherent, P(etas), neta, 2e-5, 0, mixed, P(eigs), P(status), P(nred),
-                           P(iters))
+                           P(iters), P(Mout))
     assert rc == 0
+    for e in range(neta):       # built triangle vs the reference's thth_redmap (cropped sizes vary)
+        try:
+            A = TO.thth_redmap(src, tau, fd, etas[e], edges)[0]
+        except Exception:
+            continue
+        n = A.shape[0]
+        if n < 2 or status[e] != 0:
+            continue
+        up = np.triu(A, 1)
+        got = np.triu(Mout[e, :n, :n], 1)
+        assert np.abs(got - up).max() <= 1e-6 * max(np.abs(up).max(), 1e-30)
     want_n = [int(TO.th_points(tau, fd, e, edges).sum()) for e in etas]
     assert list(nred) == want_n
     assert np.array_equal(np.isnan(eigs), np.isnan(ref)), (eigs, ref, status)
