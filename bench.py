@@ -384,7 +384,9 @@ def b200_arm(args):
         launches = int(L.sb_launch_count() - launches0)
         pm, pc = collect_prof(L, _lib)
         L.sb_profile_enable(0)
-        per = torch.tensor(np.concatenate(([ev0.elapsed_time(ev1)], pm / np.maximum(pc, 1))),
+        # per-kernel device time PER STEP (a kernel may be launched several times per
+        # step: column chunks of the CS, eta batches of a long sweep)
+        per = torch.tensor(np.concatenate(([ev0.elapsed_time(ev1)], pm / steps)),
                            device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(per, op=dist.ReduceOp.MAX)

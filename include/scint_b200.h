@@ -182,6 +182,26 @@ int sb_scale_dyn_lambda_f32(const float* dyn, int32_t nf, int32_t nt, int32_t fl
                             float p0, float pn, const int32_t* idx, const float* w4,
                             int32_t nlam, float* out, void* stream);
 
+/* Dynspec.norm_sspec, the resampling loop (scintools/dynspec.py:2076-2107) and
+ * self.powerspectrum (:2120): row ii of the secondary spectrum sspec [nr][nc] (dB,
+ * already cropped / masked by the caller like :2040-2046) is resampled with
+ * numpy.interp at the nq normalised Doppler values fdopnew[] on the axis
+ * fdop / sqrt(tdel[ii] / eta) restricted to |fdop| <= maxnormfac * sqrt(tdel[ii]/eta).
+ * out: float [nr][nq], NaN where the reference's mask is set (|fdopnew| beyond the
+ * row's reach, or a NaN sample); power: double [nr] = masked mean of 10^(out/10).
+ * fdop [nc], tdel [nr], fdopnew [nq]: device float64 (the reference's own axes). */
+int sb_norm_sspec_f32(const float* sspec, int32_t nr, int32_t nc, const double* fdop,
+                      const double* tdel, double eta, double maxnormfac,
+                      const double* fdopnew, int32_t nq, float* out, double* power,
+                      void* stream);
+
+/* Delay-scrunched profile of Dynspec.norm_sspec (scintools/dynspec.py:2159-2166):
+ * avg[j] = sum_ii w[ii] norm[ii][j] / sum_ii w[ii] over the unmasked (non-NaN)
+ * entries of column j (np.ma.average(normSspec, axis=0, weights=w)); NaN where a
+ * column is fully masked.  This is fit_arc's power-vs-curvature profile (:1156-1180). */
+int sb_norm_sspec_avg_f32(const float* norm, int32_t nr, int32_t nq, const double* weights,
+                          double* avg, void* stream);
+
 /* Replaces the arithmetic of Dynspec.calc_sspec (scintools/dynspec.py:3664-3721):
  *   x = win_t[t]*win_f[f]*(dyn - mean(dyn)); x -= mean(x); [prewhite: 2x2
  *   first difference]; |FFT2 zero-padded to nrfft x ncfft|^2; fftshift;

@@ -295,6 +295,54 @@ def golden_norm_sspec(pkg):
     print("norm_sspec:", np.shape(ds.normsspec))
 
 
+def golden_fit_arc(pkg):
+    """Dynspec.fit_arc of the reference (dynspec.py:970-1346) on a 1-D-screen dynamic
+    spectrum with a clear arc, wavelength steps (the mode prep_thetatheta uses,
+    dynspec.py:1458-1466: scale_dyn + calc_sspec(lamsteps=True) + norm_sspec):
+    default call, asymmetric fit, explicit curvature range + log parabola; plus the
+    norm_sspec products of the default call (oracle pin for SURVEY 8f rank 2).
+    (lamsteps=False needs hand-tuned curvature ranges in the reference and reads
+    self.beta anyway, :1089; norm_sspec(lamsteps=False) is pinned by norm_sspec_64x96.)"""
+    rng = np.random.default_rng(41)
+    nf, nt, dt, df, f0 = 128, 160, 8.0, 0.25, 1300.0
+    eta_true = 0.35                                         # us / mHz^2
+    nimg = 200
+    fdk = rng.uniform(-14.0, 14.0, nimg)
+    ak = (rng.normal(size=nimg) + 1j * rng.normal(size=nimg)) * np.exp(-(fdk / 7.0) ** 2)
+    ak[0] += 12.0
+    fdk[0] = 0.0
+    t = dt * np.arange(nt)
+    f = df * np.arange(nf)
+    E = sum(a * np.exp(2j * np.pi * (fd_ * 1e-3 * t[None, :] - eta_true * fd_ ** 2 * f[:, None]))
+            for a, fd_ in zip(ak, fdk))
+    dyn = np.abs(E) ** 2
+    dyn = dyn + rng.normal(0.0, 0.02 * dyn.mean(), dyn.shape)
+    out = dict(dyn=dyn, dt=dt, df=df, f0=f0, eta_true=eta_true)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ds = _ref_dynspec(pkg, dyn.copy(), dt, df, f0)
+        ds.fit_arc(lamsteps=True, plot=False)
+        out.update(betaeta=ds.betaeta, betaetaerr=ds.betaetaerr, betaetaerr2=ds.betaetaerr2,
+                   noise=ds.noise, eta_array=ds.eta_array,
+                   norm_sspec_avg=np.ma.filled(ds.norm_sspec_avg, np.nan),
+                   nsa=np.ma.filled(ds.normsspecavg, np.nan), nsf=ds.normsspec_fdop,
+                   nst=ds.normsspec_tdel, powerspectrum=np.ma.filled(ds.powerspectrum, np.nan),
+                   lamsspec=ds.lamsspec, beta=ds.beta, fdop=ds.fdop, tdel=ds.tdel,
+                   freq=float(ds.freq), prob_eta_peak=np.ma.filled(ds.prob_eta_peak, np.nan))
+        ds.fit_arc(lamsteps=True, asymm=True, plot=False, nsmooth=7, low_power_diff=-2.0,
+                   high_power_diff=-1.0)
+        out.update(betaeta_left=ds.betaeta_left, betaeta_right=ds.betaeta_right,
+                   betaetaerr_left=ds.betaetaerr_left, betaetaerr_right=ds.betaetaerr_right)
+        ds.fit_arc(lamsteps=True, numsteps=4000, etamin=300.0, etamax=12000.0,
+                   log_parabola=True, plot=False, weighted=True, cutmid=5, startbin=4)
+        out.update(betaeta_log=ds.betaeta, betaetaerr_log=ds.betaetaerr,
+                   betaetaerr2_log=ds.betaetaerr2)
+    np.savez_compressed(os.path.join(GOLD, "fit_arc_128x160.npz"), **out)
+    print("fit_arc: betaeta %.2f +- %.2f (parabola %.2f), left %.2f right %.2f, log %.2f"
+          % (out["betaeta"], out["betaetaerr"], out["betaetaerr2"], out["betaeta_left"],
+             out["betaeta_right"], out["betaeta_log"]))
+
+
 def golden_sim(pkg):
     """scint_sim.Simulation at 64^2 / 32x96, seeded (legacy MT19937)."""
     Sim = pkg.scint_sim.Simulation
@@ -341,6 +389,8 @@ def main():
         golden_scale_dyn(pkg)
     if not only or "norm" in only:
         golden_norm_sspec(pkg)
+    if not only or "fitarc" in only:
+        golden_fit_arc(pkg)
     if not only or "sim" in only:
         golden_sim(pkg)
     for fn in sorted(os.listdir(GOLD)):

@@ -72,6 +72,8 @@ _SIGS = {
     "sb_gerchberg_saxton_f32": (c_int, [vp, vp, vp, c_int, c_int, c_int, vp]),
     "sb_scale_dyn_lambda_f32": (c_int, [vp, c_int, c_int, c_int, vp, vp, vp, vp, c_flt, c_flt,
                                         vp, vp, c_int, vp, vp]),
+    "sb_norm_sspec_f32": (c_int, [vp, c_int, c_int, vp, vp, c_dbl, c_dbl, vp, c_int, vp, vp, vp]),
+    "sb_norm_sspec_avg_f32": (c_int, [vp, c_int, c_int, vp, vp, vp]),
     "sb_ifft2_c2c_f32": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, c_dbl, c_int, vp, vp]),
     "sb_acf_f32": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp]),
     "sb_acf_sspec_f32": (c_int, [vp, c_int, c_int, vp, vp, c_dbl, c_dbl, c_int, vp, vp]),

@@ -150,6 +150,11 @@ int ifft2_c2c(const float2* in, int n0, int n1, int centred, int crop0, int crop
 int gerchberg_saxton(float2* W, const float* amp, const unsigned char* rowmask, int n0, int n1,
                      int niter, cudaStream_t st);
 
+int norm_sspec_rows(const float* sspec, int nr, int nc, const double* fdop, const double* tdel,
+                    double eta, double maxnormfac, const double* fdopnew, int nq, float* out,
+                    double* power, cudaStream_t st);
+int norm_sspec_avg(const float* norm, int nr, int nq, const double* weights, double* avg,
+                   cudaStream_t st);
 int scale_dyn_lambda(const float* dyn, int nf, int nt, int flip, const float* a,
                      const float* cp, const float* inv, const float* g, float p0, float pn,
                      const int* idx, const float4* W, int nlam, float* out, cudaStream_t st);
@@ -329,6 +334,21 @@ int sb_scale_dyn_lambda_f32(const float* dyn, int32_t nf, int32_t nt, int32_t fl
     SB_ARG(dyn && a && cp && inv && g && idx && w4 && out && nt >= 1 && nlam >= 1);
     return sb::scale_dyn_lambda(dyn, nf, nt, flip_rows, a, cp, inv, g, p0, pn, idx,
                                 (const float4*)w4, nlam, out, (cudaStream_t)stream);
+}
+
+int sb_norm_sspec_f32(const float* sspec, int32_t nr, int32_t nc, const double* fdop,
+                      const double* tdel, double eta, double maxnormfac,
+                      const double* fdopnew, int32_t nq, float* out, double* power,
+                      void* stream) {
+    SB_ARG(sspec && fdop && tdel && fdopnew && out && power && nr >= 1 && nc >= 2 && nq >= 1);
+    return sb::norm_sspec_rows(sspec, nr, nc, fdop, tdel, eta, maxnormfac, fdopnew, nq, out,
+                               power, (cudaStream_t)stream);
+}
+
+int sb_norm_sspec_avg_f32(const float* norm, int32_t nr, int32_t nq, const double* weights,
+                          double* avg, void* stream) {
+    SB_ARG(norm && weights && avg && nr >= 1 && nq >= 1);
+    return sb::norm_sspec_avg(norm, nr, nq, weights, avg, (cudaStream_t)stream);
 }
 
 int sb_sspec_f32(const float* dyn, int32_t nf, int32_t nt, const float* win_t,

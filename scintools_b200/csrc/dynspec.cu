@@ -10,6 +10,7 @@
 // Reference: scintools/dynspec.py:3664-3721 (sspec), :3780-3797 (acf),
 //            scintools/ththmod.py:777-787 + dynspec.py:1572-1579 (CS).
 #include <map>
+#include <stdlib.h>
 
 #include "fft_kernels.cuh"
 #include "chirp.cuh"
@@ -338,6 +339,65 @@ static int rows_r2c(const DynRowLoad& ld, float2* H, long pitch, int NT,
     return SB_OK;
 }
 
+// ---------------------------------------------------------------- TMA maps
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library
+// does not link libcuda).  Returns false when the driver has no such symbol.
+typedef CUresult (*TmaEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmaEncodeFn tma_encoder() {
+    static TmaEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+                cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (TmaEncodeFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// float2 matrix [rows][pitch] seen as float32; tiles of L rows x W complex.
+// r2 > 0: rank-3 view (col, y < r2, i) of the row i * r2 + y with `nlive / r2`
+// valid i (rows >= nlive read as zeros); r2 == 0: plain rank-2 (col, row).
+static bool make_tile_map(CUtensorMap* m, const float2* base, long pitch, int ncols, long nrows,
+                          int r2, int L, int W) {
+    TmaEncodeFn enc = tma_encoder();
+    if (!enc) return false;
+    cuuint64_t gdim[3], gstr[2];
+    cuuint32_t box[3], estr[3] = {1, 1, 1};
+    cuuint32_t rank;
+    gdim[0] = 2ull * (cuuint64_t)ncols;
+    box[0] = 2u * (cuuint32_t)W;
+    if (r2 > 0) {
+        rank = 3;
+        gdim[1] = (cuuint64_t)r2;
+        gdim[2] = (cuuint64_t)(nrows / r2);
+        gstr[0] = (cuuint64_t)pitch * sizeof(float2);
+        gstr[1] = (cuuint64_t)r2 * pitch * sizeof(float2);
+        box[1] = 1;
+        box[2] = (cuuint32_t)L;
+    } else {
+        rank = 2;
+        gdim[1] = (cuuint64_t)nrows;
+        gstr[0] = (cuuint64_t)pitch * sizeof(float2);
+        box[1] = (cuuint32_t)L;
+    }
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, (void*)base, gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Column transform of length NF (four-step split R1 x R2, two tile passes) over the
+// half spectra H[live][pitch] -> epilogue stb.  Tiles are fetched by the TMA
+// (cp.async.bulk.tensor, zero fill for the padded rows) whenever the live rows are
+// whole r2-groups; SB_FFT_NO_TMA=1 forces the LDG path.  The columns are walked in
+// chunks whose intermediate A[NF][chunk] stays L2-resident between pass A and
+// pass B (SB_COL_CHUNK_MB, default 48; 0 = one chunk).
 template <class StoreB>
 static int cols_forward(const float2* H, float2* A, long pitch, int NF, int live,
                         int ncols, StoreB stb, cudaStream_t st, int profA = -1,
@@ -348,15 +408,40 @@ static int cols_forward(const float2* H, float2* A, long pitch, int NF, int live
     if (!wR) return SB_ERR_NOMEM;
     ColALoad la{H, pitch, R2, live};
     ColAStore sa{A, pitch, R2, NF, wR};
-    int rc = SB_OK;
-    if (profA >= 0) prof_begin(profA, st);
-    SB_TILE_DISPATCH(R1, rc = (launch_tile_fft<float, LL, 32, -1>(la, sa, ncols, R2, st)));
-    if (profA >= 0) prof_end(profA, st);
-    if (rc) return rc;
     ColBLoad lb{A, pitch, R2};
-    if (profB >= 0) prof_begin(profB, st);
-    SB_TILE_DISPATCH(R2, rc = (launch_tile_fft<float, LL, 64, -1>(lb, stb, ncols, R1, st)));
-    if (profB >= 0) prof_end(profB, st);
+    static const bool no_tma = getenv("SB_FFT_NO_TMA") != nullptr;
+    CUtensorMap mapA, mapB;
+    const bool tma = !no_tma && live % R2 == 0 && live >= R2 && R1 <= 256 && R2 <= 256 &&
+                     make_tile_map(&mapA, H, pitch, ncols, live, R2, R1, 32) &&
+                     make_tile_map(&mapB, A, pitch, ncols, NF, 0, R2, 64);
+    long chunk_mb = 48;
+    if (const char* ev = getenv("SB_COL_CHUNK_MB")) chunk_mb = atol(ev);
+    int cw = ncols;
+    if (chunk_mb > 0) {
+        const long c = (chunk_mb << 20) / ((long)NF * (long)sizeof(float2));
+        cw = (int)((c / 64) * 64);
+        if (cw < 256) cw = 256;
+        if (cw > ncols) cw = ncols;
+    }
+    int rc = SB_OK;
+    for (int cb = 0; cb < ncols && rc == SB_OK; cb += cw) {
+        const int ce = cb + cw < ncols ? cb + cw : ncols;
+        if (profA >= 0) prof_begin(profA, st);
+        if (tma) {
+            SB_TILE_DISPATCH(R1, rc = (launch_tile_fft_tma<LL, 32, -1, 3>(mapA, sa, ncols, R2, st, cb, ce)));
+        } else {
+            SB_TILE_DISPATCH(R1, rc = (launch_tile_fft<float, LL, 32, -1>(la, sa, ncols, R2, st, cb, ce)));
+        }
+        if (profA >= 0) prof_end(profA, st);
+        if (rc) return rc;
+        if (profB >= 0) prof_begin(profB, st);
+        if (tma) {
+            SB_TILE_DISPATCH(R2, rc = (launch_tile_fft_tma<LL, 64, -1, 2>(mapB, stb, ncols, R1, st, cb, ce)));
+        } else {
+            SB_TILE_DISPATCH(R2, rc = (launch_tile_fft<float, LL, 64, -1>(lb, stb, ncols, R1, st, cb, ce)));
+        }
+        if (profB >= 0) prof_end(profB, st);
+    }
     return rc;
 }
 

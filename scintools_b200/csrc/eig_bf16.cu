@@ -91,7 +91,10 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     unsigned char* ring = reinterpret_cast<unsigned char*>(u + ld);     // [NW][NST][4096]
     float2* part = reinterpret_cast<float2*>(ring);                      // [NW][512] scratch (aliases the ring)
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ring + (size_t)EB_NW * EB_NST * 4096);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp index through a shuffle: tells the compiler it is warp-uniform, so the
+    // bulk-copy addresses below live in uniform registers (no per-lane election loops)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int e = blockIdx.x;
     const int n = nred[eta0 + e];
     const float2* M = Mbase + (size_t)e * ld * ld;
@@ -131,9 +134,15 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     // Warp `warp` owns the row pairs p = warp + NW k, rows (2p, 2p+1); a lane
     // owns the columns 4 (lane + 32 j) + i, j < 4, i < 4, of every row.
     // ------------------------------------------------------------------
-    auto matvec_b = [&]() {
+    // Row pairs are dealt in a pattern of 15: warp 0 takes 1, warps 1..7 take 2, because
+    // warp 0 also runs the (deferred) convergence check of the previous step while
+    // the others are already in this mat-vec (check_m > 0).
+    auto pair_of = [&](int k) -> int {
+        return warp == 0 ? 7 + 15 * k : 15 * (k >> 1) + ((k & 1) ? warp + 7 : warp - 1);
+    };
+    auto matvec_b = [&](int check_m, double et) {
         for (int c = tid; c < ld; c += EB_THREADS) w[c] = make_float2(0.f, 0.f);
-        float xr[4][8];                        // v at the lane's columns (re, im interleaved)
+        float2 X[4][4];                        // v at the lane's columns
         float2 yc[4][4];                       // column accumulators
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -143,36 +152,36 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
                 a = *reinterpret_cast<const float4*>(v + c0);
                 b = *reinterpret_cast<const float4*>(v + c0 + 2);
             }
-            xr[j][0] = a.x; xr[j][1] = a.y; xr[j][2] = a.z; xr[j][3] = a.w;
-            xr[j][4] = b.x; xr[j][5] = b.y; xr[j][6] = b.z; xr[j][7] = b.w;
+            X[j][0] = make_float2(a.x, a.y); X[j][1] = make_float2(a.z, a.w);
+            X[j][2] = make_float2(b.x, b.y); X[j][3] = make_float2(b.z, b.w);
 #pragma unroll
             for (int i = 0; i < 4; ++i) yc[j][i] = make_float2(0.f, 0.f);
         }
         __syncthreads();
         const int npair = n >> 1;              // rows 0 .. n-2  ->  pairs 0 .. (n-2)/2
-        const int K = (npair - 1 >= warp) ? (npair - 1 - warp) / EB_NW + 1 : 0;
-        // Row pair k of this warp: rows a0 = 2 warp + 16 k and a0 + 1.  Their copies start
-        // at the columns c0 = a0 & ~3 and c0 + dc (dc = 0 / 4 by the parity of warp), so the
-        // global offset, the shared offset and the byte counts are all LINEAR in k: the
-        // issuing lane only adds constants.
-        const int dc = (2 * warp) & 2 ? 4 : 0;
+        int K;
+        if (warp == 0) K = npair > 7 ? (npair - 8) / 15 + 1 : 0;
+        else K = (npair > warp - 1 ? (npair - warp) / 15 + 1 : 0) +
+                 (npair > warp + 7 ? (npair - 8 - warp) / 15 + 1 : 0);
         auto issue = [&](int k) {
-            const int a0 = 2 * warp + 16 * k;
-            const int c0 = ((2 * warp) & ~3) + 16 * k;
+            const int a0 = 2 * pair_of(k);
+            const int c0 = a0 & ~3;            // = (a0 + 1) & ~3 for even a0
+            const int c1 = (a0 + 2) & ~3;
             const unsigned b0 = (unsigned)(ncolq - c0) * 4u;
             const bool has1 = a0 + 1 <= n - 2;
-            const unsigned b1 = has1 ? b0 - 4u * dc : 0u;
-            unsigned char* dst = mystage + (k % EB_NST) * 4096 + c0 * 4;
-            const unsigned* src = Mb + (unsigned)(a0 * ld + c0);
+            const unsigned b1 = has1 ? (unsigned)(ncolq - c1) * 4u : 0u;
+            unsigned char* dst = mystage + (k % EB_NST) * 4096;
+            const unsigned* src = Mb + (unsigned)(a0 * ld);
             mbar_expect_tx(mybar + k % EB_NST, b0 + b1);
-            bulk_g2s(dst, src, b0, mybar + k % EB_NST);
-            if (has1) bulk_g2s(dst + 2048 + 4 * dc, src + ld + dc, b1, mybar + k % EB_NST);
+            bulk_g2s(dst + c0 * 4, src + c0, b0, mybar + k % EB_NST);
+            if (has1) bulk_g2s(dst + 2048 + c1 * 4, src + ld + c1, b1, mybar + k % EB_NST);
         };
         if (lane == 0)
             for (int k = 0; k < EB_NST && k < K; ++k) issue(k);
+        if (check_m > 0 && warp == 0) lanczos_check(S, check_m, tol, et);
         float* wflat = reinterpret_cast<float*>(w);
         for (int k = 0; k < K; ++k) {
-            const int a0 = 2 * warp + 16 * k;
+            const int a0 = 2 * pair_of(k);
             const bool has1 = a0 + 1 <= n - 2;
             float4 xa = *reinterpret_cast<const float4*>(v + a0);     // v[a0], v[a0 + 1]
             if (!has1) { xa.z = 0.f; xa.w = 0.f; }
@@ -185,9 +194,9 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             const uint4* s0 = reinterpret_cast<const uint4*>(mystage + st * 4096);
             const uint4* s1 = s0 + 128;
             const int JS = (a0 + 1) >> 7;       // column groups entirely left of the diagonal
-            // row part: P += (q.re, q.im) v.re, R += (q.re, q.im) v.im;
-            // row sum = (P.x - R.y, P.y + R.x)
-            float2 P0 = make_float2(0.f, 0.f), R0 = P0, P1 = P0, R1 = P0;
+            // row part: sum += (v.re, v.im) q.re + (-v.im, v.re) q.im  (scalar q operands:
+            // the packed word needs no pairing, only one shift for q.re)
+            float2 S0a = make_float2(0.f, 0.f), S0b = S0a, S1a = S0a, S1b = S0a;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (j < JS) continue;           // warp-uniform
@@ -208,15 +217,16 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
                 const unsigned p1[4] = {q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float xre = xr[j][2 * i], xim = xr[j][2 * i + 1];
+                    const float2 x = X[j][i];
+                    const float2 xrot = make_float2(-x.y, x.x);
                     const float2 Q0 = unpack_bf16x2(p0[i]);
-                    ffma2(P0, Q0, xre);
-                    ffma2(R0, Q0, xim);
+                    ffma2(S0a, x, Q0.x);
+                    ffma2(S0b, xrot, Q0.y);
                     ffma2(yc[j][i], XA0, Q0.x);
                     ffma2(yc[j][i], XB0, Q0.y);
                     const float2 Q1 = unpack_bf16x2(p1[i]);
-                    ffma2(P1, Q1, xre);
-                    ffma2(R1, Q1, xim);
+                    ffma2(S1a, x, Q1.x);
+                    ffma2(S1b, xrot, Q1.y);
                     ffma2(yc[j][i], XA1, Q1.x);
                     ffma2(yc[j][i], XB1, Q1.y);
                 }
@@ -225,8 +235,8 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             if (lane == 0 && k + EB_NST < K) issue(k + EB_NST);
             // four row sums (re0, im0, re1, im1) with six shuffles: lanes 0-15 keep
             // row 0, lanes 16-31 row 1; then bit 3 splits re / im
-            const float r0x = P0.x - R0.y, r0y = P0.y + R0.x;
-            const float r1x = P1.x - R1.y, r1y = P1.y + R1.x;
+            const float r0x = S0a.x + S0b.x, r0y = S0a.y + S0b.y;
+            const float r1x = S1a.x + S1b.x, r1y = S1a.y + S1b.y;
             const bool h16 = lane & 16;
             float kx = h16 ? r1x : r0x, ky = h16 ? r1y : r0y;
             kx += __shfl_xor_sync(0xffffffffu, h16 ? r0x : r1x, 16);
@@ -344,71 +354,107 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     // out.  S.done / S.theta / m describe the outcome.
     // ------------------------------------------------------------------
     int m = 0;
-    auto lanczos = [&](bool BF, double et) -> bool {
+    int mv = 0;                                 // mat-vecs done (reported as iters)
+    auto lanczos_init = [&]() {
         if (tid == 0) {
             S.done = 0; S.lo = 0.0; S.theta = 0.0; S.res = 0.0; S.m_lo2 = 0; S.lo2 = 0.0;
-            S.next_check = 1; S.beta2[0] = 0.0;
+            S.next_check = 1; S.m_last = 0; S.beta2[0] = 0.0;
         }
         __syncthreads();
+    };
+    // alpha, the new (unnormalised) Lanczos vector in w and beta of step `it`
+    auto step_scalars = [&](int it, float beta_prev, double& alpha, double& beta) {
+        double apart = 0.0;
+        for (int c = tid; c < n; c += EB_THREADS) {
+            float2 x = w[c];
+            x.x += u[c].x;
+            x.y += u[c].y;
+            w[c] = x;
+            apart += (double)(v[c].x * x.x + v[c].y * x.y);
+        }
+        apart = warp_sum(apart);
+        if (lane == 0) S.red[0][warp] = apart;
+        __syncthreads();
+        alpha = 0.0;
+        for (int k = 0; k < EB_NW; ++k) alpha += S.red[0][k];
+        const float af = (float)alpha;
+        double bpart = 0.0;
+        for (int c = tid; c < n; c += EB_THREADS) {
+            float2 x = w[c];
+            x.x -= af * v[c].x + beta_prev * vp[c].x;
+            x.y -= af * v[c].y + beta_prev * vp[c].y;
+            w[c] = x;
+            bpart += (double)x.x * x.x + (double)x.y * x.y;
+        }
+        bpart = warp_sum(bpart);
+        if (lane == 0) S.red[1][warp] = bpart;
+        __syncthreads();
+        double b2 = 0.0;
+        for (int k = 0; k < EB_NW; ++k) b2 += S.red[1][k];
+        beta = sqrt(b2);
+        if (tid == 0) { S.alpha[it] = alpha; S.beta[it + 1] = beta; S.beta2[it + 1] = b2; }
+        __syncthreads();
+    };
+    auto rotate = [&](double beta) {
+        const float ib = (float)(1.0 / beta);
+        for (int c = tid; c < n; c += EB_THREADS) {
+            const float2 x = w[c];
+            vp[c] = v[c];
+            v[c] = make_float2(x.x * ib, x.y * ib);
+        }
+        __syncthreads();
+    };
+    // ------------------------------------------------------------------
+    // bf16 Lanczos from the normalised vector in v (vp = 0), basis kept.  The
+    // convergence check of the tridiagonal T_it runs on warp 0 DURING mat-vec it
+    // (one step late), so nobody idles behind its Sturm sweeps; when it reports
+    // convergence the step just taken is surplus and m = it.  Returns false if
+    // the basis slots ran out.
+    // ------------------------------------------------------------------
+    auto lanczos_b = [&](double et) -> bool {
+        lanczos_init();
         float beta_prev = 0.f;
         m = 0;
         for (int it = 0; it < max_iter; ++it) {
-            if (BF) {
-                if (it >= EB_SLOTS) return false;
-                for (int c = tid; c < ld; c += EB_THREADS) basis[(size_t)it * ld + c] = v[c];
-                matvec_b();
-            } else {
-                matvec_f();
-            }
-            // ---- alpha = Re <v, A v>
-            double apart = 0.0;
-            for (int c = tid; c < n; c += EB_THREADS) {
-                float2 x = w[c];
-                x.x += u[c].x;
-                x.y += u[c].y;
-                w[c] = x;
-                apart += (double)(v[c].x * x.x + v[c].y * x.y);
-            }
-            apart = warp_sum(apart);
-            if (lane == 0) S.red[0][warp] = apart;
-            __syncthreads();
-            double alpha = 0.0;
-            for (int k = 0; k < EB_NW; ++k) alpha += S.red[0][k];
-            // ---- w -= alpha v + beta_prev vp ; beta = ||w||
-            const float af = (float)alpha;
-            double bpart = 0.0;
-            for (int c = tid; c < n; c += EB_THREADS) {
-                float2 x = w[c];
-                x.x -= af * v[c].x + beta_prev * vp[c].x;
-                x.y -= af * v[c].y + beta_prev * vp[c].y;
-                w[c] = x;
-                bpart += (double)x.x * x.x + (double)x.y * x.y;
-            }
-            bpart = warp_sum(bpart);
-            if (lane == 0) S.red[1][warp] = bpart;
-            __syncthreads();
-            double b2 = 0.0;
-            for (int k = 0; k < EB_NW; ++k) b2 += S.red[1][k];
-            const double beta = sqrt(b2);
+            if (it >= EB_SLOTS) return false;
+            for (int c = tid; c < ld; c += EB_THREADS) basis[(size_t)it * ld + c] = v[c];
+            const bool chk = it >= 1 && it >= S.next_check;
+            matvec_b(chk ? it : 0, et);
+            ++mv;
+            double alpha, beta;
+            step_scalars(it, beta_prev, alpha, beta);
+            if (chk && S.done) { m = it; break; }
             m = it + 1;
-            if (tid == 0) { S.alpha[it] = alpha; S.beta[m] = beta; S.beta2[m] = b2; }
-            __syncthreads();
+            if (it + 1 == max_iter || !(beta > 0.0)) {      // last word: check T_m now
+                if (warp == 0) lanczos_check(S, m, tol, et);
+                __syncthreads();
+                break;
+            }
+            if (!isfinite(alpha)) break;
+            rotate(beta);
+            beta_prev = (float)beta;
+        }
+        return true;
+    };
+    // plain fp32 Lanczos (restart / continuation), check after every step as thth_eig_kernel
+    auto lanczos_f = [&](double et) {
+        lanczos_init();
+        float beta_prev = 0.f;
+        m = 0;
+        for (int it = 0; it < max_iter; ++it) {
+            matvec_f();
+            ++mv;
+            double alpha, beta;
+            step_scalars(it, beta_prev, alpha, beta);
+            m = it + 1;
             const bool last = (it + 1 == max_iter);
             if (warp == 0 && (m >= S.next_check || last || !(beta > 0.0)))
                 lanczos_check(S, m, tol, et);
             __syncthreads();
             if (S.done || !isfinite(alpha)) break;
-            // ---- rotate: vp = v, v = w / beta
-            const float ib = (float)(1.0 / beta);
-            for (int c = tid; c < n; c += EB_THREADS) {
-                const float2 x = w[c];
-                vp[c] = v[c];
-                v[c] = make_float2(x.x * ib, x.y * ib);
-            }
+            rotate(beta);
             beta_prev = (float)beta;
-            __syncthreads();
         }
-        return true;
     };
 
     // v0 = row n//2 of the Hermitian matrix (ththmod.py:398-399), from the fp32 triangle
@@ -443,14 +489,11 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         }
         return;
     }
-    int steps = 0;
-    const bool fits = lanczos(true, etol);
-    steps = m;
+    const bool fits = lanczos_b(etol);
     bool plain = !fits || !S.done;              // report the fp32 Ritz value instead
     if (!fits) {                                // more steps than basis slots: redo in fp32
         start_vector();
-        lanczos(false, etol);
-        steps += m;
+        lanczos_f(etol);
     } else if (S.done) {
         // ---- Ritz vector of T_m at theta (backward recurrence, grows towards s_0),
         // y = sum_j s_j q_j, eigenvalue = Rayleigh quotient with the fp32 triangle
@@ -518,7 +561,7 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
                             (r2 <= rtol_r * rtol_r * rho * rho * sd);
         __syncthreads();
         if (accept) {
-            if (tid == 0) { eigs[eta0 + e] = fabs(rho); iters[eta0 + e] = steps + 1; }
+            if (tid == 0) { eigs[eta0 + e] = fabs(rho); iters[eta0 + e] = mv + 1; }
             return;
         }
         // fp32 continuation from y
@@ -526,15 +569,15 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         for (int c = tid; c < ld; c += EB_THREADS) { v[c].x *= s; v[c].y *= s; }
         __syncthreads();
         if (!(sd > 0.0)) start_vector();
-        lanczos(false, etol);
-        steps += 1 + m;
+        lanczos_f(etol);
+        ++mv;                                  // the fp32 Rayleigh-quotient pass
         plain = true;
     } else {
         // iteration cap on the bf16 matrix: report what thth_eig_kernel would
     }
     if (plain && tid == 0) {
         eigs[eta0 + e] = fabs(S.theta);
-        iters[eta0 + e] = steps;
+        iters[eta0 + e] = mv;
         if (!S.done) status[eta0 + e] |= EB_ST_NOT_CONVERGED;
     }
 }

@@ -13,7 +13,10 @@
 //                    matrix (four-step inside shared memory).  Variants:
 //                    complex->complex, real->half-spectrum, half-spectrum->real.
 #pragma once
+#include <cuda.h>      // CUtensorMap (type only; the encoder is fetched through the runtime)
+
 #include "fft_core.cuh"
+#include "tma.cuh"
 
 namespace sb {
 
@@ -30,14 +33,14 @@ template <> struct ILog2<1> { static constexpr int value = 0; };
 // --------------------------------------------------------------------------
 template <typename T, int L, int W, int DIR, class Load, class Store>
 __global__ void __launch_bounds__(256)
-tile_fft_kernel(Load ld, Store st, const cx<T>* __restrict__ twL, int ncols) {
+tile_fft_kernel(Load ld, Store st, const cx<T>* __restrict__ twL, int ncols, int col_base) {
     using C = cx<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* s = reinterpret_cast<C*>(smem_raw);
     C* tw = s + L * W;
     const int tid = threadIdx.x;
     constexpr int NT = 256;
-    const int c0 = blockIdx.x * W;
+    const int c0 = col_base + blockIdx.x * W;
     const int y = blockIdx.y;
     for (int i = tid; i < L; i += NT) tw[i] = twL[i];
     for (int idx = tid; idx < L * W; idx += NT) {
@@ -52,15 +55,88 @@ tile_fft_kernel(Load ld, Store st, const cx<T>* __restrict__ twL, int ncols) {
     }
 }
 
+// columns [col_base, col_end) of the problem (col_end <= ncols_total is the store limit)
 template <typename T, int L, int W, int DIR, class Load, class Store>
-int launch_tile_fft(Load ld, Store st, int ncols, int ny, cudaStream_t stream) {
+int launch_tile_fft(Load ld, Store st, int ncols, int ny, cudaStream_t stream,
+                    int col_base = 0, int col_end = -1) {
     const cx<T>* tw = twiddle_table<T>(L, DIR, stream);
     if (!tw) return SB_ERR_NOMEM;
+    if (col_end < 0 || col_end > ncols) col_end = ncols;
     auto kern = tile_fft_kernel<T, L, W, DIR, Load, Store>;
     const size_t smem = (size_t)(L * W + L) * sizeof(cx<T>);
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((ncols + W - 1) / W, ny);
-    kern<<<grid, 256, smem, stream>>>(ld, st, tw, ncols);
+    dim3 grid((col_end - col_base + W - 1) / W, ny);
+    kern<<<grid, 256, smem, stream>>>(ld, st, tw, col_end, col_base);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
+// --------------------------------------------------------------------------
+// The same tile transform with the tile fetched by the TMA: ONE
+// cp.async.bulk.tensor box load ([L rows][W complex] -> dense shared-memory
+// tile, exactly the layout fft_axis works on) issued by one thread and awaited
+// on an mbarrier by all; rows / columns outside the tensor arrive as zeros
+// (zero padding of the live rows and of the last column tile for free).
+//   rank 3 (pass A of the four-step split): tensor (col, y = r2, i = r1), row
+//          r1 * R2 + r2, box {2W floats, 1, L}, coordinates {2 c0, y, 0};
+//   rank 2 (pass B): tensor (col, row), box {2W, L}, coordinates {2 c0, y * L}.
+// float2 data only (the tensor is described as float32 with 2 W floats per row).
+// --------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
+                                            unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int L, int W, int DIR, int RANK, class Store>
+__global__ void __launch_bounds__(256)
+tile_fft_tma_kernel(const __grid_constant__ CUtensorMap tmap, Store st,
+                    const float2* __restrict__ twL, int ncols, int col_base) {
+    extern __shared__ __align__(128) unsigned char smem_tma[];
+    float2* s = reinterpret_cast<float2*>(smem_tma);
+    float2* tw = s + L * W;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(tw + L);
+    const int tid = threadIdx.x;
+    constexpr int NT = 256;
+    const int c0 = col_base + blockIdx.x * W;
+    const int y = blockIdx.y;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbarrier_init();
+        mbar_expect_tx(bar, (unsigned)(L * W * sizeof(float2)));
+        if (RANK == 3) tma_load_3d(s, &tmap, 2 * c0, y, 0, bar);
+        else tma_load_2d(s, &tmap, 2 * c0, y * L, bar);
+    }
+    for (int i = tid; i < L; i += NT) tw[i] = twL[i];
+    __syncthreads();                       // barrier initialised (and tw in place) for everybody
+    while (!mbar_try_wait(bar, 0)) {}
+    fft_axis<float, L, DIR, false>(s, W, ILog2<W>::value, 1, tw, tid, NT);
+    for (int idx = tid; idx < L * W; idx += NT) {
+        const int k = idx / W, c = idx % W;
+        if (c0 + c < ncols) st(y, k, c0 + c, s[digit_pos<L>(k) * W + c]);
+    }
+}
+
+template <int L, int W, int DIR, int RANK, class Store>
+int launch_tile_fft_tma(const CUtensorMap& map, Store st, int ncols, int ny, cudaStream_t stream,
+                        int col_base = 0, int col_end = -1) {
+    const float2* tw = twiddle_table<float>(L, DIR, stream);
+    if (!tw) return SB_ERR_NOMEM;
+    if (col_end < 0 || col_end > ncols) col_end = ncols;
+    auto kern = tile_fft_tma_kernel<L, W, DIR, RANK, Store>;
+    const size_t smem = (size_t)(L * W + L) * sizeof(float2) + 16;
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((col_end - col_base + W - 1) / W, ny);
+    kern<<<grid, 256, smem, stream>>>(map, st, tw, col_end, col_base);
     SB_LAUNCH_CHECK();
     return SB_OK;
 }

@@ -20,7 +20,8 @@ struct alignas(16) LanczosShared {
     double theta, lo, res;
     double lo2;              // lanczos_check_fast: lower bound of the 2nd Ritz value (m_lo2 > 0)
     int done, next_check;
-    int m_lo2, pad_;
+    int m_lo2;
+    int m_last;              // lanczos_check: step of the previous check (0: none)
 };
 
 // Number of eigenvalues of the m x m tridiagonal (alpha[0..m), beta[1..m))
@@ -112,11 +113,30 @@ __device__ inline void lanczos_check(LanczosShared& S, int m, double tol, double
     }
     res = __shfl_sync(0xffffffffu, res, 0);
     bool done = (res <= tol * fabs(theta)) || !(bnew > 1e-30 * fabs(theta));
+    double gap_est = 0.0;
     if (!done && m >= 3 && res <= 3e-2 * fabs(theta)) {
         double lo2 = gl - 1e-9 * fabs(gl) - 1e-290, hi2 = theta;
         sturm_multisect(S, m, m - 1, lo2, hi2, 4);
         const double gap = theta - hi2;
         done = gap > 0.0 && res * res <= etol * fabs(theta) * gap;
+        gap_est = gap;
+    }
+    // When is the next check worth its ~10 Sturm sweeps (the other warps idle
+    // meanwhile)?  The residual decays roughly geometrically: extrapolate the rate
+    // seen since the previous check to the residual the stopping rule needs and skip
+    // half of the predicted remaining steps (at most 4).
+    int skip = (res > 0.3 * fabs(theta)) ? 2 : 1;
+    if (!done && S.m_last > 0 && m > S.m_last && S.res > 0.0 && res > 0.0 && res < S.res) {
+        const double rate = log(res / S.res) / (double)(m - S.m_last);      // < 0 per step
+        double target = tol * fabs(theta);
+        if (gap_est > 0.0) target = fmax(target, sqrt(etol * fabs(theta) * gap_est));
+        else target = fmax(target, sqrt(etol * 0.02) * fabs(theta));        // gap unknown yet
+        if (res > target) {
+            const double remaining = log(target / res) / rate;
+            int sk = (int)(0.5 * remaining);
+            sk = sk > 4 ? 4 : sk;
+            skip = sk > skip ? sk : skip;
+        }
     }
     __syncwarp();   // all lanes are done reading S.lo / S.next_check
     if (lane == 0) {
@@ -124,8 +144,8 @@ __device__ inline void lanczos_check(LanczosShared& S, int m, double tol, double
         S.lo = lo;
         S.res = res;
         S.done = done ? 1 : 0;
-        // far from convergence: skip the next check
-        S.next_check = m + ((res > 0.3 * fabs(theta)) ? 2 : 1);
+        S.m_last = m;
+        S.next_check = m + skip;
     }
 }
 

@@ -175,7 +175,7 @@ herm_eigvec_kernel(const float2* __restrict__ A, int n, int ld, float2* __restri
         p0 += (double)x.x * x.x + (double)x.y * x.y;
     }
     if (tid == 0) {
-        S.done = 0; S.lo = 0.0; S.theta = 0.0; S.res = 0.0; S.next_check = 1; S.beta2[0] = 0.0;
+        S.done = 0; S.lo = 0.0; S.theta = 0.0; S.res = 0.0; S.next_check = 1; S.m_last = 0; S.beta2[0] = 0.0;
         S.m_lo2 = 0; S.lo2 = 0.0;
     }
     const double nrm2 = ev_block_sum(p0, red);

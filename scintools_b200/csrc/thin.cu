@@ -194,7 +194,7 @@ thin_sv_kernel(const float2* __restrict__ Mbase, int ld1, int ld2,
         v[c] = c < n1 ? make_float2(1.f, 0.f) : make_float2(0.f, 0.f);
         vp[c] = make_float2(0.f, 0.f);
     }
-    if (tid == 0) { S.done = 0; S.lo = 0.0; S.theta = 0.0; S.next_check = 1; S.beta2[0] = 0.0; }
+    if (tid == 0) { S.done = 0; S.lo = 0.0; S.theta = 0.0; S.next_check = 1; S.m_last = 0; S.beta2[0] = 0.0; }
     __syncthreads();
     {
         const float s = rsqrtf((float)n1);

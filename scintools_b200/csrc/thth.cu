@@ -292,7 +292,7 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
     if (lane == 0) S.red[0][warp] = part0;
     if (tid == 0) {
         S.done = 0; S.lo = 0.0; S.theta = 0.0; S.res = 0.0; S.m_lo2 = 0; S.lo2 = 0.0;
-        S.next_check = 1; S.beta2[0] = 0.0;
+        S.next_check = 1; S.m_last = 0; S.beta2[0] = 0.0;
     }
     __syncthreads();
     double nrm2 = 0.0;

@@ -22,6 +22,7 @@ from . import _device as D
 from . import _lib
 from . import ththmod as thth
 from . import units as U
+from .arcfit import ArcFitMixin
 
 _WINDOWS = {"hanning": np.hanning, "hamming": np.hamming,
             "blackman": np.blackman, "bartlett": np.bartlett}
@@ -74,7 +75,7 @@ class BasicDyn:
         self.dyn = dyn
 
 
-class Dynspec:
+class Dynspec(ArcFitMixin):
 
     def __init__(self, filename=None, dyn=None, verbose=True, process=False,
                  lamsteps=False, remove_short_subs=True, subint_thresh=2.33,
@@ -119,6 +120,12 @@ class Dynspec:
     # secondary spectrum
     # ------------------------------------------------------------------
     def _pick_dyn(self, lamsteps, velocity, trap):
+        """The array calc_sspec transforms (reference dynspec.py:3642-3663): the
+        wavelength-rescaled copy is made on demand (scale_dyn -> self.lamdyn);
+        velocity / trapezoid resampling is outside the B200 hot path and must have
+        been set by the caller."""
+        if lamsteps and not velocity and not hasattr(self, "lamdyn"):
+            self.scale_dyn()
         for flag, attr in ((lamsteps and velocity, "vlamdyn"),
                            (lamsteps, "lamdyn"), (velocity, "vdyn"),
                            (trap, "trapdyn")):
@@ -126,8 +133,7 @@ class Dynspec:
                 if not hasattr(self, attr):
                     raise NotImplementedError(
                         "velocity / trapezoid resampling is outside the B200 hot "
-                        "path and scale_dyn(scale='lambda') is still unverified; "
-                        "set self.%s first" % attr)
+                        "path; set self.%s first" % attr)
                 return cp(getattr(self, attr))
         return self.dyn
 
@@ -206,7 +212,7 @@ class Dynspec:
     # autocovariance
     # ------------------------------------------------------------------
     # ------------------------------------------------------------------
-    # wavelength rescaling (round-2 candidate, see csrc/scale_dyn.cu)
+    # wavelength rescaling (csrc/scale_dyn.cu)
     # ------------------------------------------------------------------
     @staticmethod
     def _spline_tables(x, xq):
@@ -375,11 +381,13 @@ class Dynspec:
         if 'eta_max' in kwargs:
             eta_max = min((float(U.value(kwargs['eta_max'], "s3")), eta_max))
         if not ('eta_min' in kwargs and 'eta_max' in kwargs):
-            if not hasattr(self, "betaeta") or not hasattr(self, "betaetaerr"):
-                raise NotImplementedError(
-                    "the Hough-transform prior (Dynspec.fit_arc) is outside "
-                    "the B200 hot path: pass eta_min and eta_max")
             c = 299792458.0
+            if not hasattr(self, "betaeta"):
+                # Hough prior (reference dynspec.py:1458-1466): eta [s^3] -> betaeta
+                # [1/(m mHz^2)] = eta * fref^2 [MHz^2 = 1e12 s^-2] / c / (1e6 s^2/mHz^-2)
+                to_beta = self.fref ** 2 * 1e12 / c / 1e6
+                self.fit_arc(lamsteps=True, numsteps=1e4, etamin=eta_min * to_beta,
+                             etamax=eta_max * to_beta, delmax=tau_lim, plot=False)
             eta_hough = c * self.betaeta / self.fref ** 2 * 1e-12 * 1e6
             err_hough = c * 2 * max((self.betaetaerr, self.betaetaerr2)) \
                 / self.fref ** 2 * 1e-12 * 1e6
