@@ -395,9 +395,10 @@ static bool make_tile_map(CUtensorMap* m, const float2* base, long pitch, int nc
 // Column transform of length NF (four-step split R1 x R2, two tile passes) over the
 // half spectra H[live][pitch] -> epilogue stb.  Tiles are fetched by the TMA
 // (cp.async.bulk.tensor, zero fill for the padded rows) whenever the live rows are
-// whole r2-groups; SB_FFT_NO_TMA=1 forces the LDG path.  The columns are walked in
-// chunks whose intermediate A[NF][chunk] stays L2-resident between pass A and
-// pass B (SB_COL_CHUNK_MB, default 48; 0 = one chunk).
+// whole r2-groups; SB_FFT_NO_TMA=1 forces the LDG path.  SB_COL_CHUNK_MB=N walks the
+// columns in chunks of N MB of the intermediate A[NF][chunk] (an experiment: pass B
+// re-reads each chunk from DRAM anyway -- L2 hit rate 12 % at 48 MB chunks -- and the
+// smaller grids cost more than they save, so the default is one chunk).
 template <class StoreB>
 static int cols_forward(const float2* H, float2* A, long pitch, int NF, int live,
                         int ncols, StoreB stb, cudaStream_t st, int profA = -1,
@@ -414,7 +415,7 @@ static int cols_forward(const float2* H, float2* A, long pitch, int NF, int live
     const bool tma = !no_tma && live % R2 == 0 && live >= R2 && R1 <= 256 && R2 <= 256 &&
                      make_tile_map(&mapA, H, pitch, ncols, live, R2, R1, 32) &&
                      make_tile_map(&mapB, A, pitch, ncols, NF, 0, R2, 64);
-    long chunk_mb = 48;
+    long chunk_mb = 0;
     if (const char* ev = getenv("SB_COL_CHUNK_MB")) chunk_mb = atol(ev);
     int cw = ncols;
     if (chunk_mb > 0) {

@@ -76,6 +76,11 @@ __host__ __device__ inline size_t eig_bf16_smem(int ld) {
            (size_t)EB_NW * EB_NST * 4096 + (size_t)EB_NW * EB_NST * 8 + 16;
 }
 
+// CPA: the bf16 rows are fetched with per-lane cp.async (LDGSTS) copies -- every lane
+// copies exactly the 16-byte chunks it will read itself, so a wait_group is all the
+// synchronisation a stage needs -- instead of cp.async.bulk + mbarrier (one lane issues,
+// ~70 instructions per row pair of address / election bookkeeping).
+template <bool CPA>
 __global__ void __launch_bounds__(EB_THREADS, 2)
 thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restrict__ Mbbase,
                      int ld, const int* __restrict__ nred, int eta0,
@@ -163,7 +168,7 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         if (warp == 0) K = npair > 7 ? (npair - 8) / 15 + 1 : 0;
         else K = (npair > warp - 1 ? (npair - warp) / 15 + 1 : 0) +
                  (npair > warp + 7 ? (npair - 8 - warp) / 15 + 1 : 0);
-        auto issue = [&](int k) {
+        auto issue = [&](int k) {          // cp.async.bulk: one lane, two copies on one barrier
             const int a0 = 2 * pair_of(k);
             const int c0 = a0 & ~3;            // = (a0 + 1) & ~3 for even a0
             const int c1 = (a0 + 2) & ~3;
@@ -176,8 +181,30 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             bulk_g2s(dst + c0 * 4, src + c0, b0, mybar + k % EB_NST);
             if (has1) bulk_g2s(dst + 2048 + c1 * 4, src + ld + c1, b1, mybar + k % EB_NST);
         };
-        if (lane == 0)
+        auto fetch = [&](int k) {          // cp.async: every lane copies its own chunks
+            if (k < K) {
+                const int a0 = 2 * pair_of(k);
+                const bool has1 = a0 + 1 <= n - 2;
+                const int JS = (a0 + 1) >> 7;
+                unsigned char* dst = mystage + (k % EB_NST) * 4096 + lane * 16;
+                const unsigned* src = Mb + (unsigned)(a0 * ld) + 4 * lane;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j < JS) continue;
+                    const int cbeg = 4 * (lane + 32 * j);
+                    if (cbeg < ncolq) {
+                        if (cbeg + 3 >= a0 + 1) cp_async16(dst + j * 512, src + j * 128);
+                        if (has1 && cbeg + 3 >= a0 + 2) cp_async16(dst + 2048 + j * 512, src + ld + j * 128);
+                    }
+                }
+            }
+            cp_async_commit();             // (an empty group keeps the wait count uniform)
+        };
+        if (CPA) {
+            for (int k = 0; k < EB_NST; ++k) fetch(k);
+        } else if (lane == 0) {
             for (int k = 0; k < EB_NST && k < K; ++k) issue(k);
+        }
         if (check_m > 0 && warp == 0) lanczos_check(S, check_m, tol, et);
         float* wflat = reinterpret_cast<float*>(w);
         for (int k = 0; k < K; ++k) {
@@ -189,8 +216,12 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             const float2 XA0 = make_float2(xa.x, xa.y), XB0 = make_float2(xa.y, -xa.x);
             const float2 XA1 = make_float2(xa.z, xa.w), XB1 = make_float2(xa.w, -xa.z);
             const int st = k % EB_NST;
-            while (!mbar_try_wait(mybar + st, (phbits >> st) & 1u)) {}
-            phbits ^= 1u << st;
+            if (CPA) {
+                cp_async_wait<EB_NST - 1>();    // this lane's copies of pair k have landed
+            } else {
+                while (!mbar_try_wait(mybar + st, (phbits >> st) & 1u)) {}
+                phbits ^= 1u << st;
+            }
             const uint4* s0 = reinterpret_cast<const uint4*>(mystage + st * 4096);
             const uint4* s1 = s0 + 128;
             const int JS = (a0 + 1) >> 7;       // column groups entirely left of the diagonal
@@ -231,8 +262,12 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
                     ffma2(yc[j][i], XB1, Q1.y);
                 }
             }
-            __syncwarp();                       // every lane is done reading the stage
-            if (lane == 0 && k + EB_NST < K) issue(k + EB_NST);
+            if (CPA) {
+                fetch(k + EB_NST);              // refill this lane's chunks of the stage
+            } else {
+                __syncwarp();                   // every lane is done reading the stage
+                if (lane == 0 && k + EB_NST < K) issue(k + EB_NST);
+            }
             // four row sums (re0, im0, re1, im1) with six shuffles: lanes 0-15 keep
             // row 0, lanes 16-31 row 1; then bit 3 splits re / im
             const float r0x = S0a.x + S0b.x, r0y = S0a.y + S0b.y;
@@ -250,6 +285,7 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             // lanes 0 / 8 / 16 / 24 hold re0, im0, re1, im1 = 4 consecutive floats of w
             if ((lane & 7) == 0 && (has1 || lane < 16)) wflat[2 * a0 + (lane >> 3)] = kk;
         }
+        if (CPA) cp_async_wait<0>();            // (only empty groups are left)
         __syncthreads();                        // every warp is done with its stages
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -593,10 +629,18 @@ int eig_bf16_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* 
     double rtol_r = 2e-3;
     if (const char* ev = getenv("SB_EIG_RTOL_R")) rtol_r = atof(ev);
     if (const char* ev = getenv("SB_EIG_ETOL_B")) etol = atof(ev);
-    SB_CUDA(cudaFuncSetAttribute(thth_eig_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-    thth_eig_bf16_kernel<<<nb, EB_THREADS, smem, st>>>(d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status,
-                                                       d_iters, tol, etol, rtol_r, max_iter, d_basis);
+    static const bool bulk = getenv("SB_EIG_BULK") != nullptr;   // A/B: cp.async.bulk row fetch
+    if (bulk) {
+        SB_CUDA(cudaFuncSetAttribute(thth_eig_bf16_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        thth_eig_bf16_kernel<false><<<nb, EB_THREADS, smem, st>>>(
+            d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, etol, rtol_r, max_iter, d_basis);
+    } else {
+        SB_CUDA(cudaFuncSetAttribute(thth_eig_bf16_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        thth_eig_bf16_kernel<true><<<nb, EB_THREADS, smem, st>>>(
+            d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, etol, rtol_r, max_iter, d_basis);
+    }
     SB_LAUNCH_CHECK();
     return 1;
 }

@@ -119,8 +119,14 @@ __device__ __forceinline__ unsigned pack_bf16x2(float2 v) {
 // the same order as thth_point, so the bins stay bit-exact), one gather and the
 // Jacobian remain.  The cached pair is re-derived whenever the crop of the next
 // curvature moves the pair (idx differs).
-template <bool PACK>
-__global__ void __launch_bounds__(256, 4)
+// ROWS rows of the tile per thread (block = 32 x 32/ROWS threads).  Per curvature the
+// body runs in three phases -- (1) tau_inv and the CS offset of every row, (2) ALL the
+// gathers back to back, (3) Jacobian, clean-up, stores -- so that ROWS independent
+// L2 / DRAM gathers are in flight per thread: the kernel is bound by the latency of
+// these random 8-byte loads (ncu: long-scoreboard stalls 8.8 per issue with one load in
+// flight), not by its instruction count.
+template <bool PACK, int ROWS, typename OFF>
+__global__ void __launch_bounds__(32 * (32 / ROWS))
 thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nbatch,
                   int ld, const int* __restrict__ idx,
                   const int* __restrict__ nred, float2* __restrict__ M,
@@ -129,6 +135,7 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
     // same 32x32 tile for neighbouring curvatures, whose gathers fall on
     // the same / adjacent CS rows for small |theta1^2 - theta2^2| (L2 reuse)
     // pair index -> (ta <= tb)
+    constexpr int TY = 32 / ROWS;
     int p = blockIdx.y, ta = 0;
     const int T = ld / 32;
     while (p >= T - ta) { p -= T - ta; ++ta; }
@@ -137,14 +144,16 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
     const int b = tb * 32 + tx;
     const double ntau_d = (double)g.ntau;
     const long long hfd = g.nfd / 2;
-    // cached eta-independent state of this thread's column and its 4 rows
+    // cached eta-independent state of this thread's column and its ROWS rows
     int cj = -2;
     double thj = 0.0;
-    int ci[4] = {-2, -2, -2, -2};
-    double dk[4];
-    long long col[4];       // CS column to gather; < 0: never a valid point
-    bool conj[4];
-    float wk[4];
+    int ci[ROWS];
+    double dk[ROWS];
+    int col[ROWS];          // CS column to gather; < 0: never a valid point
+    unsigned conj = 0u;     // bit k: the point lies in the mirrored (fd < 0) half
+    float wk[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) { ci[k] = -2; dk[k] = 0.0; col[k] = -1; wk[k] = 0.f; }
     const int e_end = min(nbatch, (int)(blockIdx.x + 1) * SB_BUILD_EB);
     for (int e = blockIdx.x * SB_BUILD_EB; e < e_end; ++e) {
         const int n = nred[eta0 + e];
@@ -156,20 +165,24 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
             cj = j;
             thj = j >= 0 ? g.th[j] : 0.0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ci[k] = -2;
+            for (int k = 0; k < ROWS; ++k) ci[k] = -2;
         }
         const float seta = sqrtf((float)(2.0 * eta));
         float2* Me = M + (size_t)e * ld * ld;
+        // ---- phase 1: offsets
+        OFF off[ROWS];          // element offset into the CS (OFF = unsigned when it fits)
+        unsigned hit = 0u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int la = ty + 8 * k;
+        for (int k = 0; k < ROWS; ++k) {
+            const int la = ty + TY * k;
+            off[k] = 0;
             if (ta == tb && tx < la) continue;      // lower triangle: not stored
             const int a = ta * 32 + la;
             const int i = a < n ? id[a] : -1;
             if (i != ci[k]) {
                 ci[k] = i;
                 col[k] = -1;
-                conj[k] = false;
+                conj &= ~(1u << k);
                 wk[k] = 0.f;
                 dk[k] = 0.0;
                 if (i >= 0 && j > i && i + j != g.n - 1) {
@@ -182,22 +195,38 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
                     wk[k] = sqrtf((float)fabs(th2 - th1));
                     if (fq < g.nfd && !(fq < -g.nfd)) {     // pnts mask / IndexError (thth_point)
                         const long long fi = fq < 0 ? fq + g.nfd : fq;
-                        if (!g.cs_half) col[k] = fi;
-                        else if (fi >= hfd) col[k] = fi - hfd;
-                        else if (fi == 0) col[k] = hfd;
-                        else { col[k] = hfd - fi; conj[k] = true; }   // CS[-tau,-fd] = conj(CS[tau,fd])
+                        if (!g.cs_half) col[k] = (int)fi;
+                        else if (fi >= hfd) col[k] = (int)(fi - hfd);
+                        else if (fi == 0) col[k] = (int)hfd;
+                        else { col[k] = (int)(hfd - fi); conj |= 1u << k; }   // CS[-tau,-fd] = conj(CS[tau,fd])
                     }
                 }
             }
-            float2 v = make_float2(0.f, 0.f);
             if (col[k] >= 0) {
                 const double aa = __dadd_rn(__dsub_rn(__dmul_rn(eta, dk[k]), g.tau0), g.half_dtau);
                 const double tqd = floor_div_fast(aa, g.dtau, g.inv_dtau);
                 if (tqd > 0.0 && tqd < ntau_d) {            // tau_inv > 0 and < ntau (ththmod.py:100)
-                    const long long tq = (long long)tqd;
-                    const long long r = conj[k] ? g.ntau - tq : tq;
-                    v = __ldg(g.cs + (size_t)r * (size_t)g.cs_pitch + (size_t)col[k]);
-                    if (conj[k]) v.y = -v.y;
+                    const int tq = (int)tqd;
+                    const int r = (conj >> k) & 1u ? (int)g.ntau - tq : tq;
+                    off[k] = (OFF)r * (OFF)g.cs_pitch + (OFF)col[k];
+                    hit |= 1u << k;
+                }
+            }
+        }
+        // ---- phase 2: the gathers, all in flight together (a miss reads CS[0], ignored)
+        float2 val[ROWS];
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) val[k] = __ldg(g.cs + off[k]);
+        // ---- phase 3
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) {
+            const int la = ty + TY * k;
+            if (ta == tb && tx < la) continue;
+            float2 v = make_float2(0.f, 0.f);
+            if (col[k] >= 0) {
+                if ((hit >> k) & 1u) {
+                    v = val[k];
+                    if ((conj >> k) & 1u) v.y = -v.y;
                     if (!g.coherent) v = make_float2(hypotf(v.x, v.y), 0.f);
                 }
                 // Jacobian sqrt|2 eta (th2 - th1)| (ththmod.py:107)
@@ -209,7 +238,7 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
                     v.y = nan_to_num(v.y);
                 }
             }
-            const size_t o = (size_t)a * ld + b;
+            const size_t o = (size_t)(ta * 32 + la) * ld + b;
             Me[o] = v;
             if (PACK) Mb[(size_t)e * ld * ld + o] = pack_bf16x2(v);
         }
@@ -709,13 +738,13 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int e0 = 0; e0 < neta; e0 += batch) {
         int nb = neta - e0 < batch ? neta - e0 : batch;
-        dim3 grid((nb + SB_BUILD_EB - 1) / SB_BUILD_EB, npairs), block(32, 8);
+        constexpr int BR = 8;            // rows per thread of thth_build_kernel
+        dim3 grid((nb + SB_BUILD_EB - 1) / SB_BUILD_EB, npairs), block(32, 32 / BR);
         prof_begin(PROF_THTH_BUILD, st);
         if (mixed)
-            thth_build_kernel<true><<<grid, block, 0, st>>>(g, d_etas, e0, nb, ld, d_idx, d_nred,
-                                                            d_M, d_Mb);
+            XX1
         else
-            thth_build_kernel<false><<<grid, block, 0, st>>>(g, d_etas, e0, nb, ld, d_idx, d_nred,
+            thth_build_kernel<false, BR><<<grid, block, 0, st>>>(g, d_etas, e0, nb, ld, d_idx, d_nred,
                                                              d_M, nullptr);
         prof_end(PROF_THTH_BUILD, st);
         SB_LAUNCH_CHECK();

@@ -22,6 +22,10 @@ inline bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
 }
 inline void fence_mbarrier_init() {}
 inline void fence_proxy_async() {}
+// cp.async (LDGSTS): completes synchronously
+inline void cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
+inline void cp_async_commit() {}
+template <int N> inline void cp_async_wait() {}
 }  // namespace sb
 #else
 
@@ -55,6 +59,16 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
 
 __device__ __forceinline__ void fence_mbarrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// cp.async (LDGSTS): 16-byte global -> shared copy of the issuing thread, L2 only
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 // order generic-proxy shared-memory writes before later bulk copies (async proxy)
 __device__ __forceinline__ void fence_proxy_async() {

@@ -55,13 +55,13 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
     const unsigned gx = (unsigned)((neta + SB_BUILD_EB - 1) / SB_BUILD_EB);
     for (unsigned bx = 0; bx < gx; ++bx)
         for (unsigned by = 0; by < (unsigned)npairs; ++by)
-            emu::run_block(emu::Dim3{32, 8, 1}, emu::Dim3{bx, by, 0}, emu::Dim3{gx, (unsigned)npairs, 1},
+            emu::run_block(emu::Dim3{32, 4, 1}, emu::Dim3{bx, by, 0}, emu::Dim3{gx, (unsigned)npairs, 1},
                            [&]() {
                                if (mixed)
-                                   thth_build_kernel<true>(g, etas, 0, neta, ld, idx.data(), nred,
+                                   thth_build_kernel<true, 8>(g, etas, 0, neta, ld, idx.data(), nred,
                                                            M.data(), Mb.data());
                                else
-                                   thth_build_kernel<false>(g, etas, 0, neta, ld, idx.data(), nred,
+                                   thth_build_kernel<false, 8>(g, etas, 0, neta, ld, idx.data(), nred,
                                                             M.data(), nullptr);
                            });
     if (M_out) std::memcpy(M_out, M.data(), M.size() * sizeof(float2));   // [neta][ld][ld] triangle
@@ -74,7 +74,7 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
             std::memset(smem_raw, 0xa5, sizeof(smem_raw));     // garbage, like real shared memory
             emu::run_block(emu::Dim3{(unsigned)EB_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
                            emu::Dim3{(unsigned)neta, 1, 1}, [&]() {
-                               thth_eig_bf16_kernel(M.data(), Mb.data(), ld, nred, 0, eigs, status,
+                               thth_eig_bf16_kernel<true>(M.data(), Mb.data(), ld, nred, 0, eigs, status,
                                                     iters, tol, 2e-7, mixed >= 2 ? 0.0 : 2e-3,
                                                     max_iter, gbasis.data());
                            });
