@@ -500,6 +500,10 @@ def b200_arm(args):
             "gpu_launches": launches, "clocks": clk,
             "sweep": {"nred_min": int(nred.min()), "nred_max": int(nred.max()),
                       "iters_mean": float(iters.mean()), "iters_max": int(iters.max()),
+                      "iters_hist": {"<=20": int((iters <= 20).sum()),
+                                     "21-24": int(((iters > 20) & (iters <= 24)).sum()),
+                                     "25-32": int(((iters > 24) & (iters <= 32)).sum()),
+                                     ">32": int((iters > 32).sum())},
                       "status_nonzero": int((status != 0).sum()),
                       "eta_peak": float(etas[np.nanargmax(eigs)])},
         }

@@ -850,7 +850,13 @@ int acf(const float* dyn, int nf, int nt, int subtract_mean, int normalise,
         if (!wR) return SB_ERR_NOMEM;
         ColALoad la{H, pitch, R2, nf};
         ColAStore sa{A, pitch, R2, PF, wR};
-        SB_TILE_DISPATCH(R1, rc = (launch_tile_fft<float, LL, 32, -1>(la, sa, ncols, R2, st)));
+        CUtensorMap mapA;
+        if (!getenv("SB_FFT_NO_TMA") && nf % R2 == 0 && nf >= R2 && R1 <= 256 &&
+            make_tile_map(&mapA, H, pitch, ncols, nf, R2, R1, 32)) {
+            SB_TILE_DISPATCH(R1, rc = (launch_tile_fft_tma<LL, 32, -1, 3>(mapA, sa, ncols, R2, st)));
+        } else {
+            SB_TILE_DISPATCH(R1, rc = (launch_tile_fft<float, LL, 32, -1>(la, sa, ncols, R2, st)));
+        }
         if (rc) return rc;
     }
     // fused forward pass B -> power -> inverse over k2
@@ -872,7 +878,13 @@ int acf(const float* dyn, int nf, int nt, int subtract_mean, int normalise,
     {
         AcfInvLoad li{G, pitch, R2};
         AcfInvStore si{A, pitch, R2};
-        SB_TILE_DISPATCH(R1, rc = (launch_tile_fft<float, LL, 32, +1>(li, si, ncols, R2, st)));
+        CUtensorMap mapG;
+        if (!getenv("SB_FFT_NO_TMA") && R1 <= 256 &&
+            make_tile_map(&mapG, G, pitch, ncols, PF, R2, R1, 32)) {
+            SB_TILE_DISPATCH(R1, rc = (launch_tile_fft_tma<LL, 32, +1, 3>(mapG, si, ncols, R2, st)));
+        } else {
+            SB_TILE_DISPATCH(R1, rc = (launch_tile_fft<float, LL, 32, +1>(li, si, ncols, R2, st)));
+        }
         if (rc) return rc;
     }
     // rows: half spectrum -> real, crop to lags [-nf, nf) x [-nt, nt)

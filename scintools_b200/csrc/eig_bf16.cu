@@ -181,20 +181,29 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             bulk_g2s(dst + c0 * 4, src + c0, b0, mybar + k % EB_NST);
             if (has1) bulk_g2s(dst + 2048 + c1 * 4, src + ld + c1, b1, mybar + k % EB_NST);
         };
-        auto fetch = [&](int k) {          // cp.async: every lane copies its own chunks
+        // cp.async: every lane copies its own chunks.  gsrc / sdst are per-lane bases kept
+        // in registers (the empty asm stops the compiler from re-deriving them from
+        // blockIdx every time); per pair only a0 * ld and the two diagonal compares remain.
+        const unsigned* gsrc = Mb + 4 * lane;
+        smem_addr sdst = smem_addr_of(mystage) + lane * 16;
+#ifndef SB_HOST_EMU
+        asm volatile("" : "+l"(gsrc), "+r"(sdst));
+#endif
+        const int cb0 = 4 * lane + 3;      // last column of the lane's chunk in group 0
+        auto fetch = [&](int k) {
             if (k < K) {
                 const int a0 = 2 * pair_of(k);
-                const bool has1 = a0 + 1 <= n - 2;
                 const int JS = (a0 + 1) >> 7;
-                unsigned char* dst = mystage + (k % EB_NST) * 4096 + lane * 16;
-                const unsigned* src = Mb + (unsigned)(a0 * ld) + 4 * lane;
+                const unsigned* src = gsrc + (unsigned)(a0 * ld);
+                const smem_addr dst = sdst + (k % EB_NST) * 4096;
+                const int lim1 = (a0 + 1 <= n - 2) ? a0 + 2 : 0x7fffffff;   // row 1 absent: never
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (j < JS) continue;
-                    const int cbeg = 4 * (lane + 32 * j);
-                    if (cbeg < ncolq) {
-                        if (cbeg + 3 >= a0 + 1) cp_async16(dst + j * 512, src + j * 128);
-                        if (has1 && cbeg + 3 >= a0 + 2) cp_async16(dst + 2048 + j * 512, src + ld + j * 128);
+                    const int cend = cb0 + 128 * j;
+                    if (cend - 3 < ncolq) {
+                        if (cend >= a0 + 1) cp_async16_s(dst + j * 512, src + j * 128);
+                        if (cend >= lim1) cp_async16_s(dst + 2048 + j * 512, src + ld + j * 128);
                     }
                 }
             }

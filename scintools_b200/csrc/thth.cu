@@ -126,7 +126,7 @@ __device__ __forceinline__ unsigned pack_bf16x2(float2 v) {
 // these random 8-byte loads (ncu: long-scoreboard stalls 8.8 per issue with one load in
 // flight), not by its instruction count.
 template <bool PACK, int ROWS, typename OFF>
-__global__ void __launch_bounds__(32 * (32 / ROWS))
+__global__ void __launch_bounds__(32 * (32 / ROWS), 5)
 thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nbatch,
                   int ld, const int* __restrict__ idx,
                   const int* __restrict__ nred, float2* __restrict__ M,
@@ -741,11 +741,20 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
         constexpr int BR = 8;            // rows per thread of thth_build_kernel
         dim3 grid((nb + SB_BUILD_EB - 1) / SB_BUILD_EB, npairs), block(32, 32 / BR);
         prof_begin(PROF_THTH_BUILD, st);
-        if (mixed)
-            XX1
+        // 32-bit CS offsets whenever the spectrum has fewer than 2^32 elements
+        const bool small = (unsigned long long)g.ntau * (unsigned long long)g.cs_pitch < (1ull << 32);
+        if (mixed && small)
+            thth_build_kernel<true, BR, unsigned><<<grid, block, 0, st>>>(
+                g, d_etas, e0, nb, ld, d_idx, d_nred, d_M, d_Mb);
+        else if (mixed)
+            thth_build_kernel<true, BR, size_t><<<grid, block, 0, st>>>(
+                g, d_etas, e0, nb, ld, d_idx, d_nred, d_M, d_Mb);
+        else if (small)
+            thth_build_kernel<false, BR, unsigned><<<grid, block, 0, st>>>(
+                g, d_etas, e0, nb, ld, d_idx, d_nred, d_M, nullptr);
         else
-            thth_build_kernel<false, BR><<<grid, block, 0, st>>>(g, d_etas, e0, nb, ld, d_idx, d_nred,
-                                                             d_M, nullptr);
+            thth_build_kernel<false, BR, size_t><<<grid, block, 0, st>>>(
+                g, d_etas, e0, nb, ld, d_idx, d_nred, d_M, nullptr);
         prof_end(PROF_THTH_BUILD, st);
         SB_LAUNCH_CHECK();
         prof_begin(PROF_THTH_EIG, st);

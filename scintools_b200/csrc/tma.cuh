@@ -24,6 +24,10 @@ inline void fence_mbarrier_init() {}
 inline void fence_proxy_async() {}
 // cp.async (LDGSTS): completes synchronously
 inline void cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
+// shared-memory byte address: a plain pointer on the host
+typedef unsigned char* smem_addr;
+inline smem_addr smem_addr_of(void* p) { return (smem_addr)p; }
+inline void cp_async16_s(smem_addr dst, const void* src) { std::memcpy(dst, src, 16); }
 inline void cp_async_commit() {}
 template <int N> inline void cp_async_wait() {}
 }  // namespace sb
@@ -63,6 +67,12 @@ __device__ __forceinline__ void fence_mbarrier_init() {
 // cp.async (LDGSTS): 16-byte global -> shared copy of the issuing thread, L2 only
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// same with the destination given as a 32-bit shared address
+typedef unsigned smem_addr;
+__device__ __forceinline__ smem_addr smem_addr_of(void* p) { return smem_u32(p); }
+__device__ __forceinline__ void cp_async16_s(smem_addr dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() {
     asm volatile("cp.async.commit_group;" ::: "memory");

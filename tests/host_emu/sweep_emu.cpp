@@ -58,10 +58,10 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
             emu::run_block(emu::Dim3{32, 4, 1}, emu::Dim3{bx, by, 0}, emu::Dim3{gx, (unsigned)npairs, 1},
                            [&]() {
                                if (mixed)
-                                   thth_build_kernel<true, 8>(g, etas, 0, neta, ld, idx.data(), nred,
+                                   thth_build_kernel<true, 8, unsigned>(g, etas, 0, neta, ld, idx.data(), nred,
                                                            M.data(), Mb.data());
                                else
-                                   thth_build_kernel<false, 8>(g, etas, 0, neta, ld, idx.data(), nred,
+                                   thth_build_kernel<false, 8, size_t>(g, etas, 0, neta, ld, idx.data(), nred,
                                                             M.data(), nullptr);
                            });
     if (M_out) std::memcpy(M_out, M.data(), M.size() * sizeof(float2));   // [neta][ld][ld] triangle

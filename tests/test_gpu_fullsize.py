@@ -125,10 +125,16 @@ def test_c3_cs_and_sweep(sb):
     eigs, info = thth.eta_sweep(cs, tau, fd, etas, edges, return_info=True)
     assert (info["status"] == 0).all()
     assert abs(etas[np.argmax(eigs)] / bench.ETA_TRUE - 1) < 0.02
+    # 64 curvatures across the grid (plus the four corners of the old check) against the
+    # oracle (numpy gather + ARPACK) on the same conjugate spectrum, full 511 x 511 maps
     CS_host = cs.numpy().astype(np.complex64)
-    for i in (0, 400, 700, 1023):
+    pick = sorted(set(list(range(0, bench.NETA, 16)) + [400, 700, 1023]))
+    worst = 0.0
+    for i in pick:
         ref = TO.Eval_calc(CS_host, tau, fd, etas[i], edges)
-        assert abs(eigs[i] - ref) / ref < 1e-5
+        worst = max(worst, abs(eigs[i] - ref) / ref)
+    print("C3 full size: max rel eigenvalue error over %d etas = %.2e" % (len(pick), worst))
+    assert worst < 1e-5
     # bit-exact crop sizes
     nred = np.array([TO.th_points(tau, fd, e, edges).sum() for e in etas[::64]])
     assert np.array_equal(info["nred"][::64], nred)
