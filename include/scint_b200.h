@@ -80,7 +80,9 @@ typedef struct sb_thth_geom {
                               columns k = 0..nfd/2 are the NON-shifted fd >= 0 bins;
                               the rest follows from CS[-tau,-fd] = conj(CS[tau,fd])
                               (valid for the CS of a real dynamic spectrum) */
-    int32_t reserved;
+    int32_t cs_valid_cols; /* cs_half only: how many of the nfd/2+1 stored columns hold data
+                              (sb_cs_f32 with ncols_keep > 0 computes only those the theta
+                              grid can reach); 0 = all.  Nothing beyond is ever read. */
 } sb_thth_geom;
 
 /* Replaces the eta loop of ththmod.single_search (ththmod.py:789-811) /

@@ -37,7 +37,7 @@ class ThthGeom(ctypes.Structure):
         ("fd0", c_dbl), ("dfd", c_dbl), ("fd_half", c_dbl),
         ("th_cents", vp), ("th_cents_host", vp),
         ("n_th", c_int), ("coherent", c_int),
-        ("cs_pitch", c_i64), ("cs_half", c_int), ("reserved", c_int),
+        ("cs_pitch", c_i64), ("cs_half", c_int), ("cs_valid_cols", c_int),
     ]
 
 

@@ -181,6 +181,7 @@ static int to_geom(const sb_thth_geom* in, ThthGeom* g) {
     g->n = in->n_th;
     g->coherent = in->coherent;
     g->cs_half = in->cs_half;
+    g->cs_valid_cols = in->cs_half ? in->cs_valid_cols : 0;
     g->cs_pitch = in->cs_half ? in->cs_pitch : (in->cs_pitch > 0 ? in->cs_pitch : in->nfd);
     SB_ARG(!in->cs_half || (in->cs_pitch >= in->nfd / 2 + 1 && in->nfd % 2 == 0));
     return SB_OK;

@@ -5,27 +5,36 @@
 // Why: the fp32 streaming solver (thth_eig_kernel, thth.cu) re-reads the 1 MB
 // fp32 triangle on every Lanczos step (19.3 GB per 1024-eta sweep) and spends
 // ~32 thread-instructions per matrix element (masks, shared-memory loads of
-// the vector, per-row reductions).  This kernel
-//   * iterates on the bf16 copy of the triangle written by
-//     thth_build_kernel<true> (4 B per complex element: half the bytes),
+// the vector, per-row reductions, one-lane bulk-copy bookkeeping).  This kernel
+//   * iterates on an fp16 copy of the triangle (re | im << 16, 4 B per complex
+//     element: half the bytes) written by thth_build_kernel<true>, scaled per
+//     curvature by a power of two so that the largest element stays below 2^15
+//     (the scale cancels: only the Ritz VECTOR of this phase is used).  A bf16
+//     copy was measured first: its 8-bit mantissa leaves a residual
+//     ||A y - rho y|| / rho of 0.6e-3 .. 3e-3 and Rayleigh-quotient errors up to
+//     1.1e-5 on the 4096x8192 workload -- fp16's 11 bits give 8x / 64x less;
 //   * keeps the lane's 16 vector elements and 16 column accumulators in
 //     registers for the whole mat-vec and does the complex multiply-adds with
 //     PACKED fp32 FMAs (Blackwell FFMA2, fma.rn.f32x2, scalar operand broadcast):
-//     one LDS.128 + 4 shifts + 16 FFMA2 per four complex elements; no masks
-//     except on the diagonal group,
-//   * fetches TWO adjacent rows per mbarrier phase (two cp.async.bulk on one
-//     barrier) and reduces their four row sums with six shuffles,
+//     one LDS.128 + 8 converts + 16 FFMA2 per four complex elements; no masks
+//     except on the diagonal group;
+//   * fetches the rows with per-lane cp.async copies (every lane copies exactly
+//     the 16-byte chunks it reads itself: a wait_group is all the synchronisation
+//     a stage needs), two adjacent rows per stage, and reduces their four row
+//     sums with six shuffles;
+//   * runs the convergence check of step m on warp 0 DURING mat-vec m+1 (warp 0
+//     gets half the rows), so nobody idles behind the Sturm sweeps;
 //   * keeps the Lanczos vectors (fp32) in global memory, forms the Ritz vector
 //     y and reports the Rayleigh quotient <y, A y> / <y, y> with the FP32
-//     triangle in one extra pass.  The Rayleigh quotient is second order in
-//     the vector error (CPU study profiles/probe_mixed_precision.py: <= 5e-7
-//     at n = 511 while the bf16 Ritz value alone is off by 1.7e-4).
-//   * Safety net: the same fp32 pass yields the true residual
-//     ||A y - rho y|| / |rho|; if it exceeds rtol_r (2e-3) the solve continues
-//     as a plain fp32 Lanczos started from y with the stopping rule of
-//     thth_eig_kernel, and reports its Ritz value.
+//     triangle in one extra pass (second order in the vector error);
+//   * safety net: the same fp32 pass yields the true residual
+//     ||A y - rho y|| / |rho|; above rtol_r (1e-3) the solve continues as a plain
+//     fp32 Lanczos started from y with the stopping rule of thth_eig_kernel.
 // Failure modes / status bits as thth_eig_kernel (NaN where the reference's
 // try/except stores NaN).
+#ifndef SB_HOST_EMU
+#include <cuda_fp16.h>
+#endif
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
@@ -63,15 +72,16 @@ __device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float b
 #endif
 }
 
-// packed element of the bf16 triangle (thth.cu: pack_bf16x2): the low half is
-// bf16(re); the WHOLE word read as a float is the stored im (the packer picks the
-// high half so that this value is the nearest one to im), so only re needs a shift
-__device__ __forceinline__ float2 unpack_bf16x2(const unsigned p) {
-    return make_float2(__uint_as_float(p << 16), __uint_as_float(p));
+// packed element of the fp16 triangle (thth.cu: pack_f16x2): re in the low, im in
+// the high half
+__device__ __forceinline__ float2 unpack_f16x2(const unsigned p) {
+    __half2 h;
+    *reinterpret_cast<unsigned*>(&h) = p;
+    return __half22float2(h);
 }
 
 // shared-memory bytes of one CTA (host + device agree through this)
-__host__ __device__ inline size_t eig_bf16_smem(int ld) {
+__host__ __device__ inline size_t eig_half_smem(int ld) {
     return sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2) +
            (size_t)EB_NW * EB_NST * 4096 + (size_t)EB_NW * EB_NST * 8 + 16;
 }
@@ -82,7 +92,7 @@ __host__ __device__ inline size_t eig_bf16_smem(int ld) {
 // ~70 instructions per row pair of address / election bookkeeping).
 template <bool CPA>
 __global__ void __launch_bounds__(EB_THREADS, 2)
-thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restrict__ Mbbase,
+thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restrict__ Mbbase,
                      int ld, const int* __restrict__ nred, int eta0,
                      double* __restrict__ eigs, int* __restrict__ status,
                      int* __restrict__ iters, double tol, double etol, double rtol_r,
@@ -129,13 +139,13 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     fence_proxy_async();
     __syncthreads();
     const int ncol4 = (n + 1) >> 1;            // fp32 rows: float4 groups = two complex columns
-    const int ncolq = ((n + 3) >> 2) << 2;     // bf16 rows are fetched in multiples of 4 columns
+    const int ncolq = ((n + 3) >> 2) << 2;     // fp16 rows are fetched in multiples of 4 columns
     unsigned char* mystage = ring + (size_t)warp * EB_NST * 4096;
     unsigned long long* mybar = mbar + EB_NST * warp;
     unsigned phbits = 0;                       // bit s: phase parity of this warp's barrier s
 
     // ------------------------------------------------------------------
-    // bf16 mat-vec: w = (strict upper triangle) v row sums, u = column sums.
+    // fp16 mat-vec: w = (strict upper triangle) v row sums, u = column sums.
     // Warp `warp` owns the row pairs p = warp + NW k, rows (2p, 2p+1); a lane
     // owns the columns 4 (lane + 32 j) + i, j < 4, i < 4, of every row.
     // ------------------------------------------------------------------
@@ -259,12 +269,12 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
                 for (int i = 0; i < 4; ++i) {
                     const float2 x = X[j][i];
                     const float2 xrot = make_float2(-x.y, x.x);
-                    const float2 Q0 = unpack_bf16x2(p0[i]);
+                    const float2 Q0 = unpack_f16x2(p0[i]);
                     ffma2(S0a, x, Q0.x);
                     ffma2(S0b, xrot, Q0.y);
                     ffma2(yc[j][i], XA0, Q0.x);
                     ffma2(yc[j][i], XB0, Q0.y);
-                    const float2 Q1 = unpack_bf16x2(p1[i]);
+                    const float2 Q1 = unpack_f16x2(p1[i]);
                     ffma2(S1a, x, Q1.x);
                     ffma2(S1b, xrot, Q1.y);
                     ffma2(yc[j][i], XA1, Q1.x);
@@ -320,9 +330,9 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
 
     // ------------------------------------------------------------------
     // fp32 mat-vec (final Rayleigh quotient, fp32 continuation): one 4 KB row
-    // per stage, generic masks.  The ring may hold bf16 data interpreted as
-    // fp32 (finite: bf16 pairs never have an all-ones exponent in the high
-    // half, see bf16_bits) and vice versa it is re-zeroed afterwards.
+    // per stage, generic masks.  Stale fp16 words read as fp32 are only ever
+    // multiplied into columns that are discarded; the ring is re-zeroed afterwards
+    // because fp32 bit patterns read as fp16 could be inf / NaN.
     // ------------------------------------------------------------------
     auto matvec_f = [&]() {
         for (int c = tid; c < ld; c += EB_THREADS) w[c] = make_float2(0.f, 0.f);
@@ -386,7 +396,7 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             if (c < ld) u[c] = make_float2(sx, sy);
         }
         __syncthreads();
-        // fp32 rows may leave any bit pattern behind: the bf16 passes need zeros
+        // fp32 rows may leave any bit pattern behind: the fp16 passes need zeros
         for (int i = tid; i < EB_NW * EB_NST * 256; i += EB_THREADS)
             reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         fence_proxy_async();
@@ -450,7 +460,7 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         __syncthreads();
     };
     // ------------------------------------------------------------------
-    // bf16 Lanczos from the normalised vector in v (vp = 0), basis kept.  The
+    // fp16 Lanczos from the normalised vector in v (vp = 0), basis kept.  The
     // convergence check of the tridiagonal T_it runs on warp 0 DURING mat-vec it
     // (one step late), so nobody idles behind its Sturm sweeps; when it reports
     // convergence the step just taken is surplus and m = it.  Returns false if
@@ -628,26 +638,26 @@ thth_eig_bf16_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
 }
 
 #ifndef SB_HOST_EMU
-// d_Mb: the bf16 copy of d_M written by thth_build_kernel<true>.
-int eig_bf16_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* d_nred, int e0,
+// d_Mb: the scaled fp16 copy of d_M written by thth_build_kernel<true>.
+int eig_half_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* d_nred, int e0,
                     int nb, double* d_eigs, int* d_status, int* d_iters, double tol, double etol,
                     int max_iter, cudaStream_t st) {
     float2* d_basis = (float2*)workspace(7, (size_t)nb * EB_SLOTS * ld * sizeof(float2));
     if (!d_basis) return SB_ERR_NOMEM;
-    const size_t smem = eig_bf16_smem(ld);
-    double rtol_r = 2e-3;
+    const size_t smem = eig_half_smem(ld);
+    double rtol_r = 1e-3;
     if (const char* ev = getenv("SB_EIG_RTOL_R")) rtol_r = atof(ev);
     if (const char* ev = getenv("SB_EIG_ETOL_B")) etol = atof(ev);
     static const bool bulk = getenv("SB_EIG_BULK") != nullptr;   // A/B: cp.async.bulk row fetch
     if (bulk) {
-        SB_CUDA(cudaFuncSetAttribute(thth_eig_bf16_kernel<false>,
+        SB_CUDA(cudaFuncSetAttribute(thth_eig_half_kernel<false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        thth_eig_bf16_kernel<false><<<nb, EB_THREADS, smem, st>>>(
+        thth_eig_half_kernel<false><<<nb, EB_THREADS, smem, st>>>(
             d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, etol, rtol_r, max_iter, d_basis);
     } else {
-        SB_CUDA(cudaFuncSetAttribute(thth_eig_bf16_kernel<true>,
+        SB_CUDA(cudaFuncSetAttribute(thth_eig_half_kernel<true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        thth_eig_bf16_kernel<true><<<nb, EB_THREADS, smem, st>>>(
+        thth_eig_half_kernel<true><<<nb, EB_THREADS, smem, st>>>(
             d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, etol, rtol_r, max_iter, d_basis);
     }
     SB_LAUNCH_CHECK();

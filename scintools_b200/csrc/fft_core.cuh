@@ -50,6 +50,59 @@ __device__ __forceinline__ C mul_cs(C a, T c, T s) {
     return r;
 }
 
+// ---- float2 arithmetic on Blackwell's packed fp32 pipe ---------------------
+// add / sub / mul / fma .f32x2 (SASS FADD2 / FMUL2 / FFMA2, with free swap / negate /
+// scalar-broadcast operand forms): a complex add is ONE instruction, a complex multiply
+// TWO (b * a.x + (-b.y, b.x) * a.y) instead of two and six scalar ones.  These overloads
+// are picked over the generic templates above for every fp32 transform; the fp64
+// paths are unchanged.
+#ifndef SB_HOST_EMU
+__device__ __forceinline__ unsigned long long f2_pack(float2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2_unpack(unsigned long long r) {
+    float2 a;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+    return a;
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(r);
+}
+// a * (s, s)
+__device__ __forceinline__ float2 f2_scale(float2 a, float s) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(make_float2(s, s))));
+    return f2_unpack(r);
+}
+// a * (s, s) + c
+__device__ __forceinline__ float2 f2_fma(float2 a, float s, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r)
+        : "l"(f2_pack(a)), "l"(f2_pack(make_float2(s, s))), "l"(f2_pack(c)));
+    return f2_unpack(r);
+}
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return f2_fma(make_float2(-b.y, b.x), a.y, f2_scale(b, a.x));
+}
+template <int DIR> __device__ __forceinline__ float2 mul_w8(float2 a) {
+    const float2 r = DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+    return f2_scale(cadd(a, r), 0.70710678118654752440f);
+}
+template <int DIR> __device__ __forceinline__ float2 mul_cs(float2 a, float c, float s) {
+    const float2 r = DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+    return f2_fma(r, s, f2_scale(a, c));
+}
+#endif  // SB_HOST_EMU
+
 // ---- in-register DFTs, natural order in and out --------------------------
 template <int DIR, typename C> __device__ __forceinline__ void dft2(C& a, C& b) {
     C t = a; a = cadd(t, b); b = csub(t, b);

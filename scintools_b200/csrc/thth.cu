@@ -26,8 +26,8 @@ int eig_cluster_launch(const float2* d_M, int ld, int n_max, const int* d_nred, 
                        int nb, double* d_eigs, int* d_status, int* d_iters, double tol,
                        double etol, int max_iter, cudaStream_t st);
 
-// eig_bf16.cu: bf16 iteration + fp32 Rayleigh quotient (default for ld <= 512)
-int eig_bf16_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* d_nred, int e0,
+// eig_half.cu: bf16 iteration + fp32 Rayleigh quotient (default for ld <= 512)
+int eig_half_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* d_nred, int e0,
                     int nb, double* d_eigs, int* d_status, int* d_iters, double tol, double etol,
                     int max_iter, cudaStream_t st);
 
@@ -94,22 +94,49 @@ __global__ void thth_indexerr_kernel(ThthGeom g, const double* __restrict__ etas
 // --------------------------------------------------------------------------
 #define SB_BUILD_EB 8
 
-// fp32 pair -> one 32-bit word for eig_bf16.cu: low half = bf16(re) (round to
-// nearest even, no overflow to inf); high half h chosen so that the WHOLE word
-// (h << 16 | low) read as a float is as close to im as any h allows (error <= half
-// a bf16 ulp, like a plain bf16 rounding) -- the solver then uses the word itself as
-// im and only shifts for re.
-__device__ __forceinline__ unsigned pack_bf16x2(float2 v) {
-    const float big = 3.3895313892515355e38f;          // largest finite bf16
-    const unsigned lo = bf16_bits(fminf(fmaxf(v.x, -big), big));
-    const unsigned u = __float_as_uint(fminf(fmaxf(v.y, -big), big));
-    const unsigned m = u & 0x7fffffffu;
-    const unsigned t = m + 0x8000u;
-    const unsigned h = t >= lo ? (t - lo) >> 16 : 0u;
-    return (u & 0x80000000u) | (h << 16) | lo;
+// fp32 pair -> fp16 pair (re | im << 16, round to nearest even) for eig_half.cu
+__device__ __forceinline__ unsigned pack_f16x2(float2 v) {
+#ifdef SB_HOST_EMU
+    const __half2 h = __floats2half2_rn(v.x, v.y);
+    return (unsigned)h.x | ((unsigned)h.y << 16);
+#else
+    unsigned r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v.y), "f"(v.x));   // hi = first source
+    return r;
+#endif
 }
 
-// PACK: also write the bf16 copy Mb (re | im << 16) that eig_bf16.cu iterates on.
+// max |re|, |im| over the part of the conjugate spectrum the gather can touch
+// (rows x ncols of a [rows][pitch] array): the bound that keeps the scaled fp16
+// triangle finite.  out: non-negative float as uint bits (atomicMax), pre-zeroed.
+__global__ void cs_absmax_kernel(const float2* __restrict__ cs, long long rows, long long ncols,
+                                 long long pitch, unsigned* __restrict__ out) {
+    float m = 0.f;
+    const long long per_row4 = ncols >> 1;          // float4 = two complex columns
+    const long long total = rows * per_row4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / per_row4, c = i - r * per_row4;
+        const float4 q = __ldg(reinterpret_cast<const float4*>(cs + r * pitch) + c);
+        m = fmaxf(fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w))), m);
+    }
+    if (ncols & 1) {                                 // odd tail column
+        for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
+             r += (long long)gridDim.x * blockDim.x) {
+            const float2 q = __ldg(cs + r * pitch + ncols - 1);
+            m = fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), m);
+        }
+    }
+    if (!(m == m)) m = 3.0e38f;                      // NaN in the CS: treat as huge
+    m = fminf(m, 3.0e38f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// PACK: also write the fp16 copy Mb (re | im << 16) that eig_half.cu iterates on,
+// scaled by the power of two that puts absmax * max Jacobian of this curvature just
+// below 2^15 (absmax: device scalar from cs_absmax_kernel, span: max |theta2 - theta1|).
 //
 // Everything of thth_map's index math that does not depend on eta is computed
 // once per (row, column) pair and kept in registers while the CTA walks its
@@ -126,11 +153,11 @@ __device__ __forceinline__ unsigned pack_bf16x2(float2 v) {
 // these random 8-byte loads (ncu: long-scoreboard stalls 8.8 per issue with one load in
 // flight), not by its instruction count.
 template <bool PACK, int ROWS, typename OFF>
-__global__ void __launch_bounds__(32 * (32 / ROWS), 5)
+__global__ void __launch_bounds__(32 * (32 / ROWS), ROWS == 8 ? 5 : 4)
 thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nbatch,
                   int ld, const int* __restrict__ idx,
                   const int* __restrict__ nred, float2* __restrict__ M,
-                  unsigned* __restrict__ Mb) {
+                  unsigned* __restrict__ Mb, const unsigned* __restrict__ absmax, float span) {
     // eta is the FAST grid index: CTAs resident at the same time work on the
     // same 32x32 tile for neighbouring curvatures, whose gathers fall on
     // the same / adjacent CS rows for small |theta1^2 - theta2^2| (L2 reuse)
@@ -169,6 +196,11 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
         }
         const float seta = sqrtf((float)(2.0 * eta));
         float2* Me = M + (size_t)e * ld * ld;
+        float hscale = 1.f;             // power of two: |element| * hscale < 2^15
+        if (PACK) {
+            const float bound = __uint_as_float(*absmax) * seta * sqrtf(span);
+            if (bound > 0.f && bound < 3.0e38f) hscale = exp2f(floorf(log2f(32768.f / bound)));
+        }
         // ---- phase 1: offsets
         OFF off[ROWS];          // element offset into the CS (OFF = unsigned when it fits)
         unsigned hit = 0u;
@@ -240,7 +272,7 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
             }
             const size_t o = (size_t)(ta * 32 + la) * ld + b;
             Me[o] = v;
-            if (PACK) Mb[(size_t)e * ld * ld + o] = pack_bf16x2(v);
+            if (PACK) Mb[(size_t)e * ld * ld + o] = pack_f16x2(make_float2(v.x * hscale, v.y * hscale));
         }
     }
 }
@@ -701,7 +733,7 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
     if (batch > neta) batch = neta;
     float2* d_M = (float2*)workspace(2, per * batch);
     if (!d_M) return SB_ERR_NOMEM;
-    // default solver for ld <= 512 (eig_bf16.cu): iterates on the bf16 copy written by the
+    // default solver for ld <= 512 (eig_half.cu): iterates on the bf16 copy written by the
     // build kernel; SB_EIG_FP32=1 selects the fp32 streaming solver below instead
     const bool mixed = (ld <= 512) && !getenv("SB_EIG_FP32") && !getenv("SB_EIG_CLUSTER") &&
                        !getenv("SB_EIG_PERSIST") && !getenv("SB_EIG_NO_TMA");
@@ -736,30 +768,54 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
     else
         SB_CUDA(cudaFuncSetAttribute(thth_eig_kernel<DT, false, 1>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // scale of the fp16 copy: max |CS| over what the gather can reach, max |theta2 - theta1|
+    unsigned* d_absmax = nullptr;
+    float span = 0.f;
+    if (mixed) {
+        d_absmax = (unsigned*)workspace(0, 64 * sizeof(double)) + 32;   // behind the dynspec stats
+        if (!d_absmax) return SB_ERR_NOMEM;
+        SB_CUDA(cudaMemsetAsync(d_absmax, 0, sizeof(unsigned), st));
+        const long long ncols = g.cs_half ? (g.cs_valid_cols > 0 ? g.cs_valid_cols : g.nfd / 2 + 1)
+                                          : g.nfd;
+        cs_absmax_kernel<<<num_sms() * 8, 256, 0, st>>>(g.cs, g.ntau, ncols, g.cs_pitch, d_absmax);
+        SB_LAUNCH_CHECK();
+        double tmin = th_host[0], tmax = th_host[0];
+        for (int k = 1; k < g.n; ++k) {
+            tmin = th_host[k] < tmin ? th_host[k] : tmin;
+            tmax = th_host[k] > tmax ? th_host[k] : tmax;
+        }
+        span = (float)((tmax - tmin) * 1.0001);
+    }
     for (int e0 = 0; e0 < neta; e0 += batch) {
         int nb = neta - e0 < batch ? neta - e0 : batch;
-        constexpr int BR = 8;            // rows per thread of thth_build_kernel
+        // rows per thread of thth_build_kernel: 4 (default) or 8 (SB_BUILD_ROWS=8; measured
+        // slower: 1.54 vs 1.21 ms -- the gather is bound by random DRAM sector reads, not by
+        // the number of loads a thread keeps in flight)
+        static const int BR = (getenv("SB_BUILD_ROWS") && atoi(getenv("SB_BUILD_ROWS")) == 8) ? 8 : 4;
         dim3 grid((nb + SB_BUILD_EB - 1) / SB_BUILD_EB, npairs), block(32, 32 / BR);
         prof_begin(PROF_THTH_BUILD, st);
         // 32-bit CS offsets whenever the spectrum has fewer than 2^32 elements
         const bool small = (unsigned long long)g.ntau * (unsigned long long)g.cs_pitch < (1ull << 32);
-        if (mixed && small)
-            thth_build_kernel<true, BR, unsigned><<<grid, block, 0, st>>>(
-                g, d_etas, e0, nb, ld, d_idx, d_nred, d_M, d_Mb);
-        else if (mixed)
-            thth_build_kernel<true, BR, size_t><<<grid, block, 0, st>>>(
-                g, d_etas, e0, nb, ld, d_idx, d_nred, d_M, d_Mb);
-        else if (small)
-            thth_build_kernel<false, BR, unsigned><<<grid, block, 0, st>>>(
-                g, d_etas, e0, nb, ld, d_idx, d_nred, d_M, nullptr);
-        else
-            thth_build_kernel<false, BR, size_t><<<grid, block, 0, st>>>(
-                g, d_etas, e0, nb, ld, d_idx, d_nred, d_M, nullptr);
+#define SB_BUILD_LAUNCH(PACK, ROWS, OFF, MB, AM, SP)                                        \
+        thth_build_kernel<PACK, ROWS, OFF><<<grid, block, 0, st>>>(g, d_etas, e0, nb, ld, d_idx, \
+                                                                   d_nred, d_M, MB, AM, SP)
+        if (BR == 8) {
+            if (mixed && small) SB_BUILD_LAUNCH(true, 8, unsigned, d_Mb, d_absmax, span);
+            else if (mixed) SB_BUILD_LAUNCH(true, 8, size_t, d_Mb, d_absmax, span);
+            else if (small) SB_BUILD_LAUNCH(false, 8, unsigned, nullptr, nullptr, 0.f);
+            else SB_BUILD_LAUNCH(false, 8, size_t, nullptr, nullptr, 0.f);
+        } else {
+            if (mixed && small) SB_BUILD_LAUNCH(true, 4, unsigned, d_Mb, d_absmax, span);
+            else if (mixed) SB_BUILD_LAUNCH(true, 4, size_t, d_Mb, d_absmax, span);
+            else if (small) SB_BUILD_LAUNCH(false, 4, unsigned, nullptr, nullptr, 0.f);
+            else SB_BUILD_LAUNCH(false, 4, size_t, nullptr, nullptr, 0.f);
+        }
+#undef SB_BUILD_LAUNCH
         prof_end(PROF_THTH_BUILD, st);
         SB_LAUNCH_CHECK();
         prof_begin(PROF_THTH_EIG, st);
         // experimental solvers, each enabled by its own environment variable
-        int rc = mixed ? eig_bf16_launch(d_M, d_Mb, ld, d_nred, e0, nb, d_eigs, d_status,
+        int rc = mixed ? eig_half_launch(d_M, d_Mb, ld, d_nred, e0, nb, d_eigs, d_status,
                                          d_iters, tol, 2e-7, max_iter, st)
                        : 0;
         if (rc == 0)
@@ -767,7 +823,7 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
                                     tol, 2e-7, max_iter, st);
         if (rc < 0) return rc;
         if (rc > 0) {
-            // handled by eig_bf16.cu / eig_cluster.cu
+            // handled by eig_half.cu / eig_cluster.cu
         } else if (use_tma && persist > 0)
             thth_eig_kernel<TT, true, PS, true><<<persist < nb ? persist : nb, TT, smem_p, st>>>(
                 d_M, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, 2e-7, max_iter, nb);

@@ -11,6 +11,7 @@ struct ThthGeom {
     const float2* cs;      // conjugate spectrum, fftshifted rows
     long long ntau, nfd;   // logical size
     long long cs_pitch;    // elements per stored row
+    int cs_valid_cols;     // half layout: stored columns that hold data (0 = all nfd/2+1)
     int cs_half;           // 0: full [ntau][nfd]; 1: Hermitian half [ntau][nfd/2+1]
                            //    holding the UNSHIFTED columns k = 0..nfd/2 (fd >= 0)
     double tau0, dtau, half_dtau, tau_absmax;  // tau[0], mean diff, /2, |tau.max()|

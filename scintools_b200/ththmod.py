@@ -141,6 +141,7 @@ class _Geom:
         g.coherent = 1 if coherent else 0
         g.cs_half = 1 if (cs is not None and cs.half) else 0
         g.cs_pitch = cs.pitch if cs is not None else fd.shape[0]
+        g.cs_valid_cols = int(cs.ncols_valid) if (cs is not None and cs.half) else 0
         self.g = g
         if cs is not None and cs.half and cs.ncols_valid < fd.shape[0] // 2 + 1:
             need = needed_fd_columns(fd, edges)

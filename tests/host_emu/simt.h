@@ -54,6 +54,9 @@ template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline int atomicOr(int* p, int v) { int o = *p; *p = o | v; return o; }
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
+static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
+static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
+static inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
 using std::isfinite;
 
 namespace emu {

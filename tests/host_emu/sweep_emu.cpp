@@ -3,7 +3,7 @@
 // thth_build_kernel (gather into the strict upper triangle) and
 // thth_eig_kernel<256, TMA, 2> (bulk-copy ring + Lanczos), sources unchanged,
 // launch geometry as in sb::eta_sweep.  mixed != 0: the default solver
-// csrc/eig_bf16.cu (bf16 iteration + fp32 Rayleigh quotient) instead of the fp32
+// csrc/eig_half.cu (bf16 iteration + fp32 Rayleigh quotient) instead of the fp32
 // thth_eig_kernel; -DSB_EB_SLOTS=3 exercises its fp32 restart.
 // TEST INFRASTRUCTURE (tests/test_host_emulation.py).
 #define SB_HOST_EMU 1
@@ -18,7 +18,7 @@ namespace sb {
 alignas(128) unsigned char smem_raw[256 * 1024];
 }
 #include "../../scintools_b200/csrc/thth.cu"
-#include "../../scintools_b200/csrc/eig_bf16.cu"
+#include "../../scintools_b200/csrc/eig_half.cu"
 
 extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, long long cs_pitch,
                              int cs_half, double tau0, double dtau, double tau_absmax, double fd0,
@@ -33,7 +33,7 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
     g.tau0 = tau0; g.dtau = dtau; g.half_dtau = dtau / 2; g.tau_absmax = tau_absmax;
     g.fd0 = fd0; g.dfd = dfd; g.half_dfd = dfd / 2; g.fd_half = fd_half;
     g.inv_dtau = 1.0 / dtau; g.inv_dfd = 1.0 / dfd;
-    g.th = th; g.n = n_th; g.coherent = coherent; g.cs_half = cs_half;
+    g.th = th; g.n = n_th; g.coherent = coherent; g.cs_half = cs_half; g.cs_valid_cols = 0;
     g.cs_pitch = cs_half ? cs_pitch : (cs_pitch > 0 ? cs_pitch : nfd);
     const int ld = (n_th + 31) / 32 * 32;
     if (ld > 512) return -1;
@@ -51,6 +51,21 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
             emu::run_block(emu::Dim3{256, 1, 1}, emu::Dim3{bx, (unsigned)e, 0},
                            emu::Dim3{4, (unsigned)neta, 1},
                            [&]() { thth_indexerr_kernel(g, etas, status); });
+    // scale inputs of the fp16 copy (host versions of cs_absmax_kernel / the span in eta_sweep)
+    unsigned absmax_bits = 0;
+    {
+        float m = 0.f;
+        const long long ncols = cs_half ? nfd / 2 + 1 : nfd;
+        for (long long r = 0; r < ntau; ++r)
+            for (long long c = 0; c < ncols; ++c) {
+                const float2 q = g.cs[r * g.cs_pitch + c];
+                m = std::fmax(std::fmax(std::fabs(q.x), std::fabs(q.y)), m);
+            }
+        absmax_bits = __float_as_uint(m);
+    }
+    double tmin = th[0], tmax = th[0];
+    for (int k = 1; k < n_th; ++k) { tmin = th[k] < tmin ? th[k] : tmin; tmax = th[k] > tmax ? th[k] : tmax; }
+    const float span = (float)((tmax - tmin) * 1.0001);
     const int T = ld / 32, npairs = T * (T + 1) / 2;
     const unsigned gx = (unsigned)((neta + SB_BUILD_EB - 1) / SB_BUILD_EB);
     for (unsigned bx = 0; bx < gx; ++bx)
@@ -59,10 +74,10 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
                            [&]() {
                                if (mixed)
                                    thth_build_kernel<true, 8, unsigned>(g, etas, 0, neta, ld, idx.data(), nred,
-                                                           M.data(), Mb.data());
+                                                           M.data(), Mb.data(), &absmax_bits, span);
                                else
                                    thth_build_kernel<false, 8, size_t>(g, etas, 0, neta, ld, idx.data(), nred,
-                                                            M.data(), nullptr);
+                                                            M.data(), nullptr, nullptr, 0.f);
                            });
     if (M_out) std::memcpy(M_out, M.data(), M.size() * sizeof(float2));   // [neta][ld][ld] triangle
     if (max_iter <= 0 || max_iter > SB_LANCZOS_MAXIT) max_iter = SB_LANCZOS_MAXIT;
@@ -74,7 +89,7 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
             std::memset(smem_raw, 0xa5, sizeof(smem_raw));     // garbage, like real shared memory
             emu::run_block(emu::Dim3{(unsigned)EB_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
                            emu::Dim3{(unsigned)neta, 1, 1}, [&]() {
-                               thth_eig_bf16_kernel<true>(M.data(), Mb.data(), ld, nred, 0, eigs, status,
+                               thth_eig_half_kernel<true>(M.data(), Mb.data(), ld, nred, 0, eigs, status,
                                                     iters, tol, 2e-7, mixed >= 2 ? 0.0 : 2e-3,
                                                     max_iter, gbasis.data());
                            });

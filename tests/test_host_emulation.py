@@ -142,7 +142,7 @@ def _triangles(golden_dir, etas_idx):
 
 def _sweep_emu_lib(slots=0):
     """tests/host_emu/sweep_emu.cpp compiled for the CPU; slots > 0 shrinks the
-    Lanczos-basis capacity of eig_bf16.cu so that its fp32 restart is taken."""
+    Lanczos-basis capacity of eig_half.cu so that its fp32 restart is taken."""
     src = os.path.join(EMU, "sweep_emu.cpp")
     out = os.path.join(EMU, "_build", "sweep_emu%s.so" % ("_s%d" % slots if slots else ""))
     os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -159,11 +159,11 @@ def _sweep_emu_lib(slots=0):
 @pytest.mark.parametrize("mixed,slots", [(0, 0), (1, 0), (2, 0), (1, 3)])
 def test_default_sweep_kernels_on_host(golden_dir, mixed, slots):
     """The device code of the curvature sweep (csrc/thth.cu: thth_prep_kernel,
-    thth_indexerr_kernel, thth_build_kernel; csrc/eig_bf16.cu) under the SIMT
+    thth_indexerr_kernel, thth_build_kernel; csrc/eig_half.cu) under the SIMT
     emulator, launch geometry as in sb::eta_sweep, against the reference: cropped
     sizes bit-exact, eigenvalues to 1e-5.  mixed=0: the fp32 streaming solver
     thth_eig_kernel<256, TMA, 2> (SB_EIG_FP32=1); mixed=1: the default solver
-    (bf16 iteration + fp32 Rayleigh quotient); mixed=2: its fp32 continuation
+    (fp16 iteration + fp32 Rayleigh quotient); mixed=2: its fp32 continuation
     forced on every curvature; slots=3: its fp32 restart (basis slots exhausted)."""
     from oracle import thth_oracle as TO
     lib = _sweep_emu_lib(slots)
