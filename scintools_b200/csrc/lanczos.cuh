@@ -95,11 +95,16 @@ __device__ inline void lanczos_check(LanczosShared& S, int m, double tol, double
         double q0 = 1.0, q1 = S.alpha[0] - theta;
         for (int i = 1; i < m; ++i) {
             double q2 = (S.alpha[i] - theta) * q1 - S.beta2[i] * q0;
+            // l_{i-1} = beta_i * q_{i-1}/q_i in pivot terms: beta_i / d_{i-1}, d = q1/q0.
+            // Taken BEFORE the range rescaling below, which scales (q1, q2) but not q0:
+            // with the ratio formed afterwards the first rescale (|q| > 1e140, i.e. step
+            // ~20 for eigenvalues ~3e7) blew piv up by 1e140, the norm overflowed and the
+            // residual came out as 0 -- a silent stop at m = 21 with an unconverged value
+            // (round 1: up to 4e-3 off on 2.5 % of the 4096x8192 curvatures).
+            S.piv[i - 1] = (q1 != 0.0) ? S.beta[i] * q0 / q1 : 1e300;
             const double aq = fabs(q2);
             if (aq > 1e140) { q2 *= 1e-140; q1 *= 1e-140; }
             else if (aq < 1e-140 && fabs(q1) < 1e-140) { q2 *= 1e140; q1 *= 1e140; }
-            // l_{i-1} = beta_i * q_{i-1}/q_i in pivot terms: beta_i / d_{i-1}, d = q1/q0
-            S.piv[i - 1] = (q1 != 0.0) ? S.beta[i] * q0 / q1 : 1e300;
             q0 = q1;
             q1 = q2;
         }

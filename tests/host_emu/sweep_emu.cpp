@@ -104,3 +104,53 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
     }
     return 0;
 }
+
+// Eigen solvers on PRE-BUILT triangles M [nb][ld][ld] (strict upper triangle valid,
+// diagonal / columns >= n zero): mixed == 0 -> thth_eig_kernel<256, TMA, 2>,
+// else thth_eig_half_kernel on an fp16 copy packed here with the same rule as the
+// build kernel (power-of-two scale from the largest element).
+extern "C" int emu_eig_triangles(const float* Mf, int ld, const int* nred, int nb, int mixed,
+                                 double tol, int max_iter, double* eigs, int* status, int* iters) {
+    using namespace sb;
+    const float2* M = reinterpret_cast<const float2*>(Mf);
+    if (max_iter <= 0 || max_iter > SB_LANCZOS_MAXIT) max_iter = SB_LANCZOS_MAXIT;
+    for (int e = 0; e < nb; ++e) status[e] = 0;
+    std::vector<unsigned> Mb;
+    std::vector<float2> gbasis;
+    if (mixed) {
+        Mb.assign((size_t)nb * ld * ld, 0u);
+        gbasis.resize((size_t)nb * EB_SLOTS * ld);
+        for (int e = 0; e < nb; ++e) {
+            const int n = nred[e];
+            float mx = 0.f;
+            for (int a = 0; a < n; ++a)
+                for (int c = a + 1; c < n; ++c) {
+                    const float2 q = M[((size_t)e * ld + a) * ld + c];
+                    mx = std::fmax(std::fmax(std::fabs(q.x), std::fabs(q.y)), mx);
+                }
+            const float sc = mx > 0.f ? std::exp2(std::floor(std::log2(32768.f / mx))) : 1.f;
+            for (int a = 0; a < n; ++a)
+                for (int c = a; c < ld; ++c) {
+                    float2 q = M[((size_t)e * ld + a) * ld + c];
+                    if (c >= n || c == a) q = make_float2(0.f, 0.f);
+                    Mb[((size_t)e * ld + a) * ld + c] = pack_f16x2(make_float2(q.x * sc, q.y * sc));
+                }
+        }
+    }
+    for (int e = 0; e < nb; ++e) {
+        std::memset(smem_raw, 0xa5, sizeof(smem_raw));
+        if (mixed)
+            emu::run_block(emu::Dim3{(unsigned)EB_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
+                           emu::Dim3{(unsigned)nb, 1, 1}, [&]() {
+                               thth_eig_half_kernel<true>(M, Mb.data(), ld, nred, 0, eigs, status, iters,
+                                                          tol, 2e-7, 1e-3, max_iter, gbasis.data());
+                           });
+        else
+            emu::run_block(emu::Dim3{256, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
+                           emu::Dim3{(unsigned)nb, 1, 1}, [&]() {
+                               thth_eig_kernel<256, true, 2>(M, ld, nred, 0, eigs, status, iters, tol,
+                                                             2e-7, max_iter, nb);
+                           });
+    }
+    return 0;
+}

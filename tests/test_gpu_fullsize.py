@@ -128,7 +128,9 @@ def test_c3_cs_and_sweep(sb):
     # 64 curvatures across the grid (plus the four corners of the old check) against the
     # oracle (numpy gather + ARPACK) on the same conjugate spectrum, full 511 x 511 maps
     CS_host = cs.numpy().astype(np.complex64)
-    pick = sorted(set(list(range(0, bench.NETA, 16)) + [400, 700, 1023]))
+    # incl. the slowly converging curvatures that exposed the round-1 stopping bug
+    pick = sorted(set(list(range(0, bench.NETA, 16)) + [400, 700, 1023, 95, 118, 119, 120, 121, 162,
+                                                         174, 325, 784, 809, 810, 905]))
     worst = 0.0
     for i in pick:
         ref = TO.Eval_calc(CS_host, tau, fd, etas[i], edges)

@@ -345,3 +345,29 @@ def test_retrieval_kernels_on_host(golden_dir):
     Vr = g["V"].astype(complex)
     z = np.vdot(V, Vr)
     assert np.abs(V * (z / abs(z)) - Vr).max() < 3e-5 * np.abs(Vr).max()
+
+
+@pytest.mark.parametrize("mixed", [0, 1])
+def test_slowly_converging_curvature_on_host(golden_dir, mixed):
+    """Regression for the round-1 stopping bug (lanczos.cuh: the residual estimate
+    collapsed to 0 at the first range rescaling of the Sturm sequence, step ~21 for
+    eigenvalues ~3e7): curvature 121 of the full-size bench workload needs 38 Lanczos
+    steps (the top Ritz value plateaus 0.5 % low for steps 13-20).  Both solvers must
+    reach the dense eigenvalue."""
+    lib = _sweep_emu_lib(0)
+    g = np.load(os.path.join(golden_dir, "thth_hard_511.npz"))
+    n, ld = int(g["n"]), 512
+    M = np.zeros((1, ld, ld), np.complex64)
+    M[0][np.triu_indices(n, 1)[0], np.triu_indices(n, 1)[1]] = g["upper"]
+    nred = np.array([n], np.int32)
+    eigs = np.zeros(1)
+    st = np.zeros(1, np.int32)
+    it = np.zeros(1, np.int32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib.emu_eig_triangles.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p]
+    lib.emu_eig_triangles(P(M), ld, P(nred), 1, mixed, 2e-5, 0, P(eigs), P(st), P(it))
+    assert st[0] == 0
+    assert abs(eigs[0] - float(g["top"])) / float(g["top"]) < 1e-6, (eigs, it)
+    assert it[0] > 30
