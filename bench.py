@@ -336,7 +336,8 @@ def b200_arm(args):
     # the sweep gathers at fd = theta_j - theta_i <= 2*EDGE_LIM: only those fd
     # columns of the CS are computed (exactly what single_search does)
     keep = thth.needed_fd_columns(fd, edges) or 0
-    cs = thth.DeviceCS(d_cs, nfd=nfd, ncols_valid=keep or None)
+    d_bound = D.empty((1,), torch.float32)      # L1 bound of |CS| (scale of the solver's fp16 copy)
+    cs = thth.DeviceCS(d_cs, nfd=nfd, ncols_valid=keep or None, bound=d_bound)
     geom = thth._Geom(cs, tau, fd, edges, True)
     stream = D.stream_ptr()
     L = _lib.lib
@@ -356,6 +357,8 @@ def b200_arm(args):
         def step():
             _lib.check(L.sb_cs_f32(d_dyn.data_ptr(), NF, NT, NPAD, 0.0, 0, 1, pitch, keep,
                                    d_cs.data_ptr(), stream))
+            _lib.check(L.sb_cs_bound_f32(d_dyn.data_ptr(), NF, NT, NPAD, 0.0, d_bound.data_ptr(),
+                                         stream))
             _lib.check(L.sb_eta_sweep(geom.ref, buf["etas"].data_ptr(), n, thth.DEFAULT_TOL,
                                       0, buf["eigs"].data_ptr(), buf["stat"].data_ptr(),
                                       buf["nred"].data_ptr(), buf["iters"].data_ptr(), stream))

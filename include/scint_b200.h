@@ -83,6 +83,9 @@ typedef struct sb_thth_geom {
     int32_t cs_valid_cols; /* cs_half only: how many of the nfd/2+1 stored columns hold data
                               (sb_cs_f32 with ncols_keep > 0 computes only those the theta
                               grid can reach); 0 = all.  Nothing beyond is ever read. */
+    const float* cs_bound; /* device scalar: an upper bound of max |re|, |im| over the CS
+                              (sb_cs_bound_f32), or NULL -> the sweep scans the CS itself.
+                              Only used to scale the fp16 iteration copy of the matrices. */
 } sb_thth_geom;
 
 /* Replaces the eta loop of ththmod.single_search (ththmod.py:789-811) /
@@ -258,6 +261,14 @@ int sb_acf_sspec_f32(const float* dyn, int32_t nf, int32_t nt, const float* win_
 int sb_cs_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad,
               float pad_value, const uint8_t* tau_rowmask, int32_t half_plane,
               int64_t cs_pitch, int32_t ncols_keep, void* cs, void* stream);
+
+/* Upper bound of max |CS| for the conjugate spectrum sb_cs_f32 makes from the same
+ * (dspec, nf, nt, npad, pad_value): sum |dspec - c| + |c| (npad+1)^2 nf nt with c the
+ * padding constant (the mean when pad_value is NaN) -- the L1 norm bounds every Fourier
+ * coefficient.  One pass over dspec.  bound_out: device float.  Feeds
+ * sb_thth_geom.cs_bound (the eigen solver's fp16 scale); a loose bound is fine. */
+int sb_cs_bound_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad, float pad_value,
+                    float* bound_out, void* stream);
 
 /* ---- scint_sim.Simulation ------------------------------------------------ */
 

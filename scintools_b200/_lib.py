@@ -38,6 +38,7 @@ class ThthGeom(ctypes.Structure):
         ("th_cents", vp), ("th_cents_host", vp),
         ("n_th", c_int), ("coherent", c_int),
         ("cs_pitch", c_i64), ("cs_half", c_int), ("cs_valid_cols", c_int),
+        ("cs_bound", vp),
     ]
 
 
@@ -78,6 +79,7 @@ _SIGS = {
     "sb_acf_f32": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp]),
     "sb_acf_sspec_f32": (c_int, [vp, c_int, c_int, vp, vp, c_dbl, c_dbl, c_int, vp, vp]),
     "sb_cs_f32": (c_int, [vp, c_int, c_int, c_int, c_flt, vp, c_int, c_i64, c_int, vp, vp]),
+    "sb_cs_bound_f32": (c_int, [vp, c_int, c_int, c_int, c_flt, vp, vp]),
     "sb_sim_weights": (c_int, [ctypes.POINTER(SimParams), vp, vp]),
     "sb_sim_screen": (c_int, [c_int, c_int, vp, vp, vp, ctypes.c_uint64, vp, vp]),
     "sb_sim_intensity": (c_int, [c_int, c_int, c_int, vp, vp, c_dbl, c_dbl, vp,

@@ -150,6 +150,8 @@ int ifft2_c2c(const float2* in, int n0, int n1, int centred, int crop0, int crop
 int gerchberg_saxton(float2* W, const float* amp, const unsigned char* rowmask, int n0, int n1,
                      int niter, cudaStream_t st);
 
+int conj_spectrum_bound(const float* dyn, int nf, int nt, int npad, float pad_value, float* out,
+                        cudaStream_t st);
 int norm_sspec_rows(const float* sspec, int nr, int nc, const double* fdop, const double* tdel,
                     double eta, double maxnormfac, const double* fdopnew, int nq, float* out,
                     double* power, cudaStream_t st);
@@ -182,6 +184,7 @@ static int to_geom(const sb_thth_geom* in, ThthGeom* g) {
     g->coherent = in->coherent;
     g->cs_half = in->cs_half;
     g->cs_valid_cols = in->cs_half ? in->cs_valid_cols : 0;
+    g->cs_bound = in->cs_bound;
     g->cs_pitch = in->cs_half ? in->cs_pitch : (in->cs_pitch > 0 ? in->cs_pitch : in->nfd);
     SB_ARG(!in->cs_half || (in->cs_pitch >= in->nfd / 2 + 1 && in->nfd % 2 == 0));
     return SB_OK;
@@ -191,7 +194,7 @@ static int to_geom(const sb_thth_geom* in, ThthGeom* g) {
 
 extern "C" {
 
-int sb_abi_version(void) { return 1; }
+int sb_abi_version(void) { return 2; }
 const char* sb_last_error(void) { return sb::last_error(); }
 
 int sb_init(int device) {
@@ -386,6 +389,12 @@ int sb_cs_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad,
     return sb::conj_spectrum(dspec, nf, nt, npad, pad_value, tau_rowmask,
                              half_plane, (long)cs_pitch, ncols_keep, (float2*)cs,
                              (cudaStream_t)stream);
+}
+
+int sb_cs_bound_f32(const float* dspec, int32_t nf, int32_t nt, int32_t npad, float pad_value,
+                    float* bound_out, void* stream) {
+    SB_ARG(dspec && bound_out && nf >= 1 && nt >= 1 && npad >= 0);
+    return sb::conj_spectrum_bound(dspec, nf, nt, npad, pad_value, bound_out, (cudaStream_t)stream);
 }
 
 int sb_sim_weights(const sb_sim_params* p, double* w, void* stream) {

@@ -605,6 +605,49 @@ static int conj_spectrum_bluestein(const float* dyn, int nf, int nt, int NF, int
                                    const unsigned char* rowmask, float2* CS,
                                    cudaStream_t st);
 
+// sum |dyn - c| (c = stats[4], the mean, when use_mean; else the constant sub)
+__global__ void dyn_l1_kernel(const float* __restrict__ dyn, long total, const double* __restrict__ stats,
+                              int use_mean, float sub, double* __restrict__ acc) {
+    const float c = use_mean ? (float)stats[4] : sub;
+    double s = 0.0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long)gridDim.x * blockDim.x) {
+        const float v = fabsf(dyn[i] - c);
+        s += (v == v) ? (double)v : 0.0;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(acc, s);
+}
+__global__ void dyn_l1_final_kernel(const double* acc, const double* stats, int use_mean, float sub,
+                                    double npix_padded, float* out) {
+    const double c = use_mean ? fabs(stats[4]) : fabs((double)sub);
+    double b = (acc[0] + c * npix_padded) * 1.000001;
+    if (!(b < 3.0e38)) b = 3.0e38;
+    *out = (float)b;
+}
+
+// upper bound of max |CS| of conj_spectrum() for the same inputs: the L1 norm of what is
+// transformed (dyn - c on the live pixels) + the DC correction |c| NF NT
+int conj_spectrum_bound(const float* dyn, int nf, int nt, int npad, float pad_value, float* out,
+                        cudaStream_t st) {
+    double* stats = (double*)workspace(0, 64 * sizeof(double));
+    if (!stats) return SB_ERR_NOMEM;
+    const bool dev_mean = pad_value != pad_value;
+    if (dev_mean) {
+        int rc = stats_pass(dyn, nf, nt, nullptr, nullptr, 0, 0, stats, st);
+        if (rc) return rc;
+    }
+    double* acc = stats + 24;
+    SB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
+    dyn_l1_kernel<<<num_sms() * 4, 256, 0, st>>>(dyn, (long)nf * nt, stats, dev_mean ? 1 : 0,
+                                                 dev_mean ? 0.f : pad_value, acc);
+    SB_LAUNCH_CHECK();
+    dyn_l1_final_kernel<<<1, 1, 0, st>>>(acc, stats, dev_mean ? 1 : 0, dev_mean ? 0.f : pad_value,
+                                         (double)(npad + 1) * nf * (double)(npad + 1) * nt, out);
+    SB_LAUNCH_CHECK();
+    return SB_OK;
+}
+
 // conjugate spectrum of a zero(/constant)-padded chunk
 // (ththmod.py:777-787, dynspec.py:1572-1579)
 int conj_spectrum(const float* dyn, int nf, int nt, int npad, float pad_value,

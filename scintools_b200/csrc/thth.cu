@@ -774,11 +774,15 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
     if (mixed) {
         d_absmax = (unsigned*)workspace(0, 64 * sizeof(double)) + 32;   // behind the dynspec stats
         if (!d_absmax) return SB_ERR_NOMEM;
-        SB_CUDA(cudaMemsetAsync(d_absmax, 0, sizeof(unsigned), st));
-        const long long ncols = g.cs_half ? (g.cs_valid_cols > 0 ? g.cs_valid_cols : g.nfd / 2 + 1)
-                                          : g.nfd;
-        cs_absmax_kernel<<<num_sms() * 8, 256, 0, st>>>(g.cs, g.ntau, ncols, g.cs_pitch, d_absmax);
-        SB_LAUNCH_CHECK();
+        if (g.cs_bound) {       // the caller knows a bound (sb_cs_bound_f32): no scan
+            SB_CUDA(cudaMemcpyAsync(d_absmax, g.cs_bound, sizeof(float), cudaMemcpyDeviceToDevice, st));
+        } else {
+            SB_CUDA(cudaMemsetAsync(d_absmax, 0, sizeof(unsigned), st));
+            const long long ncols = g.cs_half ? (g.cs_valid_cols > 0 ? g.cs_valid_cols : g.nfd / 2 + 1)
+                                              : g.nfd;
+            cs_absmax_kernel<<<num_sms() * 8, 256, 0, st>>>(g.cs, g.ntau, ncols, g.cs_pitch, d_absmax);
+            SB_LAUNCH_CHECK();
+        }
         double tmin = th_host[0], tmax = th_host[0];
         for (int k = 1; k < g.n; ++k) {
             tmin = th_host[k] < tmin ? th_host[k] : tmin;

@@ -12,6 +12,7 @@ struct ThthGeom {
     long long ntau, nfd;   // logical size
     long long cs_pitch;    // elements per stored row
     int cs_valid_cols;     // half layout: stored columns that hold data (0 = all nfd/2+1)
+    const float* cs_bound; // device: upper bound of max |CS| or null (the sweep scans)
     int cs_half;           // 0: full [ntau][nfd]; 1: Hermitian half [ntau][nfd/2+1]
                            //    holding the UNSHIFTED columns k = 0..nfd/2 (fd >= 0)
     double tau0, dtau, half_dtau, tau_absmax;  // tau[0], mean diff, /2, |tau.max()|

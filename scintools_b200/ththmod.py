@@ -62,9 +62,11 @@ class DeviceCS:
     (unshifted k = 0..nfd/2) of the CS of a REAL dynamic spectrum; the other
     half is its Hermitian mirror and is never materialised."""
 
-    def __init__(self, tensor, nfd=None, ncols_valid=None):
+    def __init__(self, tensor, nfd=None, ncols_valid=None, bound=None):
         assert tensor.dim() == 3 and tensor.shape[2] == 2
         self.t = tensor
+        # device float: upper bound of max |CS| (sb_cs_bound_f32) or None -> the sweep scans
+        self.bound = bound
         self.half = nfd is not None
         self.pitch = int(tensor.shape[1])
         self.shape = (int(tensor.shape[0]), int(nfd) if self.half else self.pitch)
@@ -142,6 +144,7 @@ class _Geom:
         g.cs_half = 1 if (cs is not None and cs.half) else 0
         g.cs_pitch = cs.pitch if cs is not None else fd.shape[0]
         g.cs_valid_cols = int(cs.ncols_valid) if (cs is not None and cs.half) else 0
+        g.cs_bound = cs.bound.data_ptr() if (cs is not None and cs.bound is not None) else None
         self.g = g
         if cs is not None and cs.half and cs.ncols_valid < fd.shape[0] // 2 + 1:
             need = needed_fd_columns(fd, edges)
@@ -356,8 +359,11 @@ def conjugate_spectrum(dspec2, npad, pad_value=None, tau=None, tau_mask=0.0,
     _lib.check(_lib.lib.sb_cs_f32(dd.data_ptr(), nf, nt, npad, float(pad_value),
                                   D.ptr(mask), 1 if half else 0, pitch, keep,
                                   cs.data_ptr(), D.stream_ptr()))
+    bound = D.empty((1,), torch.float32)
+    _lib.check(_lib.lib.sb_cs_bound_f32(dd.data_ptr(), nf, nt, npad, float(pad_value),
+                                        bound.data_ptr(), D.stream_ptr()))
     return DeviceCS(cs, nfd=NT if half else None,
-                    ncols_valid=keep if keep else None)
+                    ncols_valid=keep if keep else None, bound=bound)
 
 
 def peak_fit(etas, eigs, fw):

@@ -33,7 +33,7 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
     g.tau0 = tau0; g.dtau = dtau; g.half_dtau = dtau / 2; g.tau_absmax = tau_absmax;
     g.fd0 = fd0; g.dfd = dfd; g.half_dfd = dfd / 2; g.fd_half = fd_half;
     g.inv_dtau = 1.0 / dtau; g.inv_dfd = 1.0 / dfd;
-    g.th = th; g.n = n_th; g.coherent = coherent; g.cs_half = cs_half; g.cs_valid_cols = 0;
+    g.th = th; g.n = n_th; g.coherent = coherent; g.cs_half = cs_half; g.cs_valid_cols = 0; g.cs_bound = nullptr;
     g.cs_pitch = cs_half ? cs_pitch : (cs_pitch > 0 ? cs_pitch : nfd);
     const int ld = (n_th + 31) / 32 * 32;
     if (ld > 512) return -1;
