@@ -420,9 +420,10 @@ def b200_arm(args):
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "iterative solver: every Lanczos step streams the triangle once "
-                        "(bf16 copy, 0.52 MB at N=511, ~18 steps) + one fp32 pass for the "
-                        "Rayleigh quotient = `traffic`; kernel_ms = CUDA events on the launching "
-                        "stream, max over ranks",
+                        "(scaled fp16 copy, 0.52 MB at N=511, ~19 steps + 1 surplus step of the "
+                        "deferred convergence check) + one fp32 pass for the Rayleigh quotient "
+                        "= `traffic`; kernel_ms = CUDA events on the launching stream per step, "
+                        "max over ranks",
                 "kernel_ms": kern}
 
     # ---- strong-scaling leg: fixed 8192-eta grid split over the ranks ----------

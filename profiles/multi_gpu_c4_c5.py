@@ -83,7 +83,8 @@ def main():
 
     # ---------------- C4 ----------------
     def realise(seed):
-        s = Simulation(mb2=2, ns=args.ns, nf=args.nf, dlam=0.25, seed=int(seed), device_rng=True)
+        s = Simulation(mb2=2, ns=args.ns, nf=args.nf, dlam=0.25, seed=int(seed), device_rng=True,
+                       lazy=True)       # w / xyp / xyi stay on the device unless asked for
         d = np.asarray(s.dyn, dtype=np.float64)
         return np.array([d.sum(), (d * d).sum(), float(d[d.shape[0] // 3, d.shape[1] // 5])])
 

@@ -29,7 +29,7 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
 # bench.py kernel ids (sb_profile slots) by kernel-name substring
 IDS = [("thth_eig", "thth_eig"), ("thth_build", "thth_build"), ("row_fft_r2c", "cs_rows"),
-       ("ColALoad", "cs_colA"), ("CsStore", "cs_colB")]
+       ("ColAStore", "cs_colA"), ("CsStore", "cs_colB")]
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
 

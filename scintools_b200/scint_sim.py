@@ -28,7 +28,7 @@ class Simulation():
                  inner=0.001, ns=256, nf=256, dlam=0.25, lamsteps=False,
                  seed=None, nx=None, ny=None, dx=None, dy=None, plot=False,
                  verbose=False, freq=1400, dt=30, mjd=60000, nsub=None,
-                 efield=False, noise=None, device_rng=False, keep_device=False):
+                 efield=False, noise=None, device_rng=False, keep_device=False, lazy=False):
         if plot:
             raise NotImplementedError("plotting is outside the B200 hot path")
         self.mb2 = mb2
@@ -49,6 +49,10 @@ class Simulation():
         self._noise = noise
         self._device_rng = device_rng
         self._keep_device = keep_device
+        # lazy=True (batch production, BASELINE config 4): the big arrays w / xyp (fp64
+        # nx x ny) and xyi stay on the device and are downloaded on first attribute
+        # access; spe / spi / dyn and the scalars are always on the host
+        self._lazy = bool(lazy)
 
         self.set_constants()
         if verbose:
@@ -102,8 +106,19 @@ class Simulation():
         c = 299792458.0
         beta_to_eta = c * 1e6 / ((self.freq * 10 ** 6) ** 2)
         self.betaeta = self.eta / beta_to_eta
-        if not keep_device:
+        if not keep_device and not self._lazy:
             self._d_xyp = None
+
+    def __getattr__(self, name):
+        # only reached when the attribute is not set yet: lazy download of the big arrays
+        src = {"w": "_d_w", "xyp": "_d_xyp", "xyi": "_d_xyi"}.get(name)
+        if src is not None and self.__dict__.get("_lazy") and self.__dict__.get(src) is not None:
+            val = self.__dict__[src].cpu().numpy().astype(np.float64)
+            self.__dict__[name] = val
+            if not (name == "xyp" and self.__dict__.get("_keep_device")):
+                self.__dict__[src] = None
+            return val
+        raise AttributeError(name)
 
     def set_constants(self):
         """scint_sim.py:137-167 (host scalars)."""
@@ -151,8 +166,11 @@ class Simulation():
                                           D.ptr(n2), seed, d_xyp.data_ptr(),
                                           D.stream_ptr()))
         self._d_xyp = d_xyp
-        self.w = d_w.cpu().numpy()
-        self.xyp = d_xyp.cpu().numpy()
+        if self._lazy:
+            self._d_w = d_w
+        else:
+            self.w = d_w.cpu().numpy()
+            self.xyp = d_xyp.cpu().numpy()
 
     def _scales(self):
         out = np.empty(self.nf, dtype=np.float64)
@@ -178,7 +196,10 @@ class Simulation():
         a = d_spe.cpu().numpy()
         spe_t = (a[..., 0] + 1j * a[..., 1]).astype(np.csingle)   # [nf][nx]
         self.spe = np.ascontiguousarray(spe_t.T)                  # [nx][nf]
-        self.xyi = d_xyi.cpu().numpy().astype(np.float64)
+        if self._lazy:
+            self._d_xyi = d_xyi
+        else:
+            self.xyi = d_xyi.cpu().numpy().astype(np.float64)
 
     def get_dynspec(self):
         """scint_sim.py:238-252."""
@@ -197,4 +218,8 @@ class Simulation():
         p = np.fft.fft(np.multiply(self.spe, np.blackman(self.nf)), 2 * self.nf)
         p = np.real(p * np.conj(p))
         self.pulsewin = np.transpose(np.roll(p, self.nf))
-        self.dm = self.xyp[:, int(self.ny / 2)] * self.dlam / np.pi
+        if self._lazy and "xyp" not in self.__dict__:
+            col = self._d_xyp[:, int(self.ny / 2)].cpu().numpy()   # one column, not 8 n^2 bytes
+        else:
+            col = self.xyp[:, int(self.ny / 2)]
+        self.dm = col * self.dlam / np.pi

@@ -157,6 +157,25 @@ class _Geom:
         return ctypes.byref(self.g)
 
 
+_pinned_pool = {}
+
+
+def _pinned_take(neta):
+    """Four pinned host buffers (eigs f64, status / nred / iters i32) of length neta."""
+    import torch
+    free = _pinned_pool.setdefault(neta, [])
+    if free:
+        return free.pop()
+    return [torch.empty((neta,), dtype=dt, pin_memory=True)
+            for dt in (torch.float64, torch.int32, torch.int32, torch.int32)]
+
+
+def _pinned_give(bufs):
+    free = _pinned_pool.setdefault(int(bufs[0].shape[0]), [])
+    if len(free) < 4:
+        free.append(bufs)
+
+
 class _SweepJob:
     """An eta sweep in flight on the current stream: device outputs, pinned host
     mirrors (asynchronous device->host copies) and the event that marks them
@@ -176,8 +195,9 @@ class _SweepJob:
                                          self.iters.data_ptr(), D.stream_ptr()))
         self.host = None
         if pinned:
-            self.host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                         for t in (self.eigs, self.status, self.nred, self.iters)]
+            # pinned read-back buffers come from a small pool: a fresh cudaHostAlloc per
+            # job would synchronise the device and serialise the pipeline
+            self.host = _pinned_take(neta)
             for h, t in zip(self.host, (self.eigs, self.status, self.nred, self.iters)):
                 h.copy_(t, non_blocking=True)
             self.event = torch.cuda.Event()
@@ -187,6 +207,8 @@ class _SweepJob:
         if self.host is not None:
             self.event.synchronize()
             out, st, nred, iters = [h.numpy().copy() for h in self.host]
+            _pinned_give(self.host)
+            self.host = None
         else:
             out = self.eigs.cpu().numpy()
             st = self.status.cpu().numpy()

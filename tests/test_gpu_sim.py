@@ -80,3 +80,20 @@ def test_simulation_feeds_dynspec(Sim):
     ds.calc_sspec()
     assert ds.sspec.shape == (64, 256) and np.isfinite(ds.sspec).any()
     assert ds.eta == s.eta
+
+
+def test_simulation_lazy_matches_eager(sb):
+    """lazy=True keeps w / xyp / xyi on the device until they are asked for (batch
+    production); every attribute equals the eager object's."""
+    from scintools_b200.scint_sim import Simulation
+    kw = dict(mb2=2, ns=128, nf=6, dlam=0.25, seed=7)
+    a = Simulation(**kw)
+    b = Simulation(lazy=True, **kw)
+    assert "xyp" not in b.__dict__ and "w" not in b.__dict__ and "xyi" not in b.__dict__
+    for name in ("dyn", "spe", "spi", "dm", "pulsewin"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    for name in ("w", "xyp", "xyi"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+        assert name in b.__dict__
+    with pytest.raises(AttributeError):
+        b.no_such_attribute
