@@ -88,7 +88,32 @@ __device__ inline void lanczos_check(LanczosShared& S, int m, double tol, double
     double lo = (m == 1) ? S.alpha[0] - fabs(S.alpha[0]) * 1e-9 - 1e-290 : S.lo;
     if (lo > hi) lo = hi - fabs(hi) - 1.0;
     sturm_multisect(S, m, m, lo, hi, 6);
-    const double theta = hi;
+    // Polish the upper bracket end to fp64 accuracy: Newton on p_m(x) = det(T_m - x) from
+    // above the largest root converges monotonically and quadratically (two steps from a
+    // 1e-9 bracket).  The residual estimate below is only as good as the shift is close to
+    // the Ritz value: with the raw 1e-9 offset it bottoms out near 3e-5 |theta| (and grows
+    // with m), which starved every caller that asks for less (herm_eigvec: 1e-7).
+    double theta = hi;
+    if (lane == 0 && m >= 2) {
+        double x = hi;
+        for (int nit = 0; nit < 3; ++nit) {
+            double p0 = 1.0, p1 = S.alpha[0] - x, d0 = 0.0, d1 = -1.0;
+            for (int i = 1; i < m; ++i) {
+                const double a = S.alpha[i] - x, b2 = S.beta2[i];
+                const double p2 = a * p1 - b2 * p0;
+                const double d2 = a * d1 - p1 - b2 * d0;
+                p0 = p1; p1 = p2; d0 = d1; d1 = d2;
+                const double aq = fmax(fabs(p1), fabs(d1));
+                if (aq > 1e140) { p0 *= 1e-140; p1 *= 1e-140; d0 *= 1e-140; d1 *= 1e-140; }
+                else if (aq < 1e-140 && aq > 0.0) { p0 *= 1e140; p1 *= 1e140; d0 *= 1e140; d1 *= 1e140; }
+            }
+            const double step = (d1 != 0.0) ? p1 / d1 : 0.0;
+            if (!(step > 0.0) || !(x - step >= lo)) break;     // not above the root any more
+            x -= step;
+        }
+        theta = x;
+    }
+    theta = __shfl_sync(0xffffffffu, theta, 0);
     // ratios l_i at sigma = theta: lanes in parallel, then a product chain
     double res = 0.0;
     if (lane == 0) {
@@ -109,12 +134,14 @@ __device__ inline void lanczos_check(LanczosShared& S, int m, double tol, double
             q1 = q2;
         }
         double z = 1.0, nrm = 1.0;
+        bool bad = false;
         for (int i = m - 2; i >= 0; --i) {
             z = -S.piv[i] * z;
             nrm += z * z;
-            if (!(nrm < 1e200)) break;
+            if (!(nrm < 1e200)) { bad = true; break; }
         }
-        res = bnew * rsqrt(nrm);
+        // numerical trouble must never read as "converged": no estimate -> keep iterating
+        res = bad ? DBL_MAX : bnew * rsqrt(nrm);
     }
     res = __shfl_sync(0xffffffffu, res, 0);
     bool done = (res <= tol * fabs(theta)) || !(bnew > 1e-30 * fabs(theta));

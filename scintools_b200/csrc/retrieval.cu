@@ -304,9 +304,9 @@ herm_eigvec_kernel(const float2* __restrict__ A, int n, int ld, float2* __restri
     if (tid == 0) {
         *w_out = S.theta;
         info[0] = m;
-        // the requested residual (1e-7 by default) sits at the fp32 rounding floor and may
-        // never be met; a residual <= 2e-6 |theta| at the iteration cap is a converged pair
-        // for every consumer (eigenvalue error ~ res^2 / gap), anything worse is flagged
+        // the requested residual (1e-7 by default) is close to the fp32 rounding floor; a
+        // residual <= 2e-6 |theta| at the iteration cap is still a converged pair for every
+        // consumer (eigenvalue error ~ res^2 / gap), anything worse is flagged
         info[1] = (S.done || S.res <= 2e-6 * fabs(S.theta)) ? 0 : 8;
     }
 }

@@ -13,6 +13,16 @@ Everything outside that path (file I/O, cleaning, plotting, arc fitting,
 lmfit models) is deliberately not here: use the reference for those and hand
 the arrays over with ``BasicDyn`` exactly as the reference's tutorials do.
 Units: times in s, freqs in MHz, eta in s^3, edges in mHz, tau in us.
+
+Also here: scale_dyn('lambda') (dynspec.py:3926-3957 -> sb_scale_dyn_lambda_f32),
+thetatheta_chunks / calc_wavefield / gerchberg_saxton (:1765-1896), and, through
+``arcfit.ArcFitMixin``, norm_sspec / fit_arc (:1920-2183, :970-1346).
+
+Provenance: ``prep_thetatheta`` is the reference's dynspec.py:1348-1537 with the
+astropy units stripped, line for line (host scalar bookkeeping that SURVEY.md a11
+keeps in Python; identical attributes are the contract).  The chunk loops of
+``fit_thetatheta`` / ``thetatheta_chunks`` follow :1680-1712 / :1790-1828 the same
+way.  Restated reference glue, not new design.
 """
 from copy import deepcopy as cp
 

@@ -13,6 +13,13 @@ drawn on the host exactly as the reference does (scint_sim.py:173,201-202) and
 uploaded.  ``device_rng=True`` draws statistically equivalent Gaussian noise
 on the GPU instead (counter-based Philox; no host pass, not the same stream).
 Explicit fields can be passed as ``noise=(re, im)``.
+
+Provenance: the scalar bookkeeping -- ``set_constants`` (scint_sim.py:137-167),
+``get_dynspec`` / ``get_pulse`` (:238-274) and the unit / axis tail of ``__init__``
+(:81-133) -- follows the reference LINE BY LINE (same expressions, comments
+dropped), because the drop-in contract is "identical attributes" and SURVEY.md
+a12 / a15 keep this glue in Python.  It is restated reference code, not new design;
+what is new here is everything that touches the device.
 """
 import numpy as np
 import scipy.constants as sc

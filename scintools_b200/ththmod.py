@@ -15,6 +15,12 @@ Same function names, argument order and failure behaviour as the reference
 ``CS`` may be a numpy array (uploaded on every call, like the reference's
 per-call semantics) or a ``DeviceCS`` that keeps the spectrum resident.
 There is no CPU fallback.
+
+Provenance: ``peak_fit`` (ththmod.py:813-859), ``mask_func`` / ``mosaic``
+(:1478-1554) and ``min_edges`` (:1671-1705) are the reference's host code with
+the units stripped, line for line -- sequential numpy / scipy glue that stays
+on the host in both implementations and must give identical numbers.  Restated
+reference code, not new design.
 """
 import ctypes
 

@@ -90,7 +90,7 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
             emu::run_block(emu::Dim3{(unsigned)EB_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
                            emu::Dim3{(unsigned)neta, 1, 1}, [&]() {
                                thth_eig_half_kernel<true>(M.data(), Mb.data(), ld, nred, 0, eigs, status,
-                                                    iters, tol, 2e-7, mixed >= 2 ? 0.0 : 2e-3,
+                                                    iters, tol, 2e-7, 1e-6, mixed >= 2 ? 0.0 : 1e-3,
                                                     max_iter, gbasis.data());
                            });
         }
@@ -143,7 +143,7 @@ extern "C" int emu_eig_triangles(const float* Mf, int ld, const int* nred, int n
             emu::run_block(emu::Dim3{(unsigned)EB_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
                            emu::Dim3{(unsigned)nb, 1, 1}, [&]() {
                                thth_eig_half_kernel<true>(M, Mb.data(), ld, nred, 0, eigs, status, iters,
-                                                          tol, 2e-7, 1e-3, max_iter, gbasis.data());
+                                                          tol, 2e-7, 1e-6, 1e-3, max_iter, gbasis.data());
                            });
         else
             emu::run_block(emu::Dim3{256, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
