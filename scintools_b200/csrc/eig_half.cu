@@ -80,17 +80,122 @@ __device__ __forceinline__ float2 unpack_f16x2(const unsigned p) {
     return __half22float2(h);
 }
 
+// two floats -> packed fp16 pair (first in the low half), round to nearest even
+__device__ __forceinline__ unsigned pack_h2(const float lo, const float hi) {
+#ifdef SB_HOST_EMU
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return (unsigned)h.x | ((unsigned)h.y << 16);
+#else
+    unsigned r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+#endif
+}
+
+// ---- tensor-core mat-vec (EB_MODE_TC) -------------------------------------
+// The fp16 copy is then stored in 512-byte BLOCKS of 16 rows x 8 complex columns
+// (thth_build_kernel<2>): block (I, G) = rows 16 I .., columns 8 G .., at byte
+// ((I * ld / 8 + G) * 512); a block row is [re x 8 | im x 8] (planar, 32 bytes).
+// One block is one m16n8k16 A operand (k < 8: re, k >= 8: im of column k - 8)
+// and, read through ldmatrix.trans, the A operand of the transposed product.
+constexpr int EB_TC_NST = 8;          // 512-byte stages per warp (the other 4 KB: column sums)
+// row blocks owned by each warp (5-bit fields, count in bits 25+): warp 0 gets half a
+// share because it also runs the deferred convergence check; block I has 64 - 2 I
+// blocks of columns, the shares are 70 | 144 142 140 140 140 140 140
+#define EB_OWN5(a, b, c, d, e, cnt) \
+    ((unsigned)(a) | (unsigned)(b) << 5 | (unsigned)(c) << 10 | (unsigned)(d) << 15 | \
+     (unsigned)(e) << 20 | (unsigned)(cnt) << 25)
+__device__ __forceinline__ unsigned eb_own_pack(const int warp) {
+    switch (warp) {
+        case 0: return EB_OWN5(14, 15, 0, 0, 0, 2);
+        case 1: return EB_OWN5(0, 13, 16, 29, 30, 5);
+        case 2: return EB_OWN5(1, 12, 17, 28, 31, 5);
+        case 3: return EB_OWN5(2, 11, 18, 27, 0, 4);
+        case 4: return EB_OWN5(3, 10, 19, 26, 0, 4);
+        case 5: return EB_OWN5(4, 9, 20, 25, 0, 4);
+        case 6: return EB_OWN5(5, 8, 21, 24, 0, 4);
+        default: return EB_OWN5(6, 7, 22, 23, 0, 4);
+    }
+}
+
+#ifdef SB_HOST_EMU
+// warp-collective fragment loads / MMA through the emulator's lane exchange
+inline void ldsm_x4(unsigned (&r)[4], smem_addr a) {
+    unsigned long long all[32];
+    emu::warp_gather((unsigned long long)(uintptr_t)a, all);
+    const int lane = (int)(threadIdx.x & 31), g = lane >> 2, t = lane & 3;
+    for (int i = 0; i < 4; ++i)
+        std::memcpy(&r[i], (const unsigned char*)(uintptr_t)all[8 * i + g] + 4 * t, 4);
+}
+inline void ldsm_x4_t(unsigned (&r)[4], smem_addr a) {
+    unsigned long long all[32];
+    emu::warp_gather((unsigned long long)(uintptr_t)a, all);
+    const int lane = (int)(threadIdx.x & 31), g = lane >> 2, t = lane & 3;
+    for (int i = 0; i < 4; ++i) {
+        unsigned short lo, hi;
+        std::memcpy(&lo, (const unsigned char*)(uintptr_t)all[8 * i + 2 * t] + 2 * g, 2);
+        std::memcpy(&hi, (const unsigned char*)(uintptr_t)all[8 * i + 2 * t + 1] + 2 * g, 2);
+        r[i] = (unsigned)lo | ((unsigned)hi << 16);
+    }
+}
+inline void mma16816(float (&d)[4], const unsigned (&a)[4], const unsigned b0, const unsigned b1) {
+    unsigned long long A01[32], A23[32], Bq[32];
+    emu::warp_gather((unsigned long long)a[0] | ((unsigned long long)a[1] << 32), A01);
+    emu::warp_gather((unsigned long long)a[2] | ((unsigned long long)a[3] << 32), A23);
+    emu::warp_gather((unsigned long long)b0 | ((unsigned long long)b1 << 32), Bq);
+    const int lane = (int)(threadIdx.x & 31), g = lane >> 2, t = lane & 3;
+    auto half_of = [](unsigned w, int hi) { return emu_h2f((unsigned short)(hi ? w >> 16 : w & 0xffffu)); };
+    auto Aat = [&](int row, int k) {            // fragment layout of mma.m16n8k16 (row-major A)
+        const int ln = (row & 7) * 4 + ((k & 7) >> 1);
+        const unsigned long long w = (k < 8) ? A01[ln] : A23[ln];
+        return half_of((unsigned)(row < 8 ? w : w >> 32), k & 1);
+    };
+    auto Bat = [&](int k, int n) {
+        const unsigned long long w = Bq[n * 4 + ((k & 7) >> 1)];
+        return half_of((unsigned)(k < 8 ? w : w >> 32), k & 1);
+    };
+    for (int q = 0; q < 4; ++q) {
+        const int row = g + 8 * (q >> 1), col = 2 * t + (q & 1);
+        float acc = d[q];
+        for (int k = 0; k < 16; ++k) acc += Aat(row, k) * Bat(k, col);
+        d[q] = acc;
+    }
+}
+#else
+__device__ __forceinline__ void ldsm_x4(unsigned (&r)[4], const smem_addr a) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(unsigned (&r)[4], const smem_addr a) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
+}
+// d += A (16x16 fp16, row major) * B (16x8 fp16, column major), fp32 accumulate
+__device__ __forceinline__ void mma16816(float (&d)[4], const unsigned (&a)[4], const unsigned b0,
+                                         const unsigned b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+        "{%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+#endif
+
+enum { EB_MODE_BULK = 0, EB_MODE_CPA = 1, EB_MODE_TC = 2 };
+
 // shared-memory bytes of one CTA (host + device agree through this)
-__host__ __device__ inline size_t eig_half_smem(int ld) {
+__host__ __device__ inline size_t eig_half_smem(int ld, int mode = EB_MODE_CPA) {
     return sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2) +
-           (size_t)EB_NW * EB_NST * 4096 + (size_t)EB_NW * EB_NST * 8 + 16;
+           (size_t)EB_NW * EB_NST * 4096 + (size_t)EB_NW * EB_NST * 8 + 16 +
+           (mode == EB_MODE_TC ? 4 * (size_t)(ld / 2) * 8 : 0);
 }
 
 // CPA: the bf16 rows are fetched with per-lane cp.async (LDGSTS) copies -- every lane
 // copies exactly the 16-byte chunks it will read itself, so a wait_group is all the
 // synchronisation a stage needs -- instead of cp.async.bulk + mbarrier (one lane issues,
 // ~70 instructions per row pair of address / election bookkeeping).
-template <bool CPA>
+// MODE = EB_MODE_TC: the mat-vec runs on the tensor cores (mma.sync m16n8k16, fp16 x fp16
+// -> fp32): see matvec_t below.
+template <int MODE>
 __global__ void __launch_bounds__(EB_THREADS, 2)
 thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restrict__ Mbbase,
                      int ld, const int* __restrict__ nred, int eta0,
@@ -98,6 +203,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
                      int* __restrict__ iters, double tol, double etol, double etol_h, double rtol_r,
                      int max_iter, float2* __restrict__ gbasis) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr bool CPA = MODE != EB_MODE_BULK;
     LanczosShared& S = *reinterpret_cast<LanczosShared*>(smem_raw);
     float2* v = reinterpret_cast<float2*>(smem_raw + sizeof(LanczosShared));
     float2* vp = v + ld;
@@ -106,6 +212,9 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     unsigned char* ring = reinterpret_cast<unsigned char*>(u + ld);     // [NW][NST][4096]
     float2* part = reinterpret_cast<float2*>(ring);                      // [NW][512] scratch (aliases the ring)
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ring + (size_t)EB_NW * EB_NST * 4096);
+    // EB_MODE_TC: fp16 operand forms of the vector, [4 variants][ld / 2] x {b0, b1}
+    uint2* P = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(mbar) +
+                                        (size_t)EB_NW * EB_NST * 8 + 16);
     const int tid = threadIdx.x, lane = tid & 31;
     // warp index through a shuffle: tells the compiler it is warp-uniform, so the
     // bulk-copy addresses below live in uniform registers (no per-lane election loops)
@@ -329,6 +438,141 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     };
 
     // ------------------------------------------------------------------
+    // fp16 mat-vec on the TENSOR CORES (EB_MODE_TC).  The triangle is a set of
+    // 16-row x 8-column blocks (I, G), G >= 2 I; for every block
+    //   rows:    D1[r][n] += sum_k A[r][k] B_G[k][n]     A = the block, k = (re | im) x column
+    //   columns: D2[m][n] += sum_r A[r][m] B_I[r][n]     A^T through ldmatrix.trans
+    // with the vector in the n-columns of B as fp16 hi + 2^-11 lo pairs (n = 0 / 1: real /
+    // imaginary part of the product from the hi halves, n = 2 / 3 from the lo halves;
+    // 22 mantissa bits, the fp32 accumulators do the rest).  A warp walks its row blocks
+    // column-group by column-group, so the column accumulators D2 of group G live in
+    // registers until the warp is through with G, the row accumulators D1 for the whole
+    // mat-vec: 2 ldmatrix + 2 mma per 128 matrix elements instead of 32 FFMA2 + 16
+    // converts.  Blocks arrive through an 8-stage ring of 512-byte cp.async copies per
+    // warp (one 16-byte chunk per lane, XOR-swizzled so that both ldmatrix forms are
+    // conflict free); the upper 4 KB of the warp's ring slice collect its column sums.
+    // ------------------------------------------------------------------
+    auto matvec_t = [&](int check_m, double et) {
+        const int ldh = ld >> 1;
+        for (int c = tid; c < ld; c += EB_THREADS) w[c] = make_float2(0.f, 0.f);
+        for (int i = tid; i < ldh; i += EB_THREADS) {
+            const float4 x = *reinterpret_cast<const float4*>(v + 2 * i);   // two vector elements
+            const unsigned xr = pack_h2(x.x, x.z), xi = pack_h2(x.y, x.w);
+            const float2 hr = unpack_f16x2(xr), hi = unpack_f16x2(xi);
+            const unsigned lr = pack_h2((x.x - hr.x) * 2048.f, (x.z - hr.y) * 2048.f);
+            const unsigned li = pack_h2((x.y - hi.x) * 2048.f, (x.w - hi.y) * 2048.f);
+            P[i] = make_uint2(xr, xi ^ 0x80008000u);             // n = 0: re = Mr xr - Mi xi
+            P[ldh + i] = make_uint2(xi, xr);                     // n = 1: im = Mr xi + Mi xr
+            P[2 * ldh + i] = make_uint2(lr, li ^ 0x80008000u);   // n = 2 / 3: the same from the lo halves
+            P[3 * ldh + i] = make_uint2(li, lr);
+        }
+        __syncthreads();
+        const int g = lane >> 2, t = lane & 3;
+        const int NI = (n + 14) >> 4;          // row blocks with stored elements (rows 0 .. n-2)
+        const int NG = (n + 7) >> 3;           // column groups
+        const int NGL = ld >> 3;               // groups per row block in memory
+        const unsigned own = eb_own_pack(warp);
+        const int cnt = (int)(own >> 25);
+        int ownI[5];
+        unsigned tb0[5], tb1[5];
+        float acc[5][4];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int I = (int)((own >> (5 * j)) & 31u);
+            ownI[j] = (j < cnt && I < NI) ? I : 1 << 20;      // never reached by 2 I <= G
+            tb0[j] = 0u;
+            tb1[j] = 0u;
+            if (ownI[j] < NI && g < 4) {
+                tb0[j] = P[g * ldh + 8 * I + t].x;
+                tb1[j] = P[g * ldh + 8 * I + t + 4].x;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
+        }
+        unsigned char* wring = ring + (size_t)warp * EB_NST * 4096;
+        float2* mypart = reinterpret_cast<float2*>(wring + 4096);           // [512] column sums
+        const smem_addr sbase = smem_addr_of(wring);
+        // lane's chunk of a block: row lane / 2, half lane & 1, swizzled by row bit 2
+        const int crow = lane >> 1;
+        const smem_addr cdst = sbase + crow * 32 + (((lane & 1) ^ ((crow >> 2) & 1)) << 4);
+        const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(Mb) + lane * 16;
+        const int mi = lane >> 3;
+        const int arow = (lane & 7) + 8 * (mi & 1), trow = (lane & 7) + 8 * (mi >> 1);
+        const smem_addr aoff = sbase + arow * 32 + ((((mi >> 1) & 1) ^ ((arow >> 2) & 1)) << 4);
+        const smem_addr toff = sbase + trow * 32 + (((mi & 1) ^ ((trow >> 2) & 1)) << 4);
+        // producer cursor over this warp's blocks in consumption order (G major)
+        int pG = 0, pj = -1, pk = 0;
+        auto fetch_next = [&]() {
+            bool found = false;
+            int I = 0;
+            while (pG < NG) {
+                if (++pj >= cnt) { pj = 0; ++pG; if (pG >= NG) break; }
+                I = (int)((own >> (5 * pj)) & 31u);
+                if (I < NI && 2 * I <= pG) { found = true; break; }
+            }
+            if (found)
+                cp_async16_s(cdst + (pk % EB_TC_NST) * 512,
+                             gsrc + ((size_t)(I * NGL + pG) << 9));
+            ++pk;
+            cp_async_commit();
+        };
+        for (int k = 0; k < EB_TC_NST - 1; ++k) fetch_next();
+        if (check_m > 0 && warp == 0) lanczos_check(S, check_m, tol, et);
+        const float lo_scale = 1.f / 2048.f;
+        int k = 0;
+        for (int G = 0; G < NG; ++G) {
+            float tacc[4] = {0.f, 0.f, 0.f, 0.f};
+            uint2 bq = make_uint2(0u, 0u);
+            if (g < 4) bq = P[g * ldh + 4 * G + t];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                if (2 * ownI[j] > G) continue;                   // warp-uniform
+                cp_async_wait<EB_TC_NST - 2>();                  // this lane's chunk of block k
+                __syncwarp();                                    // ... and everybody else's
+                unsigned a[4], at[4];
+                const int st = (k % EB_TC_NST) * 512;
+                ldsm_x4(a, aoff + st);
+                ldsm_x4_t(at, toff + st);
+                fetch_next();        // into the stage block k-1 was read from (before the syncwarp)
+                mma16816(acc[j], a, bq.x, bq.y);
+                mma16816(tacc, at, tb0[j], tb1[j]);
+                ++k;
+            }
+            // column sums of group G: conj(A) v = (Mr xr + Mi xi) + i (Mr xi - Mi xr)
+            float yr = tacc[0] + tacc[3], yi = tacc[1] - tacc[2];
+            const float lr = __shfl_xor_sync(0xffffffffu, yr, 1), li = __shfl_xor_sync(0xffffffffu, yi, 1);
+            if (t == 0) mypart[8 * G + g] = make_float2(fmaf(lr, lo_scale, yr), fmaf(li, lo_scale, yi));
+        }
+        cp_async_wait<0>();                    // (only empty groups are left)
+        // row sums of the owned row blocks
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            float l0 = __shfl_xor_sync(0xffffffffu, acc[j][0], 1);
+            float l1 = __shfl_xor_sync(0xffffffffu, acc[j][1], 1);
+            float l2 = __shfl_xor_sync(0xffffffffu, acc[j][2], 1);
+            float l3 = __shfl_xor_sync(0xffffffffu, acc[j][3], 1);
+            if (ownI[j] < NI && t == 0) {
+                w[16 * ownI[j] + g] = make_float2(fmaf(l0, lo_scale, acc[j][0]), fmaf(l1, lo_scale, acc[j][1]));
+                w[16 * ownI[j] + g + 8] = make_float2(fmaf(l2, lo_scale, acc[j][2]), fmaf(l3, lo_scale, acc[j][3]));
+            }
+        }
+        __syncthreads();
+        for (int c = tid; c < ld; c += EB_THREADS) {
+            float sx = 0.f, sy = 0.f;
+            if (c < 8 * NG) {
+#pragma unroll
+                for (int kk = 0; kk < EB_NW; ++kk) {
+                    const float2 q = reinterpret_cast<const float2*>(ring + (size_t)kk * EB_NST * 4096 + 4096)[c];
+                    sx += q.x;
+                    sy += q.y;
+                }
+            }
+            u[c] = make_float2(sx, sy);
+        }
+        __syncthreads();
+    };
+
+    // ------------------------------------------------------------------
     // fp32 mat-vec (final Rayleigh quotient, fp32 continuation): one 4 KB row
     // per stage, generic masks.  Stale fp16 words read as fp32 are only ever
     // multiplied into columns that are discarded; the ring is re-zeroed afterwards
@@ -474,7 +718,8 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             if (it >= EB_SLOTS) return false;
             for (int c = tid; c < ld; c += EB_THREADS) basis[(size_t)it * ld + c] = v[c];
             const bool chk = it >= 1 && it >= S.next_check;
-            matvec_b(chk ? it : 0, et);
+            if (MODE == EB_MODE_TC) matvec_t(chk ? it : 0, et);
+            else matvec_b(chk ? it : 0, et);
             ++mv;
             double alpha, beta;
             step_scalars(it, beta_prev, alpha, beta);
@@ -641,10 +886,9 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
 // d_Mb: the scaled fp16 copy of d_M written by thth_build_kernel<true>.
 int eig_half_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* d_nred, int e0,
                     int nb, double* d_eigs, int* d_status, int* d_iters, double tol, double etol,
-                    int max_iter, cudaStream_t st) {
+                    int max_iter, bool tensor, cudaStream_t st) {
     float2* d_basis = (float2*)workspace(7, (size_t)nb * EB_SLOTS * ld * sizeof(float2));
     if (!d_basis) return SB_ERR_NOMEM;
-    const size_t smem = eig_half_smem(ld);
     double rtol_r = 1e-3;
     if (const char* ev = getenv("SB_EIG_RTOL_R")) rtol_r = atof(ev);
     // stopping rule of the fp16 phase: res^2 <= etol_h * theta * gap.  Its Ritz vector only
@@ -654,17 +898,20 @@ int eig_half_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* 
     double etol_h = 1e-6;
     if (const char* ev = getenv("SB_EIG_ETOL_B")) etol_h = atof(ev);
     static const bool bulk = getenv("SB_EIG_BULK") != nullptr;   // A/B: cp.async.bulk row fetch
-    if (bulk) {
-        SB_CUDA(cudaFuncSetAttribute(thth_eig_half_kernel<false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        thth_eig_half_kernel<false><<<nb, EB_THREADS, smem, st>>>(
-            d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, etol, etol_h, rtol_r, max_iter, d_basis);
-    } else {
-        SB_CUDA(cudaFuncSetAttribute(thth_eig_half_kernel<true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        thth_eig_half_kernel<true><<<nb, EB_THREADS, smem, st>>>(
-            d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, etol, etol_h, rtol_r, max_iter, d_basis);
-    }
+    const int mode = tensor ? EB_MODE_TC : (bulk ? EB_MODE_BULK : EB_MODE_CPA);
+    const size_t smem = eig_half_smem(ld, mode);
+#define SB_EIG_HALF_LAUNCH(MODE)                                                                  \
+    do {                                                                                          \
+        SB_CUDA(cudaFuncSetAttribute(thth_eig_half_kernel<MODE>,                                  \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        thth_eig_half_kernel<MODE><<<nb, EB_THREADS, smem, st>>>(                                 \
+            d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, etol, etol_h, rtol_r,      \
+            max_iter, d_basis);                                                                   \
+    } while (0)
+    if (mode == EB_MODE_TC) SB_EIG_HALF_LAUNCH(EB_MODE_TC);
+    else if (mode == EB_MODE_BULK) SB_EIG_HALF_LAUNCH(EB_MODE_BULK);
+    else SB_EIG_HALF_LAUNCH(EB_MODE_CPA);
+#undef SB_EIG_HALF_LAUNCH
     SB_LAUNCH_CHECK();
     return 1;
 }

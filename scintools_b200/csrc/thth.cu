@@ -29,7 +29,7 @@ int eig_cluster_launch(const float2* d_M, int ld, int n_max, const int* d_nred, 
 // eig_half.cu: bf16 iteration + fp32 Rayleigh quotient (default for ld <= 512)
 int eig_half_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* d_nred, int e0,
                     int nb, double* d_eigs, int* d_status, int* d_iters, double tol, double etol,
-                    int max_iter, cudaStream_t st);
+                    int max_iter, bool tensor, cudaStream_t st);
 
 #endif  // SB_HOST_EMU
 
@@ -152,7 +152,11 @@ __global__ void cs_absmax_kernel(const float2* __restrict__ cs, long long rows, 
 // L2 / DRAM gathers are in flight per thread: the kernel is bound by the latency of
 // these random 8-byte loads (ncu: long-scoreboard stalls 8.8 per issue with one load in
 // flight), not by its instruction count.
-template <bool PACK, int ROWS, typename OFF>
+// PACK == 2: the fp16 copy in the block layout of eig_half.cu's tensor-core mat-vec:
+// 512-byte blocks of 16 rows x 8 columns, block (I, G) at ((I * ld / 8 + G) * 512) bytes,
+// a block row = [re x 8 | im x 8]; the part of a diagonal block on / below the diagonal
+// is written as zeros (the MMA has no masks).
+template <int PACK, int ROWS, typename OFF>
 __global__ void __launch_bounds__(32 * (32 / ROWS), ROWS == 8 ? 5 : 4)
 thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nbatch,
                   int ld, const int* __restrict__ idx,
@@ -197,7 +201,7 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
         const float seta = sqrtf((float)(2.0 * eta));
         float2* Me = M + (size_t)e * ld * ld;
         float hscale = 1.f;             // power of two: |element| * hscale < 2^15
-        if (PACK) {
+        if (PACK != 0) {
             const float bound = __uint_as_float(*absmax) * seta * sqrtf(span);
             if (bound > 0.f && bound < 3.0e38f) hscale = exp2f(floorf(log2f(32768.f / bound)));
         }
@@ -253,7 +257,16 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
 #pragma unroll
         for (int k = 0; k < ROWS; ++k) {
             const int la = ty + TY * k;
-            if (ta == tb && tx < la) continue;
+            if (ta == tb && tx < la) {
+                if (PACK == 2 && (tx >> 4) == (la >> 4)) {      // inside a diagonal 16 x 16 block
+                    unsigned short* Mh = reinterpret_cast<unsigned short*>(Mb + (size_t)e * ld * ld);
+                    const int a = ta * 32 + la;
+                    const size_t o = ((size_t)(a >> 4) * (ld >> 3) + (b >> 3)) * 256 + (a & 15) * 16 + (b & 7);
+                    Mh[o] = 0;
+                    Mh[o + 8] = 0;
+                }
+                continue;
+            }
             float2 v = make_float2(0.f, 0.f);
             if (col[k] >= 0) {
                 if ((hit >> k) & 1u) {
@@ -272,7 +285,15 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
             }
             const size_t o = (size_t)(ta * 32 + la) * ld + b;
             Me[o] = v;
-            if (PACK) Mb[(size_t)e * ld * ld + o] = pack_f16x2(make_float2(v.x * hscale, v.y * hscale));
+            if (PACK == 1) Mb[(size_t)e * ld * ld + o] = pack_f16x2(make_float2(v.x * hscale, v.y * hscale));
+            if (PACK == 2) {
+                const unsigned h = pack_f16x2(make_float2(v.x * hscale, v.y * hscale));
+                unsigned short* Mh = reinterpret_cast<unsigned short*>(Mb + (size_t)e * ld * ld);
+                const int a = ta * 32 + la;
+                const size_t ob = ((size_t)(a >> 4) * (ld >> 3) + (b >> 3)) * 256 + (a & 15) * 16 + (b & 7);
+                Mh[ob] = (unsigned short)(h & 0xffffu);
+                Mh[ob + 8] = (unsigned short)(h >> 16);
+            }
         }
     }
 }
@@ -425,8 +446,10 @@ thth_eig_kernel(const float2* __restrict__ Mbase, int ld,
                         bool ok = (j > JS) || (c4 >= first4);
                         if (tail) ok = ok && (c4 < ncol4);
                         if (!ok) q = make_float4(0.f, 0.f, 0.f, 0.f);
-                        float4 x = v4[c4];   // in-bounds of the dynamic smem for any ld
-                        if (tail && !ok) x = make_float4(0.f, 0.f, 0.f, 0.f);   // may be junk past ld
+                        // only the live columns are read: past ld the float4 would alias w / the
+                        // other warps' stages (racecheck flags that even though it was discarded)
+                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok) x = v4[c4];
                         rxa = fmaf(q.x, x.x, rxa); rxb = fmaf(-q.y, x.y, rxb);
                         rxa = fmaf(q.z, x.z, rxa); rxb = fmaf(-q.w, x.w, rxb);
                         rya = fmaf(q.x, x.y, rya); ryb = fmaf(q.y, x.x, ryb);
@@ -796,6 +819,9 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
         // slower: 1.54 vs 1.21 ms -- the gather is bound by random DRAM sector reads, not by
         // the number of loads a thread keeps in flight)
         static const int BR = (getenv("SB_BUILD_ROWS") && atoi(getenv("SB_BUILD_ROWS")) == 8) ? 8 : 4;
+        // tensor-core mat-vec of the default solver (block layout of the fp16 copy);
+        // SB_EIG_NO_TC=1: the packed-FMA mat-vec on the row-major copy
+        const bool tensor = mixed && BR == 4 && !getenv("SB_EIG_NO_TC");
         dim3 grid((nb + SB_BUILD_EB - 1) / SB_BUILD_EB, npairs), block(32, 32 / BR);
         prof_begin(PROF_THTH_BUILD, st);
         // 32-bit CS offsets whenever the spectrum has fewer than 2^32 elements
@@ -804,15 +830,18 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
         thth_build_kernel<PACK, ROWS, OFF><<<grid, block, 0, st>>>(g, d_etas, e0, nb, ld, d_idx, \
                                                                    d_nred, d_M, MB, AM, SP)
         if (BR == 8) {
-            if (mixed && small) SB_BUILD_LAUNCH(true, 8, unsigned, d_Mb, d_absmax, span);
-            else if (mixed) SB_BUILD_LAUNCH(true, 8, size_t, d_Mb, d_absmax, span);
-            else if (small) SB_BUILD_LAUNCH(false, 8, unsigned, nullptr, nullptr, 0.f);
-            else SB_BUILD_LAUNCH(false, 8, size_t, nullptr, nullptr, 0.f);
+            if (mixed && small) SB_BUILD_LAUNCH(1, 8, unsigned, d_Mb, d_absmax, span);
+            else if (mixed) SB_BUILD_LAUNCH(1, 8, size_t, d_Mb, d_absmax, span);
+            else if (small) SB_BUILD_LAUNCH(0, 8, unsigned, nullptr, nullptr, 0.f);
+            else SB_BUILD_LAUNCH(0, 8, size_t, nullptr, nullptr, 0.f);
+        } else if (tensor) {
+            if (small) SB_BUILD_LAUNCH(2, 4, unsigned, d_Mb, d_absmax, span);
+            else SB_BUILD_LAUNCH(2, 4, size_t, d_Mb, d_absmax, span);
         } else {
-            if (mixed && small) SB_BUILD_LAUNCH(true, 4, unsigned, d_Mb, d_absmax, span);
-            else if (mixed) SB_BUILD_LAUNCH(true, 4, size_t, d_Mb, d_absmax, span);
-            else if (small) SB_BUILD_LAUNCH(false, 4, unsigned, nullptr, nullptr, 0.f);
-            else SB_BUILD_LAUNCH(false, 4, size_t, nullptr, nullptr, 0.f);
+            if (mixed && small) SB_BUILD_LAUNCH(1, 4, unsigned, d_Mb, d_absmax, span);
+            else if (mixed) SB_BUILD_LAUNCH(1, 4, size_t, d_Mb, d_absmax, span);
+            else if (small) SB_BUILD_LAUNCH(0, 4, unsigned, nullptr, nullptr, 0.f);
+            else SB_BUILD_LAUNCH(0, 4, size_t, nullptr, nullptr, 0.f);
         }
 #undef SB_BUILD_LAUNCH
         prof_end(PROF_THTH_BUILD, st);
@@ -820,7 +849,7 @@ int eta_sweep(const ThthGeom& g, const double* th_host, const double* d_etas,
         prof_begin(PROF_THTH_EIG, st);
         // experimental solvers, each enabled by its own environment variable
         int rc = mixed ? eig_half_launch(d_M, d_Mb, ld, d_nred, e0, nb, d_eigs, d_status,
-                                         d_iters, tol, 2e-7, max_iter, st)
+                                         d_iters, tol, 2e-7, max_iter, tensor, st)
                        : 0;
         if (rc == 0)
             rc = eig_cluster_launch(d_M, ld, g.n, d_nred, e0, nb, d_eigs, d_status, d_iters,

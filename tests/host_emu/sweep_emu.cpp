@@ -72,25 +72,34 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
         for (unsigned by = 0; by < (unsigned)npairs; ++by)
             emu::run_block(emu::Dim3{32, 4, 1}, emu::Dim3{bx, by, 0}, emu::Dim3{gx, (unsigned)npairs, 1},
                            [&]() {
-                               if (mixed)
-                                   thth_build_kernel<true, 8, unsigned>(g, etas, 0, neta, ld, idx.data(), nred,
+                               if (mixed == 3)
+                                   thth_build_kernel<2, 8, unsigned>(g, etas, 0, neta, ld, idx.data(), nred,
+                                                           M.data(), Mb.data(), &absmax_bits, span);
+                               else if (mixed)
+                                   thth_build_kernel<1, 8, unsigned>(g, etas, 0, neta, ld, idx.data(), nred,
                                                            M.data(), Mb.data(), &absmax_bits, span);
                                else
-                                   thth_build_kernel<false, 8, size_t>(g, etas, 0, neta, ld, idx.data(), nred,
+                                   thth_build_kernel<0, 8, size_t>(g, etas, 0, neta, ld, idx.data(), nred,
                                                             M.data(), nullptr, nullptr, 0.f);
                            });
     if (M_out) std::memcpy(M_out, M.data(), M.size() * sizeof(float2));   // [neta][ld][ld] triangle
     if (max_iter <= 0 || max_iter > SB_LANCZOS_MAXIT) max_iter = SB_LANCZOS_MAXIT;
     if (mixed) {
-        // mixed = 1: default thresholds; 2: residual threshold 0 -> every curvature takes
-        // the fp32 continuation from the Ritz vector
+        // mixed = 1: packed-FMA mat-vec, default thresholds; 2: residual threshold 0 -> every
+        // curvature takes the fp32 continuation from the Ritz vector; 3: tensor-core mat-vec
+        // on the block layout (the default on the GPU)
         std::vector<float2> gbasis((size_t)neta * EB_SLOTS * ld);
         for (int e = 0; e < neta; ++e) {
             std::memset(smem_raw, 0xa5, sizeof(smem_raw));     // garbage, like real shared memory
             emu::run_block(emu::Dim3{(unsigned)EB_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
                            emu::Dim3{(unsigned)neta, 1, 1}, [&]() {
-                               thth_eig_half_kernel<true>(M.data(), Mb.data(), ld, nred, 0, eigs, status,
-                                                    iters, tol, 2e-7, 1e-6, mixed >= 2 ? 0.0 : 1e-3,
+                               if (mixed == 3)
+                                   thth_eig_half_kernel<EB_MODE_TC>(M.data(), Mb.data(), ld, nred, 0, eigs,
+                                                    status, iters, tol, 2e-7, 1e-6, 1e-3, max_iter,
+                                                    gbasis.data());
+                               else
+                                   thth_eig_half_kernel<EB_MODE_CPA>(M.data(), Mb.data(), ld, nred, 0, eigs,
+                                                    status, iters, tol, 2e-7, 1e-6, mixed == 2 ? 0.0 : 1e-3,
                                                     max_iter, gbasis.data());
                            });
         }
@@ -133,7 +142,15 @@ extern "C" int emu_eig_triangles(const float* Mf, int ld, const int* nred, int n
                 for (int c = a; c < ld; ++c) {
                     float2 q = M[((size_t)e * ld + a) * ld + c];
                     if (c >= n || c == a) q = make_float2(0.f, 0.f);
-                    Mb[((size_t)e * ld + a) * ld + c] = pack_f16x2(make_float2(q.x * sc, q.y * sc));
+                    const unsigned h = pack_f16x2(make_float2(q.x * sc, q.y * sc));
+                    if (mixed == 3) {       // block layout (zeros elsewhere: Mb starts as zeros)
+                        unsigned short* Mh = reinterpret_cast<unsigned short*>(Mb.data() + (size_t)e * ld * ld);
+                        const size_t ob = ((size_t)(a >> 4) * (ld >> 3) + (c >> 3)) * 256 + (a & 15) * 16 + (c & 7);
+                        Mh[ob] = (unsigned short)(h & 0xffffu);
+                        Mh[ob + 8] = (unsigned short)(h >> 16);
+                    } else {
+                        Mb[((size_t)e * ld + a) * ld + c] = h;
+                    }
                 }
         }
     }
@@ -142,8 +159,12 @@ extern "C" int emu_eig_triangles(const float* Mf, int ld, const int* nred, int n
         if (mixed)
             emu::run_block(emu::Dim3{(unsigned)EB_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
                            emu::Dim3{(unsigned)nb, 1, 1}, [&]() {
-                               thth_eig_half_kernel<true>(M, Mb.data(), ld, nred, 0, eigs, status, iters,
-                                                          tol, 2e-7, 1e-6, 1e-3, max_iter, gbasis.data());
+                               if (mixed == 3)
+                                   thth_eig_half_kernel<EB_MODE_TC>(M, Mb.data(), ld, nred, 0, eigs, status,
+                                                          iters, tol, 2e-7, 1e-6, 1e-3, max_iter, gbasis.data());
+                               else
+                                   thth_eig_half_kernel<EB_MODE_CPA>(M, Mb.data(), ld, nred, 0, eigs, status,
+                                                          iters, tol, 2e-7, 1e-6, 1e-3, max_iter, gbasis.data());
                            });
         else
             emu::run_block(emu::Dim3{256, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},

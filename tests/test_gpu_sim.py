@@ -82,10 +82,10 @@ def test_simulation_feeds_dynspec(Sim):
     assert ds.eta == s.eta
 
 
-def test_simulation_lazy_matches_eager(sb):
+def test_simulation_lazy_matches_eager(Sim):
     """lazy=True keeps w / xyp / xyi on the device until they are asked for (batch
     production); every attribute equals the eager object's."""
-    from scintools_b200.scint_sim import Simulation
+    Simulation = Sim
     kw = dict(mb2=2, ns=128, nf=6, dlam=0.25, seed=7)
     a = Simulation(**kw)
     b = Simulation(lazy=True, **kw)
