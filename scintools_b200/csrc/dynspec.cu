@@ -59,22 +59,76 @@ void twiddle_release() {
 }
 
 // ------------------------------------------------------------------- stats
-// out[0] = sum dyn, out[1] = sum wt*wf*dyn, out[2] = #finite, out[3] = sum finite
-__global__ void dyn_stats_kernel(const float* __restrict__ dyn, long nf, long nt,
-                                 const float* __restrict__ wt,
-                                 const float* __restrict__ wf,
-                                 double* __restrict__ out) {
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    const long total = nf * nt;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long)gridDim.x * blockDim.x) {
-        float v = dyn[i];
-        s0 += v;
-        if (wt) s1 += (double)(wt[i % nt] * wf[i / nt]) * v;
-        if (isfinite(v)) { s2 += 1.0; s3 += v; }
+// Sum over a 1-D CTA (result in thread 0).  One atomic per CTA instead of one per warp: the
+// per-warp fp64 atomics of round 1 all hit one address and serialised in the L2
+// (acf_mid_kernel: 263 k of them, 690 us for a 250 us kernel; dyn_stats_kernel likewise).
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = l < (int)((blockDim.x + 31) >> 5) ? sh[l] : 0.0;
+        r = warp_sum(r);
     }
-    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-    if ((threadIdx.x & 31) == 0) {
+    return r;
+}
+// out[0] = sum dyn, out[1] = sum wt*wf*dyn, out[2] = #finite, out[3] = sum finite
+// Work item = (row, chunk of 256 x 8 columns); a thread keeps two 16-byte loads in
+// flight per item and the items of a block are independent, so the pass streams
+// (the flat one-float-per-iteration loop with i % nt, i / nt ran at 1 TB/s).
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+dyn_stats_kernel(const float* __restrict__ dyn, long nf, long nt,
+                 const float* __restrict__ wt, const float* __restrict__ wf,
+                 double* __restrict__ out) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    const long nchunk = (nt + 2047) / 2048;
+    const long items = nf * nchunk;
+    for (long it = blockIdx.x; it < items; it += gridDim.x) {
+        const long row = it / nchunk;
+        const long t0 = (it - row * nchunk) * 2048;
+        const float* src = dyn + row * nt;
+        const float fw = wt ? wf[row] : 0.f;
+        float v[8], wv[8];
+        bool ok[8];
+        if (VEC) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const long t = t0 + 4 * (threadIdx.x + 256 * h);
+                const bool in = t < nt;                 // nt % 4 == 0: whole groups
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f), ww = q;
+                if (in) {
+                    q = *reinterpret_cast<const float4*>(src + t);
+                    if (wt) ww = *reinterpret_cast<const float4*>(wt + t);
+                }
+                v[4 * h] = q.x; v[4 * h + 1] = q.y; v[4 * h + 2] = q.z; v[4 * h + 3] = q.w;
+                wv[4 * h] = ww.x; wv[4 * h + 1] = ww.y; wv[4 * h + 2] = ww.z; wv[4 * h + 3] = ww.w;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ok[4 * h + i] = in;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long t = t0 + threadIdx.x + 256 * i;
+                ok[i] = t < nt;
+                v[i] = ok[i] ? src[t] : 0.f;
+                wv[i] = (ok[i] && wt) ? wt[t] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (!ok[i]) continue;
+            s0 += v[i];
+            if (wt) s1 += (double)(wv[i] * fw) * v[i];
+            if (isfinite(v[i])) { s2 += 1.0; s3 += v[i]; }
+        }
+    }
+    __shared__ double sh[32];
+    s0 = block_sum(s0, sh); s1 = block_sum(s1, sh); s2 = block_sum(s2, sh); s3 = block_sum(s3, sh);
+    if (threadIdx.x == 0) {
         atomicAdd(out + 0, s0); atomicAdd(out + 1, s1);
         atomicAdd(out + 2, s2); atomicAdd(out + 3, s3);
     }
@@ -260,8 +314,9 @@ acf_mid_kernel(const float2* __restrict__ A, float2* __restrict__ G, long pitch,
         s[idx] = make_float2(p, 0.f);
         if (c < ncols) part += (c == 0 || c == NT / 2) ? (double)p : 2.0 * (double)p;
     }
-    part = warp_sum(part);
-    if ((tid & 31) == 0) atomicAdd(psum, part);
+    __shared__ double sh[32];
+    part = block_sum(part, sh);          // (its barriers also order the power writes)
+    if (tid == 0) atomicAdd(psum + ((blockIdx.x + blockIdx.y) & 31), part);   // 32 slots
     __syncthreads();
     // the DIF output order is exactly the DIT input order
     fft_axis<float, L, +1, true>(s, W, ILog2<W>::value, 1, ti, tid, NTH);
@@ -302,9 +357,7 @@ struct AcfRowLoad {   // output row i <- circular row (i - nf) mod PF
 struct AcfRowStore {
     float* acf;
     int nt, PT;
-    const double* stats;   // [7] = full-plane power sum
-    int normalise;
-    double raw_scale;
+    const float* scale;    // device scalar written by acf_scale_kernel
     __device__ __forceinline__ void one(long row, int t, float x, float sc) const {
         int j;
         if (t < nt) j = t + nt;
@@ -313,11 +366,22 @@ struct AcfRowStore {
         acf[(size_t)row * (2 * nt) + j] = x * sc;
     }
     __device__ __forceinline__ void operator()(long row, int n, float2 z) const {
-        const float sc = (float)(normalise ? 1.0 / stats[7] : raw_scale);
+        const float sc = *scale;
         one(row, 2 * n, z.x, sc);
         one(row, 2 * n + 1, z.y, sc);
     }
 };
+
+// stats[7] = full-plane power sum (32 slots at stats[32..63]); the factor the row pass
+// multiplies with, as a float at stats[8]: 1 / sum (normalise) or the raw ifft2 scale
+__global__ void acf_scale_kernel(double* stats, int normalise, double raw_scale) {
+    double v = stats[32 + threadIdx.x];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) {
+        stats[7] = v;
+        *reinterpret_cast<float*>(stats + 8) = (float)(normalise ? 1.0 / v : raw_scale);
+    }
+}
 
 // ------------------------------------------------------------ host drivers
 int stats_pass(const float* dyn, int nf, int nt, const float* wt, const float* wf,
@@ -448,8 +512,10 @@ static int cols_forward(const float2* H, float2* A, long pitch, int NF, int live
 
 int stats_pass(const float* dyn, int nf, int nt, const float* wt, const float* wf,
                double swt, double swf, double* stats, cudaStream_t st) {
-    SB_CUDA(cudaMemsetAsync(stats, 0, 8 * sizeof(double), st));
-    dyn_stats_kernel<<<num_sms() * 4, 256, 0, st>>>(dyn, nf, nt, wt, wf, stats);
+    SB_CUDA(cudaMemsetAsync(stats, 0, 64 * sizeof(double), st));
+    const bool vec = nt % 4 == 0 && ((uintptr_t)dyn & 15) == 0 && (!wt || ((uintptr_t)wt & 15) == 0);
+    if (vec) dyn_stats_kernel<true><<<num_sms() * 8, 256, 0, st>>>(dyn, nf, nt, wt, wf, stats);
+    else dyn_stats_kernel<false><<<num_sms() * 8, 256, 0, st>>>(dyn, nf, nt, wt, wf, stats);
     SB_LAUNCH_CHECK();
     dyn_stats_final_kernel<<<1, 1, 0, st>>>(stats, (double)nf * nt, swt, swf, wt != nullptr);
     SB_LAUNCH_CHECK();
@@ -615,8 +681,9 @@ __global__ void dyn_l1_kernel(const float* __restrict__ dyn, long total, const d
         const float v = fabsf(dyn[i] - c);
         s += (v == v) ? (double)v : 0.0;
     }
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) atomicAdd(acc, s);
+    __shared__ double sh[32];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) atomicAdd(acc, s);
 }
 __global__ void dyn_l1_final_kernel(const double* acc, const double* stats, int use_mean, float sub,
                                     double npix_padded, float* out) {
@@ -913,8 +980,10 @@ int acf(const float* dyn, int nf, int nt, int subtract_mean, int normalise,
             auto kern = acf_mid_kernel<LL, 32>;
             const size_t smem = (size_t)(LL * 32 + 2 * LL) * sizeof(float2);
             SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, 256, smem, st>>>(A, G, pitch, R1, ncols, PT, twf, twi, wRi, stats + 7);
+            kern<<<grid, 256, smem, st>>>(A, G, pitch, R1, ncols, PT, twf, twi, wRi, stats + 32);
         });
+        SB_LAUNCH_CHECK();
+        acf_scale_kernel<<<1, 32, 0, st>>>(stats, normalise, 1.0 / ((double)PF * (double)PT));
         SB_LAUNCH_CHECK();
     }
     // inverse over k1 -> Q (reuse A)
@@ -932,7 +1001,7 @@ int acf(const float* dyn, int nf, int nt, int subtract_mean, int normalise,
     }
     // rows: half spectrum -> real, crop to lags [-nf, nf) x [-nt, nt)
     AcfRowLoad rl{A, pitch, nf, PF};
-    AcfRowStore rs{out, nt, PT, stats, normalise, 1.0 / ((double)PF * (double)PT)};
+    AcfRowStore rs{out, nt, PT, reinterpret_cast<const float*>(stats + 8)};
     const int N = PT / 2;
     SB_ROW_DISPATCH(N, return (launch_row_c2r<float, N1, N2>(rl, rs, 2L * nf, st)));
     return SB_OK;

@@ -98,7 +98,7 @@ __device__ __forceinline__ unsigned pack_h2(const float lo, const float hi) {
 // ((I * ld / 8 + G) * 512); a block row is [re x 8 | im x 8] (planar, 32 bytes).
 // One block is one m16n8k16 A operand (k < 8: re, k >= 8: im of column k - 8)
 // and, read through ldmatrix.trans, the A operand of the transposed product.
-constexpr int EB_TC_NST = 8;          // 512-byte stages per warp (the other 4 KB: column sums)
+constexpr int EB_TC_NST = 5;          // 1 KB stages (two adjacent blocks) per warp, + 4 KB column sums
 // row blocks owned by each warp (5-bit fields, count in bits 25+): warp 0 gets half a
 // share because it also runs the deferred convergence check; block I has 64 - 2 I
 // blocks of columns, the shares are 70 | 144 142 140 140 140 140 140
@@ -183,9 +183,14 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const unsigned (&a)[4], 
 enum { EB_MODE_BULK = 0, EB_MODE_CPA = 1, EB_MODE_TC = 2 };
 
 // shared-memory bytes of one CTA (host + device agree through this)
+// bytes of a warp's slice of the ring: two 4 KB row stages, or (tensor-core mat-vec)
+// EB_TC_NST 1 KB stages + the 4 KB column-sum buffer (the fp32 pass re-uses the first 8 KB)
+__host__ __device__ constexpr size_t eig_half_slice(int mode) {
+    return mode == EB_MODE_TC ? (size_t)EB_TC_NST * 1024 + 4096 : (size_t)EB_NST * 4096;
+}
 __host__ __device__ inline size_t eig_half_smem(int ld, int mode = EB_MODE_CPA) {
     return sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2) +
-           (size_t)EB_NW * EB_NST * 4096 + (size_t)EB_NW * EB_NST * 8 + 16 +
+           (size_t)EB_NW * eig_half_slice(mode) + (size_t)EB_NW * EB_NST * 8 + 16 +
            (mode == EB_MODE_TC ? 4 * (size_t)(ld / 2) * 8 : 0);
 }
 
@@ -211,7 +216,9 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     float2* u = w + ld;           // column sums
     unsigned char* ring = reinterpret_cast<unsigned char*>(u + ld);     // [NW][NST][4096]
     float2* part = reinterpret_cast<float2*>(ring);                      // [NW][512] scratch (aliases the ring)
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ring + (size_t)EB_NW * EB_NST * 4096);
+    constexpr int WSL = (int)eig_half_slice(MODE);                       // bytes per warp
+    static_assert(WSL >= EB_NST * 4096, "the fp32 pass needs two 4 KB stages per warp");
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ring + (size_t)EB_NW * WSL);
     // EB_MODE_TC: fp16 operand forms of the vector, [4 variants][ld / 2] x {b0, b1}
     uint2* P = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(mbar) +
                                         (size_t)EB_NW * EB_NST * 8 + 16);
@@ -239,7 +246,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     }
     // The ring starts out as zeros: positions a row's copy does not cover keep
     // older (finite) data, which only ever meets vector elements that are zero.
-    for (int i = tid; i < EB_NW * EB_NST * 256; i += EB_THREADS)
+    for (int i = tid; i < EB_NW * WSL / 16; i += EB_THREADS)
         reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
         for (int i = 0; i < EB_NW * EB_NST; ++i) mbar_init(mbar + i, 1);
@@ -249,7 +256,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     __syncthreads();
     const int ncol4 = (n + 1) >> 1;            // fp32 rows: float4 groups = two complex columns
     const int ncolq = ((n + 3) >> 2) << 2;     // fp16 rows are fetched in multiples of 4 columns
-    unsigned char* mystage = ring + (size_t)warp * EB_NST * 4096;
+    unsigned char* mystage = ring + (size_t)warp * WSL;
     unsigned long long* mybar = mbar + EB_NST * warp;
     unsigned phbits = 0;                       // bit s: phase parity of this warp's barrier s
 
@@ -441,128 +448,164 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     // fp16 mat-vec on the TENSOR CORES (EB_MODE_TC).  The triangle is a set of
     // 16-row x 8-column blocks (I, G), G >= 2 I; for every block
     //   rows:    D1[r][n] += sum_k A[r][k] B_G[k][n]     A = the block, k = (re | im) x column
-    //   columns: D2[m][n] += sum_r A[r][m] B_I[r][n]     A^T through ldmatrix.trans
+    //   columns: D2[m][n]  = sum_r A[r][m] B_I[r][n]     A^T through ldmatrix.trans
     // with the vector in the n-columns of B as fp16 hi + 2^-11 lo pairs (n = 0 / 1: real /
     // imaginary part of the product from the hi halves, n = 2 / 3 from the lo halves;
-    // 22 mantissa bits, the fp32 accumulators do the rest).  A warp walks its row blocks
-    // column-group by column-group, so the column accumulators D2 of group G live in
-    // registers until the warp is through with G, the row accumulators D1 for the whole
-    // mat-vec: 2 ldmatrix + 2 mma per 128 matrix elements instead of 32 FFMA2 + 16
-    // converts.  Blocks arrive through an 8-stage ring of 512-byte cp.async copies per
-    // warp (one 16-byte chunk per lane, XOR-swizzled so that both ldmatrix forms are
-    // conflict free); the upper 4 KB of the warp's ring slice collect its column sums.
+    // 22 mantissa bits, the fp32 accumulators do the rest): 2 ldmatrix + 2 mma per 128
+    // matrix elements instead of 32 FFMA2 + 16 converts.
+    // A warp walks its row blocks one after the other and the blocks of a row block left to
+    // right, two adjacent blocks (1 KB, contiguous in memory) per step -- one linear stream
+    // per row block, so the producer cursor is an address increment.  (The first version
+    // walked column-group major to keep the column sums in registers: its cursor search was
+    // 45 % of all instructions executed -- ncu source view, profiles/r2c13_eig_tc_lines.txt --
+    // and the kernel slower than the packed-FMA one.)  The row sums D1 of the current row
+    // block stay in registers; the column sums of every step are added to the warp's private
+    // 4 KB column buffer (one lane per slot, LDS.128 / STS.128: no hazards).  Units arrive
+    // through a ring of EB_TC_NST 1 KB stages per warp (two 16-byte cp.async chunks per lane,
+    // XOR-swizzled so that both ldmatrix forms are conflict free).
     // ------------------------------------------------------------------
     auto matvec_t = [&](int check_m, double et) {
         const int ldh = ld >> 1;
         for (int c = tid; c < ld; c += EB_THREADS) w[c] = make_float2(0.f, 0.f);
+        // operand forms of the vector, [4 variants][ld / 2] x {b0, b1}; the entries of column
+        // groups 2 h and 2 h + 1 are interleaved so that one LDS.128 fetches both: entry
+        // (G, t) at (4 (G >> 1) + t) * 2 + (G & 1)
         for (int i = tid; i < ldh; i += EB_THREADS) {
             const float4 x = *reinterpret_cast<const float4*>(v + 2 * i);   // two vector elements
             const unsigned xr = pack_h2(x.x, x.z), xi = pack_h2(x.y, x.w);
             const float2 hr = unpack_f16x2(xr), hi = unpack_f16x2(xi);
             const unsigned lr = pack_h2((x.x - hr.x) * 2048.f, (x.z - hr.y) * 2048.f);
             const unsigned li = pack_h2((x.y - hi.x) * 2048.f, (x.w - hi.y) * 2048.f);
-            P[i] = make_uint2(xr, xi ^ 0x80008000u);             // n = 0: re = Mr xr - Mi xi
-            P[ldh + i] = make_uint2(xi, xr);                     // n = 1: im = Mr xi + Mi xr
-            P[2 * ldh + i] = make_uint2(lr, li ^ 0x80008000u);   // n = 2 / 3: the same from the lo halves
-            P[3 * ldh + i] = make_uint2(li, lr);
+            const int q = (((i >> 3) << 2) + (i & 3)) * 2 + ((i >> 2) & 1);
+            P[q] = make_uint2(xr, xi ^ 0x80008000u);             // n = 0: re = Mr xr - Mi xi
+            P[ldh + q] = make_uint2(xi, xr);                     // n = 1: im = Mr xi + Mi xr
+            P[2 * ldh + q] = make_uint2(lr, li ^ 0x80008000u);   // n = 2 / 3: the same from the lo halves
+            P[3 * ldh + q] = make_uint2(li, lr);
         }
+        unsigned char* wring = ring + (size_t)warp * WSL;
+        // column sums of this warp: float4 slot (h, g) = {re, im of column 16 h + g, re, im of
+        // column 16 h + 8 + g} at index 8 h + g
+        float4* mypart = reinterpret_cast<float4*>(wring + EB_TC_NST * 1024);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mypart[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
         const int g = lane >> 2, t = lane & 3;
         const int NI = (n + 14) >> 4;          // row blocks with stored elements (rows 0 .. n-2)
-        const int NG = (n + 7) >> 3;           // column groups
+        const int NH = (n + 15) >> 4;          // pairs of column groups (a group past n reads the
+                                               // zeros thth_build_kernel writes up to the tile edge)
         const int NGL = ld >> 3;               // groups per row block in memory
         const unsigned own = eb_own_pack(warp);
         const int cnt = (int)(own >> 25);
-        int ownI[5];
-        unsigned tb0[5], tb1[5];
-        float acc[5][4];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const int I = (int)((own >> (5 * j)) & 31u);
-            ownI[j] = (j < cnt && I < NI) ? I : 1 << 20;      // never reached by 2 I <= G
-            tb0[j] = 0u;
-            tb1[j] = 0u;
-            if (ownI[j] < NI && g < 4) {
-                tb0[j] = P[g * ldh + 8 * I + t].x;
-                tb1[j] = P[g * ldh + 8 * I + t + 4].x;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
-        }
-        unsigned char* wring = ring + (size_t)warp * EB_NST * 4096;
-        float2* mypart = reinterpret_cast<float2*>(wring + 4096);           // [512] column sums
         const smem_addr sbase = smem_addr_of(wring);
         // lane's chunk of a block: row lane / 2, half lane & 1, swizzled by row bit 2
         const int crow = lane >> 1;
-        const smem_addr cdst = sbase + crow * 32 + (((lane & 1) ^ ((crow >> 2) & 1)) << 4);
+        smem_addr cdst = sbase + crow * 32 + (((lane & 1) ^ ((crow >> 2) & 1)) << 4);
         const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(Mb) + lane * 16;
         const int mi = lane >> 3;
         const int arow = (lane & 7) + 8 * (mi & 1), trow = (lane & 7) + 8 * (mi >> 1);
-        const smem_addr aoff = sbase + arow * 32 + ((((mi >> 1) & 1) ^ ((arow >> 2) & 1)) << 4);
-        const smem_addr toff = sbase + trow * 32 + (((mi & 1) ^ ((trow >> 2) & 1)) << 4);
-        // producer cursor over this warp's blocks in consumption order (G major)
-        int pG = 0, pj = -1, pk = 0;
+        smem_addr aoff = sbase + arow * 32 + ((((mi >> 1) & 1) ^ ((arow >> 2) & 1)) << 4);
+        smem_addr toff = sbase + trow * 32 + (((mi & 1) ^ ((trow >> 2) & 1)) << 4);
+#ifndef SB_HOST_EMU
+        // keep the per-lane bases in registers (the compiler re-derived them from the lane
+        // index inside the loop: ~20 of the 80 instructions per step)
+        asm volatile("" : "+r"(cdst), "+r"(aoff), "+r"(toff), "+l"(gsrc));
+#endif
+        constexpr unsigned RING_BYTES = EB_TC_NST * 1024;
+        // producer cursor: row block pj of this warp, prem units (1 KB = blocks (I, 2 h),
+        // (I, 2 h + 1)) left in it, next unit at byte pa of the fp16 copy, next stage at pst
+        int pj = -1, prem = 0;
+        unsigned pa = 0u, pst = 0u;
+        bool pend = false;
         auto fetch_next = [&]() {
-            bool found = false;
-            int I = 0;
-            while (pG < NG) {
-                if (++pj >= cnt) { pj = 0; ++pG; if (pG >= NG) break; }
-                I = (int)((own >> (5 * pj)) & 31u);
-                if (I < NI && 2 * I <= pG) { found = true; break; }
+            if (prem == 0 && !pend) {
+                for (;;) {
+                    if (++pj >= cnt) { pend = true; break; }
+                    const int I = (int)((own >> (5 * pj)) & 31u);
+                    if (I < NI) {                 // (then I < NH: the diagonal unit exists)
+                        prem = NH - I;
+                        pa = (unsigned)(I * NGL + 2 * I) << 9;
+                        break;
+                    }
+                }
             }
-            if (found)
-                cp_async16_s(cdst + (pk % EB_TC_NST) * 512,
-                             gsrc + ((size_t)(I * NGL + pG) << 9));
-            ++pk;
-            cp_async_commit();
+            if (!pend) {
+                cp_async16_s(cdst + pst, gsrc + pa);
+                cp_async16_s(cdst + pst + 512u, gsrc + pa + 512u);
+                pa += 1024u;
+                --prem;
+            }
+            pst += 1024u;
+            if (pst == RING_BYTES) pst = 0u;
+            cp_async_commit();                   // (an empty group keeps the wait count uniform)
         };
         for (int k = 0; k < EB_TC_NST - 1; ++k) fetch_next();
         if (check_m > 0 && warp == 0) lanczos_check(S, check_m, tol, et);
         const float lo_scale = 1.f / 2048.f;
-        int k = 0;
-        for (int G = 0; G < NG; ++G) {
-            float tacc[4] = {0.f, 0.f, 0.f, 0.f};
-            uint2 bq = make_uint2(0u, 0u);
-            if (g < 4) bq = P[g * ldh + 4 * G + t];
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                if (2 * ownI[j] > G) continue;                   // warp-uniform
-                cp_async_wait<EB_TC_NST - 2>();                  // this lane's chunk of block k
-                __syncwarp();                                    // ... and everybody else's
-                unsigned a[4], at[4];
-                const int st = (k % EB_TC_NST) * 512;
-                ldsm_x4(a, aoff + st);
-                ldsm_x4_t(at, toff + st);
-                fetch_next();        // into the stage block k-1 was read from (before the syncwarp)
-                mma16816(acc[j], a, bq.x, bq.y);
-                mma16816(tacc, at, tb0[j], tb1[j]);
-                ++k;
+        const bool bact = g < 4;                         // n >= 4: unused columns of B (zeros)
+        // operand forms of this lane's n-column, pairs of groups: uint4 (h, t) at 4 h + t
+        const uint4* Pg = reinterpret_cast<const uint4*>(P + (g & 3) * ldh) + t;
+        unsigned cst = 0u;
+        for (int j = 0; j < cnt; ++j) {
+            const int I = (int)((own >> (5 * j)) & 31u);
+            if (I >= NI) continue;                       // warp-uniform
+            const uint4* pb = Pg + 4 * I;                // groups 2 I, 2 I + 1
+            unsigned tb0 = 0u, tb1 = 0u;                 // the vector at the rows of this block
+            if (bact) { const uint4 e4 = *pb; tb0 = e4.x; tb1 = e4.z; }
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float4* pc = mypart + 8 * I + g;
+            for (int h = I; h < NH; ++h) {
+                cp_async_wait<EB_TC_NST - 2>();          // this lane's chunks of the unit
+                __syncwarp();                            // ... and everybody else's
+                unsigned a0[4], t0[4], a1[4], t1[4];
+                ldsm_x4(a0, aoff + cst);
+                ldsm_x4_t(t0, toff + cst);
+                ldsm_x4(a1, aoff + cst + 512u);
+                ldsm_x4_t(t1, toff + cst + 512u);
+                fetch_next();        // into the stage the previous unit was read from (before the syncwarp)
+                uint4 bq = make_uint4(0u, 0u, 0u, 0u);
+                if (bact) bq = *pb;
+                float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+                mma16816(acc, a0, bq.x, bq.y);
+                mma16816(c0, t0, tb0, tb1);
+                mma16816(acc, a1, bq.z, bq.w);
+                mma16816(c1, t1, tb0, tb1);
+                cst += 1024u;
+                if (cst == RING_BYTES) cst = 0u;
+                // column sums of the two blocks: conj(A) v = (Mr xr + Mi xi) + i (Mr xi - Mi xr)
+                const float yr0 = c0[0] + c0[3], yi0 = c0[1] - c0[2];
+                const float yr1 = c1[0] + c1[3], yi1 = c1[1] - c1[2];
+                const float lr0 = __shfl_xor_sync(0xffffffffu, yr0, 1), li0 = __shfl_xor_sync(0xffffffffu, yi0, 1);
+                const float lr1 = __shfl_xor_sync(0xffffffffu, yr1, 1), li1 = __shfl_xor_sync(0xffffffffu, yi1, 1);
+                if (t == 0) {
+                    float4 q = *pc;
+                    q.x += fmaf(lr0, lo_scale, yr0);
+                    q.y += fmaf(li0, lo_scale, yi0);
+                    q.z += fmaf(lr1, lo_scale, yr1);
+                    q.w += fmaf(li1, lo_scale, yi1);
+                    *pc = q;
+                }
+                pb += 4;
+                pc += 8;
             }
-            // column sums of group G: conj(A) v = (Mr xr + Mi xi) + i (Mr xi - Mi xr)
-            float yr = tacc[0] + tacc[3], yi = tacc[1] - tacc[2];
-            const float lr = __shfl_xor_sync(0xffffffffu, yr, 1), li = __shfl_xor_sync(0xffffffffu, yi, 1);
-            if (t == 0) mypart[8 * G + g] = make_float2(fmaf(lr, lo_scale, yr), fmaf(li, lo_scale, yi));
+            // row sums of this row block
+            const float l0 = __shfl_xor_sync(0xffffffffu, acc[0], 1);
+            const float l1 = __shfl_xor_sync(0xffffffffu, acc[1], 1);
+            const float l2 = __shfl_xor_sync(0xffffffffu, acc[2], 1);
+            const float l3 = __shfl_xor_sync(0xffffffffu, acc[3], 1);
+            if (t == 0) {
+                w[16 * I + g] = make_float2(fmaf(l0, lo_scale, acc[0]), fmaf(l1, lo_scale, acc[1]));
+                w[16 * I + g + 8] = make_float2(fmaf(l2, lo_scale, acc[2]), fmaf(l3, lo_scale, acc[3]));
+            }
         }
         cp_async_wait<0>();                    // (only empty groups are left)
-        // row sums of the owned row blocks
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            float l0 = __shfl_xor_sync(0xffffffffu, acc[j][0], 1);
-            float l1 = __shfl_xor_sync(0xffffffffu, acc[j][1], 1);
-            float l2 = __shfl_xor_sync(0xffffffffu, acc[j][2], 1);
-            float l3 = __shfl_xor_sync(0xffffffffu, acc[j][3], 1);
-            if (ownI[j] < NI && t == 0) {
-                w[16 * ownI[j] + g] = make_float2(fmaf(l0, lo_scale, acc[j][0]), fmaf(l1, lo_scale, acc[j][1]));
-                w[16 * ownI[j] + g + 8] = make_float2(fmaf(l2, lo_scale, acc[j][2]), fmaf(l3, lo_scale, acc[j][3]));
-            }
-        }
         __syncthreads();
         for (int c = tid; c < ld; c += EB_THREADS) {
             float sx = 0.f, sy = 0.f;
-            if (c < 8 * NG) {
+            if (c < 16 * NH) {
+                const int slot = (((c >> 4) << 3) + (c & 7)) * 2 + ((c >> 3) & 1);   // float2 index
 #pragma unroll
                 for (int kk = 0; kk < EB_NW; ++kk) {
-                    const float2 q = reinterpret_cast<const float2*>(ring + (size_t)kk * EB_NST * 4096 + 4096)[c];
+                    const float2 q = reinterpret_cast<const float2*>(ring + (size_t)kk * WSL + EB_TC_NST * 1024)[slot];
                     sx += q.x;
                     sy += q.y;
                 }
@@ -641,7 +684,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         }
         __syncthreads();
         // fp32 rows may leave any bit pattern behind: the fp16 passes need zeros
-        for (int i = tid; i < EB_NW * EB_NST * 256; i += EB_THREADS)
+        for (int i = tid; i < EB_NW * WSL / 16; i += EB_THREADS)
             reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         fence_proxy_async();
         __syncthreads();
@@ -899,7 +942,10 @@ int eig_half_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* 
     if (const char* ev = getenv("SB_EIG_ETOL_B")) etol_h = atof(ev);
     static const bool bulk = getenv("SB_EIG_BULK") != nullptr;   // A/B: cp.async.bulk row fetch
     const int mode = tensor ? EB_MODE_TC : (bulk ? EB_MODE_BULK : EB_MODE_CPA);
-    const size_t smem = eig_half_smem(ld, mode);
+    size_t smem = eig_half_smem(ld, mode);
+    // SB_EIG_SMEM_PAD=bytes: experiment switch -- extra dynamic shared memory so that only one
+    // CTA fits an SM (148 matrices x 0.52 MB in flight fit the 126 MB L2)
+    if (const char* ev = getenv("SB_EIG_SMEM_PAD")) smem += (size_t)atoi(ev);
 #define SB_EIG_HALF_LAUNCH(MODE)                                                                  \
     do {                                                                                          \
         SB_CUDA(cudaFuncSetAttribute(thth_eig_half_kernel<MODE>,                                  \

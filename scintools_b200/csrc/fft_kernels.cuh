@@ -14,6 +14,7 @@
 //                    complex->complex, real->half-spectrum, half-spectrum->real.
 #pragma once
 #include <cuda.h>      // CUtensorMap (type only; the encoder is fetched through the runtime)
+#include <stdlib.h>
 
 #include "fft_core.cuh"
 #include "tma.cuh"
@@ -286,7 +287,11 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) row_fft_c2r_kerne
 }
 
 inline int row_threads(int N, int elem_bytes = 8) {
-    int t = N / 8;
+    // SB_ROW_DIV=16: one radix-16 butterfly per thread and pass (N / 16 threads), so that two
+    // CTAs share an SM for rows up to 8192 points and overlap their load / transform / store
+    // phases; default 8
+    static const int div = (getenv("SB_ROW_DIV") && atoi(getenv("SB_ROW_DIV")) == 16) ? 16 : 8;
+    int t = N / div;
     if (t < 32) t = 32;
     const int cap = elem_bytes <= 8 ? 1024 : 512;   // fp32 rows: 32 warps hide latency
     if (t > cap) t = cap;
