@@ -99,23 +99,15 @@ __device__ __forceinline__ unsigned pack_h2(const float lo, const float hi) {
 // One block is one m16n8k16 A operand (k < 8: re, k >= 8: im of column k - 8)
 // and, read through ldmatrix.trans, the A operand of the transposed product.
 constexpr int EB_TC_NST = 5;          // 1 KB stages (two adjacent blocks) per warp, + 4 KB column sums
-// row blocks owned by each warp (5-bit fields, count in bits 25+): warp 0 gets half a
-// share because it also runs the deferred convergence check; block I has 64 - 2 I
-// blocks of columns, the shares are 70 | 144 142 140 140 140 140 140
+// row blocks owned by each mat-vec warp (5-bit fields, count in bits 25+).  Row block I has
+// 32 - I units (pairs of column groups 2 h, 2 h + 1, h >= I): {w, 15 - w, 16 + w, 31 - w} is
+// (32 - w) + (17 + w) + (16 - w) + (1 + w) = 66 units for every warp, longest stream first.
 #define EB_OWN5(a, b, c, d, e, cnt) \
     ((unsigned)(a) | (unsigned)(b) << 5 | (unsigned)(c) << 10 | (unsigned)(d) << 15 | \
      (unsigned)(e) << 20 | (unsigned)(cnt) << 25)
 __device__ __forceinline__ unsigned eb_own_pack(const int warp) {
-    switch (warp) {
-        case 0: return EB_OWN5(14, 15, 0, 0, 0, 2);
-        case 1: return EB_OWN5(0, 13, 16, 29, 30, 5);
-        case 2: return EB_OWN5(1, 12, 17, 28, 31, 5);
-        case 3: return EB_OWN5(2, 11, 18, 27, 0, 4);
-        case 4: return EB_OWN5(3, 10, 19, 26, 0, 4);
-        case 5: return EB_OWN5(4, 9, 20, 25, 0, 4);
-        case 6: return EB_OWN5(5, 8, 21, 24, 0, 4);
-        default: return EB_OWN5(6, 7, 22, 23, 0, 4);
-    }
+    if (warp >= EB_NW) return 0u;                  // the check warp owns nothing
+    return EB_OWN5(warp, 15 - warp, 16 + warp, 31 - warp, 0, 4);
 }
 
 #ifdef SB_HOST_EMU
@@ -200,8 +192,13 @@ __host__ __device__ inline size_t eig_half_smem(int ld, int mode = EB_MODE_CPA) 
 // ~70 instructions per row pair of address / election bookkeeping).
 // MODE = EB_MODE_TC: the mat-vec runs on the tensor cores (mma.sync m16n8k16, fp16 x fp16
 // -> fp32): see matvec_t below.
+// EB_MODE_TC runs one more warp (warp EB_NW): it only joins the barriers and runs the
+// deferred convergence checks, so the eight mat-vec warps carry equal shares in every step
+// (with the check on warp 0 that warp idled through half of every step without a check and
+// was the straggler of the steps with one: 16 % of all warp samples sat at the barrier
+// that ends the mat-vec, ncu source view of call 14).
 template <int MODE>
-__global__ void __launch_bounds__(EB_THREADS, 2)
+__global__ void __launch_bounds__(MODE == EB_MODE_TC ? EB_THREADS + 32 : EB_THREADS, 2)
 thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restrict__ Mbbase,
                      int ld, const int* __restrict__ nred, int eta0,
                      double* __restrict__ eigs, int* __restrict__ status,
@@ -226,6 +223,9 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     // warp index through a shuffle: tells the compiler it is warp-uniform, so the
     // bulk-copy addresses below live in uniform registers (no per-lane election loops)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    constexpr int CHKW = MODE == EB_MODE_TC ? EB_NW : 0;      // the warp that runs the deferred checks
+    const bool worker = warp < EB_NW;
+    const int tidw = worker ? tid : (1 << 24);               // strided loops: worker threads only
     const int e = blockIdx.x;
     const int n = nred[eta0 + e];
     const float2* M = Mbase + (size_t)e * ld * ld;
@@ -246,7 +246,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     }
     // The ring starts out as zeros: positions a row's copy does not cover keep
     // older (finite) data, which only ever meets vector elements that are zero.
-    for (int i = tid; i < EB_NW * WSL / 16; i += EB_THREADS)
+    for (int i = tidw; i < EB_NW * WSL / 16; i += EB_THREADS)
         reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
         for (int i = 0; i < EB_NW * EB_NST; ++i) mbar_init(mbar + i, 1);
@@ -272,7 +272,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         return warp == 0 ? 7 + 15 * k : 15 * (k >> 1) + ((k & 1) ? warp + 7 : warp - 1);
     };
     auto matvec_b = [&](int check_m, double et) {
-        for (int c = tid; c < ld; c += EB_THREADS) w[c] = make_float2(0.f, 0.f);
+        for (int c = tidw; c < ld; c += EB_THREADS) w[c] = make_float2(0.f, 0.f);
         float2 X[4][4];                        // v at the lane's columns
         float2 yc[4][4];                       // column accumulators
 #pragma unroll
@@ -429,7 +429,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             dst[1] = make_float4(yc[j][2].x, yc[j][2].y, yc[j][3].x, yc[j][3].y);
         }
         __syncthreads();
-        for (int c = tid; c < 512; c += EB_THREADS) {
+        for (int c = tidw; c < 512; c += EB_THREADS) {
             float sx = 0.f, sy = 0.f;
 #pragma unroll
             for (int kk = 0; kk < EB_NW; ++kk) { sx += part[kk * 512 + c].x; sy += part[kk * 512 + c].y; }
@@ -438,7 +438,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         __syncthreads();
         // the scratch aliased the ring: back to zeros (finite, harmless under a
         // zero vector element), ordered before the next bulk copies (async proxy)
-        for (int i = tid; i < EB_NW * 256; i += EB_THREADS)
+        for (int i = tidw; i < EB_NW * 256; i += EB_THREADS)
             reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         fence_proxy_async();
         __syncthreads();
@@ -466,11 +466,11 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     // ------------------------------------------------------------------
     auto matvec_t = [&](int check_m, double et) {
         const int ldh = ld >> 1;
-        for (int c = tid; c < ld; c += EB_THREADS) w[c] = make_float2(0.f, 0.f);
+        for (int c = tidw; c < ld; c += EB_THREADS) w[c] = make_float2(0.f, 0.f);
         // operand forms of the vector, [4 variants][ld / 2] x {b0, b1}; the entries of column
         // groups 2 h and 2 h + 1 are interleaved so that one LDS.128 fetches both: entry
         // (G, t) at (4 (G >> 1) + t) * 2 + (G & 1)
-        for (int i = tid; i < ldh; i += EB_THREADS) {
+        for (int i = tidw; i < ldh; i += EB_THREADS) {
             const float4 x = *reinterpret_cast<const float4*>(v + 2 * i);   // two vector elements
             const unsigned xr = pack_h2(x.x, x.z), xi = pack_h2(x.y, x.w);
             const float2 hr = unpack_f16x2(xr), hi = unpack_f16x2(xi);
@@ -486,8 +486,10 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         // column sums of this warp: float4 slot (h, g) = {re, im of column 16 h + g, re, im of
         // column 16 h + 8 + g} at index 8 h + g
         float4* mypart = reinterpret_cast<float4*>(wring + EB_TC_NST * 1024);
+        if (worker) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mypart[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 8; ++i) mypart[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         __syncthreads();
         const int g = lane >> 2, t = lane & 3;
         const int NI = (n + 14) >> 4;          // row blocks with stored elements (rows 0 .. n-2)
@@ -539,7 +541,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             cp_async_commit();                   // (an empty group keeps the wait count uniform)
         };
         for (int k = 0; k < EB_TC_NST - 1; ++k) fetch_next();
-        if (check_m > 0 && warp == 0) lanczos_check(S, check_m, tol, et);
+        if (check_m > 0 && warp == CHKW) lanczos_check(S, check_m, tol, et);
         const float lo_scale = 1.f / 2048.f;
         const bool bact = g < 4;                         // n >= 4: unused columns of B (zeros)
         // operand forms of this lane's n-column, pairs of groups: uint4 (h, t) at 4 h + t
@@ -554,6 +556,12 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             float4* pc = mypart + 8 * I + g;
             for (int h = I; h < NH; ++h) {
+                // operands that do not come through the ring first: their shared-memory latency
+                // overlaps the wait (the asm statements below are barriers to the compiler)
+                uint4 bq = make_uint4(0u, 0u, 0u, 0u);
+                if (bact) bq = *pb;
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t == 0) q = *pc;
                 cp_async_wait<EB_TC_NST - 2>();          // this lane's chunks of the unit
                 __syncwarp();                            // ... and everybody else's
                 unsigned a0[4], t0[4], a1[4], t1[4];
@@ -562,8 +570,6 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
                 ldsm_x4(a1, aoff + cst + 512u);
                 ldsm_x4_t(t1, toff + cst + 512u);
                 fetch_next();        // into the stage the previous unit was read from (before the syncwarp)
-                uint4 bq = make_uint4(0u, 0u, 0u, 0u);
-                if (bact) bq = *pb;
                 float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
                 mma16816(acc, a0, bq.x, bq.y);
                 mma16816(c0, t0, tb0, tb1);
@@ -577,7 +583,6 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
                 const float lr0 = __shfl_xor_sync(0xffffffffu, yr0, 1), li0 = __shfl_xor_sync(0xffffffffu, yi0, 1);
                 const float lr1 = __shfl_xor_sync(0xffffffffu, yr1, 1), li1 = __shfl_xor_sync(0xffffffffu, yi1, 1);
                 if (t == 0) {
-                    float4 q = *pc;
                     q.x += fmaf(lr0, lo_scale, yr0);
                     q.y += fmaf(li0, lo_scale, yi0);
                     q.z += fmaf(lr1, lo_scale, yr1);
@@ -599,7 +604,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         }
         cp_async_wait<0>();                    // (only empty groups are left)
         __syncthreads();
-        for (int c = tid; c < ld; c += EB_THREADS) {
+        for (int c = tidw; c < ld; c += EB_THREADS) {
             float sx = 0.f, sy = 0.f;
             if (c < 16 * NH) {
                 const int slot = (((c >> 4) << 3) + (c & 7)) * 2 + ((c >> 3) & 1);   // float2 index
@@ -622,12 +627,12 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     // because fp32 bit patterns read as fp16 could be inf / NaN.
     // ------------------------------------------------------------------
     auto matvec_f = [&]() {
-        for (int c = tid; c < ld; c += EB_THREADS) w[c] = make_float2(0.f, 0.f);
+        for (int c = tidw; c < ld; c += EB_THREADS) w[c] = make_float2(0.f, 0.f);
         __syncthreads();
         float4 yc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) yc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int K = (n - 2 >= warp) ? (n - 2 - warp) / EB_NW + 1 : 0;
+        const int K = (worker && n - 2 >= warp) ? (n - 2 - warp) / EB_NW + 1 : 0;
         auto issue = [&](int k) {
             const int a2 = warp + EB_NW * k;
             const int st = k % EB_NST;
@@ -672,11 +677,13 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             if (lane == 0) w[a] = make_float2(rx, ry);
         }
         __syncthreads();
+        if (worker) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(part + warp * 512 + 2 * (lane + 32 * j)) = yc[j];
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(part + warp * 512 + 2 * (lane + 32 * j)) = yc[j];
+        }
         __syncthreads();
-        for (int c = tid; c < 512; c += EB_THREADS) {
+        for (int c = tidw; c < 512; c += EB_THREADS) {
             float sx = 0.f, sy = 0.f;
 #pragma unroll
             for (int kk = 0; kk < EB_NW; ++kk) { sx += part[kk * 512 + c].x; sy += part[kk * 512 + c].y; }
@@ -684,7 +691,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         }
         __syncthreads();
         // fp32 rows may leave any bit pattern behind: the fp16 passes need zeros
-        for (int i = tid; i < EB_NW * WSL / 16; i += EB_THREADS)
+        for (int i = tidw; i < EB_NW * WSL / 16; i += EB_THREADS)
             reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         fence_proxy_async();
         __syncthreads();
@@ -707,7 +714,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     // alpha, the new (unnormalised) Lanczos vector in w and beta of step `it`
     auto step_scalars = [&](int it, float beta_prev, double& alpha, double& beta) {
         double apart = 0.0;
-        for (int c = tid; c < n; c += EB_THREADS) {
+        for (int c = tidw; c < n; c += EB_THREADS) {
             float2 x = w[c];
             x.x += u[c].x;
             x.y += u[c].y;
@@ -721,7 +728,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         for (int k = 0; k < EB_NW; ++k) alpha += S.red[0][k];
         const float af = (float)alpha;
         double bpart = 0.0;
-        for (int c = tid; c < n; c += EB_THREADS) {
+        for (int c = tidw; c < n; c += EB_THREADS) {
             float2 x = w[c];
             x.x -= af * v[c].x + beta_prev * vp[c].x;
             x.y -= af * v[c].y + beta_prev * vp[c].y;
@@ -739,7 +746,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     };
     auto rotate = [&](double beta) {
         const float ib = (float)(1.0 / beta);
-        for (int c = tid; c < n; c += EB_THREADS) {
+        for (int c = tidw; c < n; c += EB_THREADS) {
             const float2 x = w[c];
             vp[c] = v[c];
             v[c] = make_float2(x.x * ib, x.y * ib);
@@ -759,7 +766,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         m = 0;
         for (int it = 0; it < max_iter; ++it) {
             if (it >= EB_SLOTS) return false;
-            for (int c = tid; c < ld; c += EB_THREADS) basis[(size_t)it * ld + c] = v[c];
+            for (int c = tidw; c < ld; c += EB_THREADS) basis[(size_t)it * ld + c] = v[c];
             const bool chk = it >= 1 && it >= S.next_check;
             if (MODE == EB_MODE_TC) matvec_t(chk ? it : 0, et);
             else matvec_b(chk ? it : 0, et);
@@ -769,7 +776,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             if (chk && S.done) { m = it; break; }
             m = it + 1;
             if (it + 1 == max_iter || !(beta > 0.0)) {      // last word: check T_m now
-                if (warp == 0) lanczos_check(S, m, tol, et);
+                if (warp == CHKW) lanczos_check(S, m, tol, et);
                 __syncthreads();
                 break;
             }
@@ -804,7 +811,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     auto start_vector = [&]() -> bool {
         const int h = n / 2;
         double part0 = 0.0;
-        for (int c = tid; c < ld; c += EB_THREADS) {
+        for (int c = tidw; c < ld; c += EB_THREADS) {
             float2 x = make_float2(0.f, 0.f);
             if (c < n && c > h) x = M[(size_t)h * ld + c];
             else if (c < h) { x = M[(size_t)c * ld + h]; x.y = -x.y; }
@@ -820,7 +827,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         for (int k = 0; k < EB_NW; ++k) nrm2 += S.red[0][k];
         if (!(nrm2 > 0.0) || !isfinite(nrm2)) return false;
         const float s = (float)(1.0 / sqrt(nrm2));
-        for (int c = tid; c < ld; c += EB_THREADS) { v[c].x *= s; v[c].y *= s; }
+        for (int c = tidw; c < ld; c += EB_THREADS) { v[c].x *= s; v[c].y *= s; }
         __syncthreads();
         return true;
     };
@@ -857,7 +864,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             for (int i = 0; i < m; ++i) s[i] *= nn;
         }
         __syncthreads();
-        for (int c = tid; c < ld; c += EB_THREADS) {
+        for (int c = tidw; c < ld; c += EB_THREADS) {
             float sx = 0.f, sy = 0.f;
             if (c < n) {
                 for (int j = 0; j < m; ++j) {
@@ -873,7 +880,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         __syncthreads();
         matvec_f();
         double num = 0.0, den = 0.0;
-        for (int c = tid; c < n; c += EB_THREADS) {
+        for (int c = tidw; c < n; c += EB_THREADS) {
             const float2 y = v[c];
             float2 ay = w[c];
             ay.x += u[c].x;
@@ -891,7 +898,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         const double rho = (sd > 0.0) ? sn / sd : 0.0;
         __syncthreads();
         double rpart = 0.0;
-        for (int c = tid; c < n; c += EB_THREADS) {
+        for (int c = tidw; c < n; c += EB_THREADS) {
             const double rx = (double)w[c].x - rho * v[c].x, ry = (double)w[c].y - rho * v[c].y;
             rpart += rx * rx + ry * ry;
         }
@@ -909,7 +916,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         }
         // fp32 continuation from y
         const float s = (sd > 0.0) ? (float)(1.0 / sqrt(sd)) : 0.f;
-        for (int c = tid; c < ld; c += EB_THREADS) { v[c].x *= s; v[c].y *= s; }
+        for (int c = tidw; c < ld; c += EB_THREADS) { v[c].x *= s; v[c].y *= s; }
         __syncthreads();
         if (!(sd > 0.0)) start_vector();
         lanczos_f(etol);
@@ -950,7 +957,7 @@ int eig_half_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* 
     do {                                                                                          \
         SB_CUDA(cudaFuncSetAttribute(thth_eig_half_kernel<MODE>,                                  \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        thth_eig_half_kernel<MODE><<<nb, EB_THREADS, smem, st>>>(                                 \
+        thth_eig_half_kernel<MODE><<<nb, MODE == EB_MODE_TC ? EB_THREADS + 32 : EB_THREADS, smem, st>>>( \
             d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, etol, etol_h, rtol_r,      \
             max_iter, d_basis);                                                                   \
     } while (0)

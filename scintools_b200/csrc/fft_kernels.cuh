@@ -218,6 +218,11 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) row_fft_c2c_kerne
     for (int k = tid; k < N; k += nt) st(row, k, s[row_out_pos<T, N1, N2>(k)]);
 }
 
+// hooks of the row load functors (overloaded next to the functor, found by ADL): read
+// per-launch constants once per thread; how many leading entries of a row can be non-zero
+template <class L> __device__ __forceinline__ void row_load_init(L&) {}
+template <class L> __device__ __forceinline__ int row_load_live(const L&, int N) { return N; }
+
 // real (length 2N, packed two per complex) -> half spectrum X[0..N], forward
 // Load(row, n) returns (x[2n], x[2n+1]); Store(row, k, X[k]) for k in [0, N].
 template <typename T, int N1, int N2, class Load, class Store>
@@ -234,7 +239,11 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) row_fft_r2c_kerne
     row_load_tables<T, N1, N2, -1>(tw1, tw2, twl, tabs.wN, tid, nt);
     for (int i = tid; i <= N1; i += nt) ta[i] = tabs.w2N[(i * N2) % (2 * N)];
     for (int i = tid; i < N2; i += nt) tb[i] = tabs.w2N[i];
-    for (int n = tid; n < N; n += nt) s[row_in_pos<T, N1, N2>(n)] = ld(row, n);
+    Load lld = ld;
+    row_load_init(lld);
+    const int live = row_load_live(lld, N);          // zero padding beyond: no loads
+    for (int n = tid; n < N; n += nt)
+        s[row_in_pos<T, N1, N2>(n)] = n < live ? lld(row, n) : mkc<T>(0, 0);
     __syncthreads();
     row_fft_smem<T, N1, N2, -1>(s, tw1, tw2, twl, tid, nt);
     const T half = (T)0.5;
@@ -287,10 +296,11 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 1024 : 512) row_fft_c2r_kerne
 }
 
 inline int row_threads(int N, int elem_bytes = 8) {
-    // SB_ROW_DIV=16: one radix-16 butterfly per thread and pass (N / 16 threads), so that two
-    // CTAs share an SM for rows up to 8192 points and overlap their load / transform / store
-    // phases; default 8
-    static const int div = (getenv("SB_ROW_DIV") && atoi(getenv("SB_ROW_DIV")) == 16) ? 16 : 8;
+    // N / 16 threads: one radix-16 butterfly per thread and pass, and two CTAs share an SM for
+    // rows up to 8192 points, overlapping their load / transform / store phases (measured at
+    // 4096x8192, call 15: r2c 322 -> 258 us, c2r 616 -> 444 us; 16384-point rows keep 1024
+    // threads either way).  SB_ROW_DIV=8: the round-1 geometry (N / 8 threads)
+    static const int div = (getenv("SB_ROW_DIV") && atoi(getenv("SB_ROW_DIV")) == 8) ? 8 : 16;
     int t = N / div;
     if (t < 32) t = 32;
     const int cap = elem_bytes <= 8 ? 1024 : 512;   // fp32 rows: 32 warps hide latency

@@ -186,6 +186,33 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
 #pragma unroll
     for (int k = 0; k < ROWS; ++k) { ci[k] = -2; dk[k] = 0.0; col[k] = -1; wk[k] = 0.f; }
     const int e_end = min(nbatch, (int)(blockIdx.x + 1) * SB_BUILD_EB);
+    // per-curvature power-of-two scale of the fp16 copy, once per CTA (it was ~40 instructions
+    // of log2f / exp2f per thread and curvature): 2^floor(log2(2^15 / bound)) is the exponent
+    // field of the quotient
+    __shared__ float s_hscale[SB_BUILD_EB];
+    if (PACK != 0) {
+        const int lin = ty * 32 + tx;
+        if (lin < SB_BUILD_EB) {
+            const int e = blockIdx.x * SB_BUILD_EB + lin;
+            float hs = 1.f;
+            if (e < e_end) {
+                const float seta = sqrtf((float)(2.0 * etas[eta0 + e]));
+                const float bound = __uint_as_float(*absmax) * seta * sqrtf(span);
+                if (bound > 0.f && bound < 3.0e38f) {
+                    const float q = 32768.f / bound;
+                    hs = q >= 1.1754944e-38f ? __uint_as_float(__float_as_uint(q) & 0x7f800000u) : 1.1754944e-38f;
+                }
+            }
+            s_hscale[lin] = hs;
+        }
+        __syncthreads();
+    }
+    // eta-independent store offsets: fp32 element (row a0 + TY k, column b) and, PACK == 2,
+    // the 4-byte word of the fp16 block row this lane stores (see phase 3)
+    const unsigned foff0 = (unsigned)(ta * 32 + ty) * (unsigned)ld + (unsigned)b;
+    const unsigned frow = (unsigned)TY * (unsigned)ld;
+    const unsigned woff0 = ((unsigned)(2 * ta) * (unsigned)(ld >> 3) + (unsigned)(b >> 3)) * 128u +
+                           (unsigned)ty * 8u + (unsigned)(tx & 7);
     for (int e = blockIdx.x * SB_BUILD_EB; e < e_end; ++e) {
         const int n = nred[eta0 + e];
         if (tb * 32 >= n) continue;  // never read by the eigen kernel
@@ -200,11 +227,8 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
         }
         const float seta = sqrtf((float)(2.0 * eta));
         float2* Me = M + (size_t)e * ld * ld;
-        float hscale = 1.f;             // power of two: |element| * hscale < 2^15
-        if (PACK != 0) {
-            const float bound = __uint_as_float(*absmax) * seta * sqrtf(span);
-            if (bound > 0.f && bound < 3.0e38f) hscale = exp2f(floorf(log2f(32768.f / bound)));
-        }
+        // power of two: |element| * hscale < 2^15
+        const float hscale = PACK != 0 ? s_hscale[e - blockIdx.x * SB_BUILD_EB] : 1.f;
         // ---- phase 1: offsets
         OFF off[ROWS];          // element offset into the CS (OFF = unsigned when it fits)
         unsigned hit = 0u;
@@ -275,7 +299,7 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
                         v.y = nan_to_num(v.y);
                     }
                 }
-                const size_t o = (size_t)(ta * 32 + la) * ld + b;
+                const unsigned o = foff0 + (unsigned)k * frow;
                 Me[o] = v;
                 if (PACK == 1) Mb[(size_t)e * ld * ld + o] = pack_f16x2(make_float2(v.x * hscale, v.y * hscale));
             }
@@ -291,9 +315,9 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
                 const unsigned hb = __shfl_sync(0xffffffffu, h, s0 + 1);
                 const unsigned word = i8 < 4 ? ((ha & 0xffffu) | (hb << 16)) : ((ha >> 16) | (hb & 0xffff0000u));
                 if (!(ta == tb && (tx >> 4) < (la >> 4))) {
-                    const int a = ta * 32 + la;
+                    // row a = 32 ta + ty + TY k: block row 2 ta + (la >> 4), row (la & 15) in it
                     unsigned* Mw = Mb + (size_t)e * ld * ld;
-                    Mw[((size_t)(a >> 4) * (ld >> 3) + (b >> 3)) * 128 + (a & 15) * 8 + i8] = word;
+                    Mw[woff0 + (unsigned)(la >> 4) * (unsigned)(ld >> 3) * 128u + (unsigned)((la & 15) - ty) * 8u] = word;
                 }
             }
         }

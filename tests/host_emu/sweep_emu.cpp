@@ -91,7 +91,7 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
         std::vector<float2> gbasis((size_t)neta * EB_SLOTS * ld);
         for (int e = 0; e < neta; ++e) {
             std::memset(smem_raw, 0xa5, sizeof(smem_raw));     // garbage, like real shared memory
-            emu::run_block(emu::Dim3{(unsigned)EB_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
+            emu::run_block(emu::Dim3{(unsigned)(mixed == 3 ? EB_THREADS + 32 : EB_THREADS), 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
                            emu::Dim3{(unsigned)neta, 1, 1}, [&]() {
                                if (mixed == 3)
                                    thth_eig_half_kernel<EB_MODE_TC>(M.data(), Mb.data(), ld, nred, 0, eigs,
@@ -157,7 +157,7 @@ extern "C" int emu_eig_triangles(const float* Mf, int ld, const int* nred, int n
     for (int e = 0; e < nb; ++e) {
         std::memset(smem_raw, 0xa5, sizeof(smem_raw));
         if (mixed)
-            emu::run_block(emu::Dim3{(unsigned)EB_THREADS, 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
+            emu::run_block(emu::Dim3{(unsigned)(mixed == 3 ? EB_THREADS + 32 : EB_THREADS), 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
                            emu::Dim3{(unsigned)nb, 1, 1}, [&]() {
                                if (mixed == 3)
                                    thth_eig_half_kernel<EB_MODE_TC>(M, Mb.data(), ld, nred, 0, eigs, status,
