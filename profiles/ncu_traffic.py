@@ -63,7 +63,8 @@ def main():
         wr.writerows(out_rows)
     with open(os.path.join(here, "r2_ncu_traffic.json"), "w") as fh:
         json.dump({"source": "ncu --set full --clock-control none of `python bench.py --steps 1 "
-                             "--warmup 3 --no-cpu --no-strong --no-extra`, one launch per kernel",
+                             "--warmup 2 --no-cpu --no-strong --no-extra`, one launch per kernel "
+                             "(%s)" % ", ".join(os.path.basename(a) for a in args),
                    "kernels": traffic}, fh, indent=1)
     print(json.dumps(traffic, indent=1))
 

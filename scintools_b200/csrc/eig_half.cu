@@ -172,18 +172,22 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const unsigned (&a)[4], 
 }
 #endif
 
-enum { EB_MODE_BULK = 0, EB_MODE_CPA = 1, EB_MODE_TC = 2 };
+// EB_MODE_TC2: the tensor-core mat-vec taking two 1 KB units per step where the row block has
+// them (8 ldmatrix in flight together, two independent MMA / epilogue chains)
+enum { EB_MODE_BULK = 0, EB_MODE_CPA = 1, EB_MODE_TC = 2, EB_MODE_TC2 = 3 };
+constexpr bool EB_PAIR_DEFAULT = false;
+__host__ __device__ constexpr bool eb_is_tc(int mode) { return mode == EB_MODE_TC || mode == EB_MODE_TC2; }
 
 // shared-memory bytes of one CTA (host + device agree through this)
 // bytes of a warp's slice of the ring: two 4 KB row stages, or (tensor-core mat-vec)
 // EB_TC_NST 1 KB stages + the 4 KB column-sum buffer (the fp32 pass re-uses the first 8 KB)
 __host__ __device__ constexpr size_t eig_half_slice(int mode) {
-    return mode == EB_MODE_TC ? (size_t)EB_TC_NST * 1024 + 4096 : (size_t)EB_NST * 4096;
+    return eb_is_tc(mode) ? (size_t)EB_TC_NST * 1024 + 4096 : (size_t)EB_NST * 4096;
 }
 __host__ __device__ inline size_t eig_half_smem(int ld, int mode = EB_MODE_CPA) {
     return sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2) +
            (size_t)EB_NW * eig_half_slice(mode) + (size_t)EB_NW * EB_NST * 8 + 16 +
-           (mode == EB_MODE_TC ? 4 * (size_t)(ld / 2) * 8 : 0);
+           (eb_is_tc(mode) ? 4 * (size_t)(ld / 2) * 8 : 0);
 }
 
 // CPA: the bf16 rows are fetched with per-lane cp.async (LDGSTS) copies -- every lane
@@ -198,7 +202,7 @@ __host__ __device__ inline size_t eig_half_smem(int ld, int mode = EB_MODE_CPA) 
 // was the straggler of the steps with one: 16 % of all warp samples sat at the barrier
 // that ends the mat-vec, ncu source view of call 14).
 template <int MODE>
-__global__ void __launch_bounds__(MODE == EB_MODE_TC ? EB_THREADS + 32 : EB_THREADS, 2)
+__global__ void __launch_bounds__(eb_is_tc(MODE) ? EB_THREADS + 32 : EB_THREADS, 2)
 thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restrict__ Mbbase,
                      int ld, const int* __restrict__ nred, int eta0,
                      double* __restrict__ eigs, int* __restrict__ status,
@@ -223,7 +227,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     // warp index through a shuffle: tells the compiler it is warp-uniform, so the
     // bulk-copy addresses below live in uniform registers (no per-lane election loops)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    constexpr int CHKW = MODE == EB_MODE_TC ? EB_NW : 0;      // the warp that runs the deferred checks
+    constexpr int CHKW = eb_is_tc(MODE) ? EB_NW : 0;      // the warp that runs the deferred checks
     const bool worker = warp < EB_NW;
     const int tidw = worker ? tid : (1 << 24);               // strided loops: worker threads only
     const int e = blockIdx.x;
@@ -555,7 +559,67 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             if (bact) { const uint4 e4 = *pb; tb0 = e4.x; tb1 = e4.z; }
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             float4* pc = mypart + 8 * I + g;
-            for (int h = I; h < NH; ++h) {
+            int h = I;
+            if (MODE == EB_MODE_TC2) {
+                float accB[4] = {0.f, 0.f, 0.f, 0.f};
+                for (; h + 1 < NH; h += 2) {
+                    uint4 bq0 = make_uint4(0u, 0u, 0u, 0u), bq1 = bq0;
+                    if (bact) { bq0 = pb[0]; bq1 = pb[4]; }
+                    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+                    if (t == 0) { q0 = pc[0]; q1 = pc[8]; }
+                    cp_async_wait<EB_TC_NST - 3>();      // this lane's chunks of both units
+                    __syncwarp();                        // ... and everybody else's
+                    fetch_next();                        // into the stage read two units ago
+                    const unsigned cs2 = cst + 1024u == RING_BYTES ? 0u : cst + 1024u;
+                    unsigned a0[4], t0[4], a1[4], t1[4], b0[4], s0[4], b1[4], s1[4];
+                    ldsm_x4(a0, aoff + cst);
+                    ldsm_x4_t(t0, toff + cst);
+                    ldsm_x4(a1, aoff + cst + 512u);
+                    ldsm_x4_t(t1, toff + cst + 512u);
+                    ldsm_x4(b0, aoff + cs2);
+                    ldsm_x4_t(s0, toff + cs2);
+                    ldsm_x4(b1, aoff + cs2 + 512u);
+                    ldsm_x4_t(s1, toff + cs2 + 512u);
+                    __syncwarp();                        // every lane has read the first of the two stages
+                    fetch_next();                        // ... which the next request overwrites
+                    cst = cs2 + 1024u == RING_BYTES ? 0u : cs2 + 1024u;
+                    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+                    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma16816(acc, a0, bq0.x, bq0.y);
+                    mma16816(accB, b0, bq1.x, bq1.y);
+                    mma16816(c0, t0, tb0, tb1);
+                    mma16816(d0, s0, tb0, tb1);
+                    mma16816(acc, a1, bq0.z, bq0.w);
+                    mma16816(accB, b1, bq1.z, bq1.w);
+                    mma16816(c1, t1, tb0, tb1);
+                    mma16816(d1, s1, tb0, tb1);
+                    const float yr0 = c0[0] + c0[3], yi0 = c0[1] - c0[2];
+                    const float yr1 = c1[0] + c1[3], yi1 = c1[1] - c1[2];
+                    const float zr0 = d0[0] + d0[3], zi0 = d0[1] - d0[2];
+                    const float zr1 = d1[0] + d1[3], zi1 = d1[1] - d1[2];
+                    const float lr0 = __shfl_xor_sync(0xffffffffu, yr0, 1), li0 = __shfl_xor_sync(0xffffffffu, yi0, 1);
+                    const float lr1 = __shfl_xor_sync(0xffffffffu, yr1, 1), li1 = __shfl_xor_sync(0xffffffffu, yi1, 1);
+                    const float mr0 = __shfl_xor_sync(0xffffffffu, zr0, 1), mi0 = __shfl_xor_sync(0xffffffffu, zi0, 1);
+                    const float mr1 = __shfl_xor_sync(0xffffffffu, zr1, 1), mi1 = __shfl_xor_sync(0xffffffffu, zi1, 1);
+                    if (t == 0) {
+                        q0.x += fmaf(lr0, lo_scale, yr0);
+                        q0.y += fmaf(li0, lo_scale, yi0);
+                        q0.z += fmaf(lr1, lo_scale, yr1);
+                        q0.w += fmaf(li1, lo_scale, yi1);
+                        q1.x += fmaf(mr0, lo_scale, zr0);
+                        q1.y += fmaf(mi0, lo_scale, zi0);
+                        q1.z += fmaf(mr1, lo_scale, zr1);
+                        q1.w += fmaf(mi1, lo_scale, zi1);
+                        pc[0] = q0;
+                        pc[8] = q1;
+                    }
+                    pb += 8;
+                    pc += 16;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] += accB[i];
+            }
+            for (; h < NH; ++h) {
                 // operands that do not come through the ring first: their shared-memory latency
                 // overlaps the wait (the asm statements below are barriers to the compiler)
                 uint4 bq = make_uint4(0u, 0u, 0u, 0u);
@@ -768,7 +832,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             if (it >= EB_SLOTS) return false;
             for (int c = tidw; c < ld; c += EB_THREADS) basis[(size_t)it * ld + c] = v[c];
             const bool chk = it >= 1 && it >= S.next_check;
-            if (MODE == EB_MODE_TC) matvec_t(chk ? it : 0, et);
+            if (eb_is_tc(MODE)) matvec_t(chk ? it : 0, et);
             else matvec_b(chk ? it : 0, et);
             ++mv;
             double alpha, beta;
@@ -948,7 +1012,10 @@ int eig_half_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* 
     double etol_h = 1e-6;
     if (const char* ev = getenv("SB_EIG_ETOL_B")) etol_h = atof(ev);
     static const bool bulk = getenv("SB_EIG_BULK") != nullptr;   // A/B: cp.async.bulk row fetch
-    const int mode = tensor ? EB_MODE_TC : (bulk ? EB_MODE_BULK : EB_MODE_CPA);
+    // two units per step (EB_MODE_TC2) or one (EB_MODE_TC); SB_EIG_PAIR=0 / 1 overrides the default
+    bool pair = EB_PAIR_DEFAULT;
+    if (const char* ev = getenv("SB_EIG_PAIR")) pair = atoi(ev) != 0;
+    const int mode = tensor ? (pair ? EB_MODE_TC2 : EB_MODE_TC) : (bulk ? EB_MODE_BULK : EB_MODE_CPA);
     size_t smem = eig_half_smem(ld, mode);
     // SB_EIG_SMEM_PAD=bytes: experiment switch -- extra dynamic shared memory so that only one
     // CTA fits an SM (148 matrices x 0.52 MB in flight fit the 126 MB L2)
@@ -957,11 +1024,12 @@ int eig_half_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* 
     do {                                                                                          \
         SB_CUDA(cudaFuncSetAttribute(thth_eig_half_kernel<MODE>,                                  \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        thth_eig_half_kernel<MODE><<<nb, MODE == EB_MODE_TC ? EB_THREADS + 32 : EB_THREADS, smem, st>>>( \
+        thth_eig_half_kernel<MODE><<<nb, eb_is_tc(MODE) ? EB_THREADS + 32 : EB_THREADS, smem, st>>>( \
             d_M, d_Mb, ld, d_nred, e0, d_eigs, d_status, d_iters, tol, etol, etol_h, rtol_r,      \
             max_iter, d_basis);                                                                   \
     } while (0)
     if (mode == EB_MODE_TC) SB_EIG_HALF_LAUNCH(EB_MODE_TC);
+    else if (mode == EB_MODE_TC2) SB_EIG_HALF_LAUNCH(EB_MODE_TC2);
     else if (mode == EB_MODE_BULK) SB_EIG_HALF_LAUNCH(EB_MODE_BULK);
     else SB_EIG_HALF_LAUNCH(EB_MODE_CPA);
 #undef SB_EIG_HALF_LAUNCH

@@ -72,7 +72,7 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
         for (unsigned by = 0; by < (unsigned)npairs; ++by)
             emu::run_block(emu::Dim3{32, 4, 1}, emu::Dim3{bx, by, 0}, emu::Dim3{gx, (unsigned)npairs, 1},
                            [&]() {
-                               if (mixed == 3)
+                               if (mixed >= 3)
                                    thth_build_kernel<2, 8, unsigned>(g, etas, 0, neta, ld, idx.data(), nred,
                                                            M.data(), Mb.data(), &absmax_bits, span);
                                else if (mixed)
@@ -91,10 +91,14 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
         std::vector<float2> gbasis((size_t)neta * EB_SLOTS * ld);
         for (int e = 0; e < neta; ++e) {
             std::memset(smem_raw, 0xa5, sizeof(smem_raw));     // garbage, like real shared memory
-            emu::run_block(emu::Dim3{(unsigned)(mixed == 3 ? EB_THREADS + 32 : EB_THREADS), 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
+            emu::run_block(emu::Dim3{(unsigned)(mixed >= 3 ? EB_THREADS + 32 : EB_THREADS), 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
                            emu::Dim3{(unsigned)neta, 1, 1}, [&]() {
                                if (mixed == 3)
                                    thth_eig_half_kernel<EB_MODE_TC>(M.data(), Mb.data(), ld, nred, 0, eigs,
+                                                    status, iters, tol, 2e-7, 1e-6, 1e-3, max_iter,
+                                                    gbasis.data());
+                               else if (mixed == 4)
+                                   thth_eig_half_kernel<EB_MODE_TC2>(M.data(), Mb.data(), ld, nred, 0, eigs,
                                                     status, iters, tol, 2e-7, 1e-6, 1e-3, max_iter,
                                                     gbasis.data());
                                else
@@ -143,7 +147,7 @@ extern "C" int emu_eig_triangles(const float* Mf, int ld, const int* nred, int n
                     float2 q = M[((size_t)e * ld + a) * ld + c];
                     if (c >= n || c == a) q = make_float2(0.f, 0.f);
                     const unsigned h = pack_f16x2(make_float2(q.x * sc, q.y * sc));
-                    if (mixed == 3) {       // block layout (zeros elsewhere: Mb starts as zeros)
+                    if (mixed >= 3) {       // block layout (zeros elsewhere: Mb starts as zeros)
                         unsigned short* Mh = reinterpret_cast<unsigned short*>(Mb.data() + (size_t)e * ld * ld);
                         const size_t ob = ((size_t)(a >> 4) * (ld >> 3) + (c >> 3)) * 256 + (a & 15) * 16 + (c & 7);
                         Mh[ob] = (unsigned short)(h & 0xffffu);
@@ -157,10 +161,13 @@ extern "C" int emu_eig_triangles(const float* Mf, int ld, const int* nred, int n
     for (int e = 0; e < nb; ++e) {
         std::memset(smem_raw, 0xa5, sizeof(smem_raw));
         if (mixed)
-            emu::run_block(emu::Dim3{(unsigned)(mixed == 3 ? EB_THREADS + 32 : EB_THREADS), 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
+            emu::run_block(emu::Dim3{(unsigned)(mixed >= 3 ? EB_THREADS + 32 : EB_THREADS), 1, 1}, emu::Dim3{(unsigned)e, 0, 0},
                            emu::Dim3{(unsigned)nb, 1, 1}, [&]() {
                                if (mixed == 3)
                                    thth_eig_half_kernel<EB_MODE_TC>(M, Mb.data(), ld, nred, 0, eigs, status,
+                                                          iters, tol, 2e-7, 1e-6, 1e-3, max_iter, gbasis.data());
+                               else if (mixed == 4)
+                                   thth_eig_half_kernel<EB_MODE_TC2>(M, Mb.data(), ld, nred, 0, eigs, status,
                                                           iters, tol, 2e-7, 1e-6, 1e-3, max_iter, gbasis.data());
                                else
                                    thth_eig_half_kernel<EB_MODE_CPA>(M, Mb.data(), ld, nred, 0, eigs, status,
