@@ -174,9 +174,17 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const unsigned (&a)[4], 
 
 // EB_MODE_TC2: the tensor-core mat-vec taking two 1 KB units per step where the row block has
 // them (8 ldmatrix in flight together, two independent MMA / epilogue chains)
-enum { EB_MODE_BULK = 0, EB_MODE_CPA = 1, EB_MODE_TC = 2, EB_MODE_TC2 = 3 };
+// EB_MODE_TCB: the tensor-core mat-vec with the 1 KB units fetched by cp.async.bulk (one elected
+// lane, mbarrier complete_tx) instead of per-lane cp.async: the bulk copy writes shared memory
+// through the async proxy, not through the LSU data pipe, which ncu shows as the unit that
+// limits the cp.async version (l1tex 80 % of peak: per 512-byte block 4 wavefronts of LDGSTS
+// writes + 4 + 4 of the two ldmatrix reads)
+enum { EB_MODE_BULK = 0, EB_MODE_CPA = 1, EB_MODE_TC = 2, EB_MODE_TC2 = 3, EB_MODE_TCB = 4 };
 constexpr bool EB_PAIR_DEFAULT = false;
-__host__ __device__ constexpr bool eb_is_tc(int mode) { return mode == EB_MODE_TC || mode == EB_MODE_TC2; }
+constexpr bool EB_TCBULK_DEFAULT = false;
+__host__ __device__ constexpr bool eb_is_tc(int mode) {
+    return mode == EB_MODE_TC || mode == EB_MODE_TC2 || mode == EB_MODE_TCB;
+}
 
 // shared-memory bytes of one CTA (host + device agree through this)
 // bytes of a warp's slice of the ring: two 4 KB row stages, or (tensor-core mat-vec)
@@ -187,7 +195,7 @@ __host__ __device__ constexpr size_t eig_half_slice(int mode) {
 __host__ __device__ inline size_t eig_half_smem(int ld, int mode = EB_MODE_CPA) {
     return sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2) +
            (size_t)EB_NW * eig_half_slice(mode) + (size_t)EB_NW * EB_NST * 8 + 16 +
-           (eb_is_tc(mode) ? 4 * (size_t)(ld / 2) * 8 : 0);
+           (eb_is_tc(mode) ? 4 * (size_t)(ld / 2) * 8 + (size_t)EB_NW * EB_TC_NST * 8 : 0);
 }
 
 // CPA: the bf16 rows are fetched with per-lane cp.async (LDGSTS) copies -- every lane
@@ -223,6 +231,8 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     // EB_MODE_TC: fp16 operand forms of the vector, [4 variants][ld / 2] x {b0, b1}
     uint2* P = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(mbar) +
                                         (size_t)EB_NW * EB_NST * 8 + 16);
+    // EB_MODE_TCB: one mbarrier per ring stage and warp, [NW][EB_TC_NST], behind P
+    unsigned long long* tbar = reinterpret_cast<unsigned long long*>(P + 4 * (ld >> 1));
     const int tid = threadIdx.x, lane = tid & 31;
     // warp index through a shuffle: tells the compiler it is warp-uniform, so the
     // bulk-copy addresses below live in uniform registers (no per-lane election loops)
@@ -254,6 +264,8 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
         for (int i = 0; i < EB_NW * EB_NST; ++i) mbar_init(mbar + i, 1);
+        if (MODE == EB_MODE_TCB)
+            for (int i = 0; i < EB_NW * EB_TC_NST; ++i) mbar_init(tbar + i, 1);
         fence_mbarrier_init();
     }
     fence_proxy_async();
@@ -263,6 +275,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     unsigned char* mystage = ring + (size_t)warp * WSL;
     unsigned long long* mybar = mbar + EB_NST * warp;
     unsigned phbits = 0;                       // bit s: phase parity of this warp's barrier s
+    unsigned tph = 0;                          // EB_MODE_TCB: the same for the ring barriers
 
     // ------------------------------------------------------------------
     // fp16 mat-vec: w = (strict upper triangle) v row sums, u = column sums.
@@ -487,6 +500,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             P[3 * ldh + q] = make_uint2(li, lr);
         }
         unsigned char* wring = ring + (size_t)warp * WSL;
+        unsigned long long* mytbar = tbar + (worker ? warp : 0) * EB_TC_NST;
         // column sums of this warp: float4 slot (h, g) = {re, im of column 16 h + g, re, im of
         // column 16 h + 8 + g} at index 8 h + g
         float4* mypart = reinterpret_cast<float4*>(wring + EB_TC_NST * 1024);
@@ -503,9 +517,10 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         const unsigned own = eb_own_pack(warp);
         const int cnt = (int)(own >> 25);
         const smem_addr sbase = smem_addr_of(wring);
-        // lane's chunk of a block: row lane / 2, half lane & 1, swizzled by row bit 2
-        const int crow = lane >> 1;
-        smem_addr cdst = sbase + crow * 32 + (((lane & 1) ^ ((crow >> 2) & 1)) << 4);
+        // lane's 16-byte chunk of a block: a linear copy (thth_build_kernel stores the two halves
+        // of a block row swapped in rows 4-7 / 12-15, which is the XOR swizzle that makes both
+        // ldmatrix forms below conflict free)
+        smem_addr cdst = sbase + lane * 16;
         const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(Mb) + lane * 16;
         const int mi = lane >> 3;
         const int arow = (lane & 7) + 8 * (mi & 1), trow = (lane & 7) + 8 * (mi >> 1);
@@ -521,6 +536,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         // (I, 2 h + 1)) left in it, next unit at byte pa of the fp16 copy, next stage at pst
         int pj = -1, prem = 0;
         unsigned pa = 0u, pst = 0u;
+        unsigned cst = 0u;                   // consumer: byte offset of the stage read next
         bool pend = false;
         auto fetch_next = [&]() {
             if (prem == 0 && !pend) {
@@ -535,14 +551,33 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
                 }
             }
             if (!pend) {
-                cp_async16_s(cdst + pst, gsrc + pa);
-                cp_async16_s(cdst + pst + 512u, gsrc + pa + 512u);
+                if (MODE == EB_MODE_TCB) {
+                    if (lane == 0) {
+                        unsigned long long* bar = mytbar + (pst >> 10);
+                        mbar_expect_tx(bar, 1024u);
+                        bulk_g2s(wring + pst, reinterpret_cast<const unsigned char*>(Mb) + pa, 1024u, bar);
+                    }
+                } else {
+                    cp_async16_s(cdst + pst, gsrc + pa);
+                    cp_async16_s(cdst + pst + 512u, gsrc + pa + 512u);
+                }
                 pa += 1024u;
                 --prem;
             }
             pst += 1024u;
             if (pst == RING_BYTES) pst = 0u;
-            cp_async_commit();                   // (an empty group keeps the wait count uniform)
+            if (MODE != EB_MODE_TCB) cp_async_commit();   // (an empty group keeps the wait count uniform)
+        };
+        // the unit in stage `cst` has landed
+        auto wait_unit = [&]() {
+            if (MODE == EB_MODE_TCB) {
+                const unsigned st = cst >> 10;
+                while (!mbar_try_wait(mytbar + st, (tph >> st) & 1u)) {}
+                tph ^= 1u << st;
+            } else {
+                cp_async_wait<EB_TC_NST - 2>();          // this lane's chunks of the unit
+                __syncwarp();                            // ... and everybody else's
+            }
         };
         for (int k = 0; k < EB_TC_NST - 1; ++k) fetch_next();
         if (check_m > 0 && warp == CHKW) lanczos_check(S, check_m, tol, et);
@@ -550,7 +585,6 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         const bool bact = g < 4;                         // n >= 4: unused columns of B (zeros)
         // operand forms of this lane's n-column, pairs of groups: uint4 (h, t) at 4 h + t
         const uint4* Pg = reinterpret_cast<const uint4*>(P + (g & 3) * ldh) + t;
-        unsigned cst = 0u;
         for (int j = 0; j < cnt; ++j) {
             const int I = (int)((own >> (5 * j)) & 31u);
             if (I >= NI) continue;                       // warp-uniform
@@ -626,8 +660,7 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
                 if (bact) bq = *pb;
                 float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (t == 0) q = *pc;
-                cp_async_wait<EB_TC_NST - 2>();          // this lane's chunks of the unit
-                __syncwarp();                            // ... and everybody else's
+                wait_unit();
                 unsigned a0[4], t0[4], a1[4], t1[4];
                 ldsm_x4(a0, aoff + cst);
                 ldsm_x4_t(t0, toff + cst);
@@ -1015,7 +1048,11 @@ int eig_half_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* 
     // two units per step (EB_MODE_TC2) or one (EB_MODE_TC); SB_EIG_PAIR=0 / 1 overrides the default
     bool pair = EB_PAIR_DEFAULT;
     if (const char* ev = getenv("SB_EIG_PAIR")) pair = atoi(ev) != 0;
-    const int mode = tensor ? (pair ? EB_MODE_TC2 : EB_MODE_TC) : (bulk ? EB_MODE_BULK : EB_MODE_CPA);
+    // units fetched by cp.async.bulk (EB_MODE_TCB) or per-lane cp.async; SB_EIG_TCBULK=0 / 1
+    bool tcbulk = EB_TCBULK_DEFAULT;
+    if (const char* ev = getenv("SB_EIG_TCBULK")) tcbulk = atoi(ev) != 0;
+    const int mode = tensor ? (tcbulk ? EB_MODE_TCB : (pair ? EB_MODE_TC2 : EB_MODE_TC))
+                            : (bulk ? EB_MODE_BULK : EB_MODE_CPA);
     size_t smem = eig_half_smem(ld, mode);
     // SB_EIG_SMEM_PAD=bytes: experiment switch -- extra dynamic shared memory so that only one
     // CTA fits an SM (148 matrices x 0.52 MB in flight fit the 126 MB L2)
@@ -1030,6 +1067,7 @@ int eig_half_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* 
     } while (0)
     if (mode == EB_MODE_TC) SB_EIG_HALF_LAUNCH(EB_MODE_TC);
     else if (mode == EB_MODE_TC2) SB_EIG_HALF_LAUNCH(EB_MODE_TC2);
+    else if (mode == EB_MODE_TCB) SB_EIG_HALF_LAUNCH(EB_MODE_TCB);
     else if (mode == EB_MODE_BULK) SB_EIG_HALF_LAUNCH(EB_MODE_BULK);
     else SB_EIG_HALF_LAUNCH(EB_MODE_CPA);
 #undef SB_EIG_HALF_LAUNCH

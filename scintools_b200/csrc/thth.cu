@@ -154,8 +154,8 @@ __global__ void cs_absmax_kernel(const float2* __restrict__ cs, long long rows, 
 // flight), not by its instruction count.
 // PACK == 2: the fp16 copy in the block layout of eig_half.cu's tensor-core mat-vec:
 // 512-byte blocks of 16 rows x 8 columns, block (I, G) at ((I * ld / 8 + G) * 512) bytes,
-// a block row = [re x 8 | im x 8]; the part of a diagonal block on / below the diagonal
-// is written as zeros (the MMA has no masks).
+// a block row = [re x 8 | im x 8] (the halves swapped in rows 4-7, 12-15); the part of a
+// diagonal block on / below the diagonal is written as zeros (the MMA has no masks).
 template <int PACK, int ROWS, typename OFF>
 __global__ void __launch_bounds__(32 * (32 / ROWS), ROWS == 8 ? 5 : 4)
 thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nbatch,
@@ -212,7 +212,7 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
     const unsigned foff0 = (unsigned)(ta * 32 + ty) * (unsigned)ld + (unsigned)b;
     const unsigned frow = (unsigned)TY * (unsigned)ld;
     const unsigned woff0 = ((unsigned)(2 * ta) * (unsigned)(ld >> 3) + (unsigned)(b >> 3)) * 128u +
-                           (unsigned)ty * 8u + (unsigned)(tx & 7);
+                           (unsigned)ty * 8u;
     for (int e = blockIdx.x * SB_BUILD_EB; e < e_end; ++e) {
         const int n = nred[eta0 + e];
         if (tb * 32 >= n) continue;  // never read by the eigen kernel
@@ -317,7 +317,12 @@ thth_build_kernel(ThthGeom g, const double* __restrict__ etas, int eta0, int nba
                 if (!(ta == tb && (tx >> 4) < (la >> 4))) {
                     // row a = 32 ta + ty + TY k: block row 2 ta + (la >> 4), row (la & 15) in it
                     unsigned* Mw = Mb + (size_t)e * ld * ld;
-                    Mw[woff0 + (unsigned)(la >> 4) * (unsigned)(ld >> 3) * 128u + (unsigned)((la & 15) - ty) * 8u] = word;
+                    // the two 16-byte halves of a block row are stored swapped in rows 4-7 and
+                    // 12-15: a LINEAR copy of the block into shared memory is then conflict free for
+                    // both ldmatrix forms (eig_half.cu), so a bulk copy can fetch it
+                    const unsigned swz = (unsigned)(((la & 15) >> 2) & 1) << 2;
+                    Mw[woff0 + (unsigned)(la >> 4) * (unsigned)(ld >> 3) * 128u + (unsigned)((la & 15) - ty) * 8u +
+                       ((unsigned)i8 ^ swz)] = word;
                 }
             }
         }

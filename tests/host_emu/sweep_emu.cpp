@@ -101,6 +101,10 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
                                    thth_eig_half_kernel<EB_MODE_TC2>(M.data(), Mb.data(), ld, nred, 0, eigs,
                                                     status, iters, tol, 2e-7, 1e-6, 1e-3, max_iter,
                                                     gbasis.data());
+                               else if (mixed == 5)
+                                   thth_eig_half_kernel<EB_MODE_TCB>(M.data(), Mb.data(), ld, nred, 0, eigs,
+                                                    status, iters, tol, 2e-7, 1e-6, 1e-3, max_iter,
+                                                    gbasis.data());
                                else
                                    thth_eig_half_kernel<EB_MODE_CPA>(M.data(), Mb.data(), ld, nred, 0, eigs,
                                                     status, iters, tol, 2e-7, 1e-6, mixed == 2 ? 0.0 : 1e-3,
@@ -150,8 +154,9 @@ extern "C" int emu_eig_triangles(const float* Mf, int ld, const int* nred, int n
                     if (mixed >= 3) {       // block layout (zeros elsewhere: Mb starts as zeros)
                         unsigned short* Mh = reinterpret_cast<unsigned short*>(Mb.data() + (size_t)e * ld * ld);
                         const size_t ob = ((size_t)(a >> 4) * (ld >> 3) + (c >> 3)) * 256 + (a & 15) * 16 + (c & 7);
-                        Mh[ob] = (unsigned short)(h & 0xffffu);
-                        Mh[ob + 8] = (unsigned short)(h >> 16);
+                        const int sw = (((a & 15) >> 2) & 1) * 8;      // halves swapped in rows 4-7, 12-15
+                        Mh[ob + sw] = (unsigned short)(h & 0xffffu);
+                        Mh[ob + (8 - sw)] = (unsigned short)(h >> 16);
                     } else {
                         Mb[((size_t)e * ld + a) * ld + c] = h;
                     }
@@ -168,6 +173,9 @@ extern "C" int emu_eig_triangles(const float* Mf, int ld, const int* nred, int n
                                                           iters, tol, 2e-7, 1e-6, 1e-3, max_iter, gbasis.data());
                                else if (mixed == 4)
                                    thth_eig_half_kernel<EB_MODE_TC2>(M, Mb.data(), ld, nred, 0, eigs, status,
+                                                          iters, tol, 2e-7, 1e-6, 1e-3, max_iter, gbasis.data());
+                               else if (mixed == 5)
+                                   thth_eig_half_kernel<EB_MODE_TCB>(M, Mb.data(), ld, nred, 0, eigs, status,
                                                           iters, tol, 2e-7, 1e-6, 1e-3, max_iter, gbasis.data());
                                else
                                    thth_eig_half_kernel<EB_MODE_CPA>(M, Mb.data(), ld, nred, 0, eigs, status,
