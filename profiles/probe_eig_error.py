@@ -17,8 +17,8 @@ os.environ["SB_EIG_FP32"] = "1"
 ref, iref = thth.eta_sweep(cs, tau, fd, etas, edges, return_info=True)
 del os.environ["SB_EIG_FP32"]
 out = {"fp32_iters_mean": float(iref["iters"].mean())}
-for label, env in (("default", {}), ("no_tc", {"SB_EIG_NO_TC": "1"}), ("pair", {"SB_EIG_PAIR": "1"}),
-                   ("tcbulk", {"SB_EIG_TCBULK": "1"}), ("tccpa", {"SB_EIG_TCBULK": "0"})):
+for label, env in (("default", {}), ("no_tc", {"SB_EIG_NO_TC": "1"}), ("rtol5e4", {"SB_EIG_RTOL_R": "5e-4"}),
+                   ("etol5e7", {"SB_EIG_ETOL_B": "5e-7"})):
     os.environ.update(env)
     got, info = thth.eta_sweep(cs, tau, fd, etas, edges, return_info=True)
     for k in env: del os.environ[k]

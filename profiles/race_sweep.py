@@ -12,11 +12,7 @@ t = np.arange(nt) * 10.0; f = 1400.0 + np.arange(nf) * 0.05
 fd = thth.fft_axis(t, "mHz", npad); tau = thth.fft_axis(f, "us", npad)
 edges = np.linspace(-20, 20, 96); etas = np.linspace(0.002, 0.02, 4)
 cs = thth.conjugate_spectrum(d0, npad, 0.0)
-os.environ["SB_EIG_TCBULK"] = "0"
 print("tensor-core", thth.eta_sweep(cs, tau, fd, etas, edges))
-os.environ["SB_EIG_TCBULK"] = "1"
-print("tc + bulk  ", thth.eta_sweep(cs, tau, fd, etas, edges))
-del os.environ["SB_EIG_TCBULK"]
 os.environ["SB_EIG_NO_TC"] = "1"
 print("packed-FMA ", thth.eta_sweep(cs, tau, fd, etas, edges))
 os.environ["SB_EIG_FP32"] = "1"

@@ -172,19 +172,8 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const unsigned (&a)[4], 
 }
 #endif
 
-// EB_MODE_TC2: the tensor-core mat-vec taking two 1 KB units per step where the row block has
-// them (8 ldmatrix in flight together, two independent MMA / epilogue chains)
-// EB_MODE_TCB: the tensor-core mat-vec with the 1 KB units fetched by cp.async.bulk (one elected
-// lane, mbarrier complete_tx) instead of per-lane cp.async: the bulk copy writes shared memory
-// through the async proxy, not through the LSU data pipe, which ncu shows as the unit that
-// limits the cp.async version (l1tex 80 % of peak: per 512-byte block 4 wavefronts of LDGSTS
-// writes + 4 + 4 of the two ldmatrix reads)
-enum { EB_MODE_BULK = 0, EB_MODE_CPA = 1, EB_MODE_TC = 2, EB_MODE_TC2 = 3, EB_MODE_TCB = 4 };
-constexpr bool EB_PAIR_DEFAULT = false;
-constexpr bool EB_TCBULK_DEFAULT = false;
-__host__ __device__ constexpr bool eb_is_tc(int mode) {
-    return mode == EB_MODE_TC || mode == EB_MODE_TC2 || mode == EB_MODE_TCB;
-}
+enum { EB_MODE_BULK = 0, EB_MODE_CPA = 1, EB_MODE_TC = 2 };
+__host__ __device__ constexpr bool eb_is_tc(int mode) { return mode == EB_MODE_TC; }
 
 // shared-memory bytes of one CTA (host + device agree through this)
 // bytes of a warp's slice of the ring: two 4 KB row stages, or (tensor-core mat-vec)
@@ -195,7 +184,7 @@ __host__ __device__ constexpr size_t eig_half_slice(int mode) {
 __host__ __device__ inline size_t eig_half_smem(int ld, int mode = EB_MODE_CPA) {
     return sizeof(LanczosShared) + 4 * (size_t)ld * sizeof(float2) +
            (size_t)EB_NW * eig_half_slice(mode) + (size_t)EB_NW * EB_NST * 8 + 16 +
-           (eb_is_tc(mode) ? 4 * (size_t)(ld / 2) * 8 + (size_t)EB_NW * EB_TC_NST * 8 : 0);
+           (eb_is_tc(mode) ? 4 * (size_t)(ld / 2) * 8 : 0);
 }
 
 // CPA: the bf16 rows are fetched with per-lane cp.async (LDGSTS) copies -- every lane
@@ -231,8 +220,6 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     // EB_MODE_TC: fp16 operand forms of the vector, [4 variants][ld / 2] x {b0, b1}
     uint2* P = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(mbar) +
                                         (size_t)EB_NW * EB_NST * 8 + 16);
-    // EB_MODE_TCB: one mbarrier per ring stage and warp, [NW][EB_TC_NST], behind P
-    unsigned long long* tbar = reinterpret_cast<unsigned long long*>(P + 4 * (ld >> 1));
     const int tid = threadIdx.x, lane = tid & 31;
     // warp index through a shuffle: tells the compiler it is warp-uniform, so the
     // bulk-copy addresses below live in uniform registers (no per-lane election loops)
@@ -264,8 +251,6 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
         reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
         for (int i = 0; i < EB_NW * EB_NST; ++i) mbar_init(mbar + i, 1);
-        if (MODE == EB_MODE_TCB)
-            for (int i = 0; i < EB_NW * EB_TC_NST; ++i) mbar_init(tbar + i, 1);
         fence_mbarrier_init();
     }
     fence_proxy_async();
@@ -275,7 +260,6 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
     unsigned char* mystage = ring + (size_t)warp * WSL;
     unsigned long long* mybar = mbar + EB_NST * warp;
     unsigned phbits = 0;                       // bit s: phase parity of this warp's barrier s
-    unsigned tph = 0;                          // EB_MODE_TCB: the same for the ring barriers
 
     // ------------------------------------------------------------------
     // fp16 mat-vec: w = (strict upper triangle) v row sums, u = column sums.
@@ -500,7 +484,6 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             P[3 * ldh + q] = make_uint2(li, lr);
         }
         unsigned char* wring = ring + (size_t)warp * WSL;
-        unsigned long long* mytbar = tbar + (worker ? warp : 0) * EB_TC_NST;
         // column sums of this warp: float4 slot (h, g) = {re, im of column 16 h + g, re, im of
         // column 16 h + 8 + g} at index 8 h + g
         float4* mypart = reinterpret_cast<float4*>(wring + EB_TC_NST * 1024);
@@ -551,33 +534,14 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
                 }
             }
             if (!pend) {
-                if (MODE == EB_MODE_TCB) {
-                    if (lane == 0) {
-                        unsigned long long* bar = mytbar + (pst >> 10);
-                        mbar_expect_tx(bar, 1024u);
-                        bulk_g2s(wring + pst, reinterpret_cast<const unsigned char*>(Mb) + pa, 1024u, bar);
-                    }
-                } else {
-                    cp_async16_s(cdst + pst, gsrc + pa);
-                    cp_async16_s(cdst + pst + 512u, gsrc + pa + 512u);
-                }
+                cp_async16_s(cdst + pst, gsrc + pa);
+                cp_async16_s(cdst + pst + 512u, gsrc + pa + 512u);
                 pa += 1024u;
                 --prem;
             }
             pst += 1024u;
             if (pst == RING_BYTES) pst = 0u;
-            if (MODE != EB_MODE_TCB) cp_async_commit();   // (an empty group keeps the wait count uniform)
-        };
-        // the unit in stage `cst` has landed
-        auto wait_unit = [&]() {
-            if (MODE == EB_MODE_TCB) {
-                const unsigned st = cst >> 10;
-                while (!mbar_try_wait(mytbar + st, (tph >> st) & 1u)) {}
-                tph ^= 1u << st;
-            } else {
-                cp_async_wait<EB_TC_NST - 2>();          // this lane's chunks of the unit
-                __syncwarp();                            // ... and everybody else's
-            }
+            cp_async_commit();                   // (an empty group keeps the wait count uniform)
         };
         for (int k = 0; k < EB_TC_NST - 1; ++k) fetch_next();
         if (check_m > 0 && warp == CHKW) lanczos_check(S, check_m, tol, et);
@@ -593,74 +557,15 @@ thth_eig_half_kernel(const float2* __restrict__ Mbase, const unsigned* __restric
             if (bact) { const uint4 e4 = *pb; tb0 = e4.x; tb1 = e4.z; }
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             float4* pc = mypart + 8 * I + g;
-            int h = I;
-            if (MODE == EB_MODE_TC2) {
-                float accB[4] = {0.f, 0.f, 0.f, 0.f};
-                for (; h + 1 < NH; h += 2) {
-                    uint4 bq0 = make_uint4(0u, 0u, 0u, 0u), bq1 = bq0;
-                    if (bact) { bq0 = pb[0]; bq1 = pb[4]; }
-                    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
-                    if (t == 0) { q0 = pc[0]; q1 = pc[8]; }
-                    cp_async_wait<EB_TC_NST - 3>();      // this lane's chunks of both units
-                    __syncwarp();                        // ... and everybody else's
-                    fetch_next();                        // into the stage read two units ago
-                    const unsigned cs2 = cst + 1024u == RING_BYTES ? 0u : cst + 1024u;
-                    unsigned a0[4], t0[4], a1[4], t1[4], b0[4], s0[4], b1[4], s1[4];
-                    ldsm_x4(a0, aoff + cst);
-                    ldsm_x4_t(t0, toff + cst);
-                    ldsm_x4(a1, aoff + cst + 512u);
-                    ldsm_x4_t(t1, toff + cst + 512u);
-                    ldsm_x4(b0, aoff + cs2);
-                    ldsm_x4_t(s0, toff + cs2);
-                    ldsm_x4(b1, aoff + cs2 + 512u);
-                    ldsm_x4_t(s1, toff + cs2 + 512u);
-                    __syncwarp();                        // every lane has read the first of the two stages
-                    fetch_next();                        // ... which the next request overwrites
-                    cst = cs2 + 1024u == RING_BYTES ? 0u : cs2 + 1024u;
-                    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-                    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-                    mma16816(acc, a0, bq0.x, bq0.y);
-                    mma16816(accB, b0, bq1.x, bq1.y);
-                    mma16816(c0, t0, tb0, tb1);
-                    mma16816(d0, s0, tb0, tb1);
-                    mma16816(acc, a1, bq0.z, bq0.w);
-                    mma16816(accB, b1, bq1.z, bq1.w);
-                    mma16816(c1, t1, tb0, tb1);
-                    mma16816(d1, s1, tb0, tb1);
-                    const float yr0 = c0[0] + c0[3], yi0 = c0[1] - c0[2];
-                    const float yr1 = c1[0] + c1[3], yi1 = c1[1] - c1[2];
-                    const float zr0 = d0[0] + d0[3], zi0 = d0[1] - d0[2];
-                    const float zr1 = d1[0] + d1[3], zi1 = d1[1] - d1[2];
-                    const float lr0 = __shfl_xor_sync(0xffffffffu, yr0, 1), li0 = __shfl_xor_sync(0xffffffffu, yi0, 1);
-                    const float lr1 = __shfl_xor_sync(0xffffffffu, yr1, 1), li1 = __shfl_xor_sync(0xffffffffu, yi1, 1);
-                    const float mr0 = __shfl_xor_sync(0xffffffffu, zr0, 1), mi0 = __shfl_xor_sync(0xffffffffu, zi0, 1);
-                    const float mr1 = __shfl_xor_sync(0xffffffffu, zr1, 1), mi1 = __shfl_xor_sync(0xffffffffu, zi1, 1);
-                    if (t == 0) {
-                        q0.x += fmaf(lr0, lo_scale, yr0);
-                        q0.y += fmaf(li0, lo_scale, yi0);
-                        q0.z += fmaf(lr1, lo_scale, yr1);
-                        q0.w += fmaf(li1, lo_scale, yi1);
-                        q1.x += fmaf(mr0, lo_scale, zr0);
-                        q1.y += fmaf(mi0, lo_scale, zi0);
-                        q1.z += fmaf(mr1, lo_scale, zr1);
-                        q1.w += fmaf(mi1, lo_scale, zi1);
-                        pc[0] = q0;
-                        pc[8] = q1;
-                    }
-                    pb += 8;
-                    pc += 16;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] += accB[i];
-            }
-            for (; h < NH; ++h) {
+            for (int h = I; h < NH; ++h) {
                 // operands that do not come through the ring first: their shared-memory latency
                 // overlaps the wait (the asm statements below are barriers to the compiler)
                 uint4 bq = make_uint4(0u, 0u, 0u, 0u);
                 if (bact) bq = *pb;
                 float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (t == 0) q = *pc;
-                wait_unit();
+                cp_async_wait<EB_TC_NST - 2>();          // this lane's chunks of the unit
+                __syncwarp();                            // ... and everybody else's
                 unsigned a0[4], t0[4], a1[4], t1[4];
                 ldsm_x4(a0, aoff + cst);
                 ldsm_x4_t(t0, toff + cst);
@@ -1045,14 +950,7 @@ int eig_half_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* 
     double etol_h = 1e-6;
     if (const char* ev = getenv("SB_EIG_ETOL_B")) etol_h = atof(ev);
     static const bool bulk = getenv("SB_EIG_BULK") != nullptr;   // A/B: cp.async.bulk row fetch
-    // two units per step (EB_MODE_TC2) or one (EB_MODE_TC); SB_EIG_PAIR=0 / 1 overrides the default
-    bool pair = EB_PAIR_DEFAULT;
-    if (const char* ev = getenv("SB_EIG_PAIR")) pair = atoi(ev) != 0;
-    // units fetched by cp.async.bulk (EB_MODE_TCB) or per-lane cp.async; SB_EIG_TCBULK=0 / 1
-    bool tcbulk = EB_TCBULK_DEFAULT;
-    if (const char* ev = getenv("SB_EIG_TCBULK")) tcbulk = atoi(ev) != 0;
-    const int mode = tensor ? (tcbulk ? EB_MODE_TCB : (pair ? EB_MODE_TC2 : EB_MODE_TC))
-                            : (bulk ? EB_MODE_BULK : EB_MODE_CPA);
+    const int mode = tensor ? EB_MODE_TC : (bulk ? EB_MODE_BULK : EB_MODE_CPA);
     size_t smem = eig_half_smem(ld, mode);
     // SB_EIG_SMEM_PAD=bytes: experiment switch -- extra dynamic shared memory so that only one
     // CTA fits an SM (148 matrices x 0.52 MB in flight fit the 126 MB L2)
@@ -1066,8 +964,6 @@ int eig_half_launch(const float2* d_M, const unsigned* d_Mb, int ld, const int* 
             max_iter, d_basis);                                                                   \
     } while (0)
     if (mode == EB_MODE_TC) SB_EIG_HALF_LAUNCH(EB_MODE_TC);
-    else if (mode == EB_MODE_TC2) SB_EIG_HALF_LAUNCH(EB_MODE_TC2);
-    else if (mode == EB_MODE_TCB) SB_EIG_HALF_LAUNCH(EB_MODE_TCB);
     else if (mode == EB_MODE_BULK) SB_EIG_HALF_LAUNCH(EB_MODE_BULK);
     else SB_EIG_HALF_LAUNCH(EB_MODE_CPA);
 #undef SB_EIG_HALF_LAUNCH

@@ -97,14 +97,6 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
                                    thth_eig_half_kernel<EB_MODE_TC>(M.data(), Mb.data(), ld, nred, 0, eigs,
                                                     status, iters, tol, 2e-7, 1e-6, 1e-3, max_iter,
                                                     gbasis.data());
-                               else if (mixed == 4)
-                                   thth_eig_half_kernel<EB_MODE_TC2>(M.data(), Mb.data(), ld, nred, 0, eigs,
-                                                    status, iters, tol, 2e-7, 1e-6, 1e-3, max_iter,
-                                                    gbasis.data());
-                               else if (mixed == 5)
-                                   thth_eig_half_kernel<EB_MODE_TCB>(M.data(), Mb.data(), ld, nred, 0, eigs,
-                                                    status, iters, tol, 2e-7, 1e-6, 1e-3, max_iter,
-                                                    gbasis.data());
                                else
                                    thth_eig_half_kernel<EB_MODE_CPA>(M.data(), Mb.data(), ld, nred, 0, eigs,
                                                     status, iters, tol, 2e-7, 1e-6, mixed == 2 ? 0.0 : 1e-3,
@@ -170,12 +162,6 @@ extern "C" int emu_eig_triangles(const float* Mf, int ld, const int* nred, int n
                            emu::Dim3{(unsigned)nb, 1, 1}, [&]() {
                                if (mixed == 3)
                                    thth_eig_half_kernel<EB_MODE_TC>(M, Mb.data(), ld, nred, 0, eigs, status,
-                                                          iters, tol, 2e-7, 1e-6, 1e-3, max_iter, gbasis.data());
-                               else if (mixed == 4)
-                                   thth_eig_half_kernel<EB_MODE_TC2>(M, Mb.data(), ld, nred, 0, eigs, status,
-                                                          iters, tol, 2e-7, 1e-6, 1e-3, max_iter, gbasis.data());
-                               else if (mixed == 5)
-                                   thth_eig_half_kernel<EB_MODE_TCB>(M, Mb.data(), ld, nred, 0, eigs, status,
                                                           iters, tol, 2e-7, 1e-6, 1e-3, max_iter, gbasis.data());
                                else
                                    thth_eig_half_kernel<EB_MODE_CPA>(M, Mb.data(), ld, nred, 0, eigs, status,
