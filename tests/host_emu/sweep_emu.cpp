@@ -70,10 +70,13 @@ extern "C" int emu_eta_sweep(const float* cs, long long ntau, long long nfd, lon
     const unsigned gx = (unsigned)((neta + SB_BUILD_EB - 1) / SB_BUILD_EB);
     for (unsigned bx = 0; bx < gx; ++bx)
         for (unsigned by = 0; by < (unsigned)npairs; ++by)
-            emu::run_block(emu::Dim3{32, 4, 1}, emu::Dim3{bx, by, 0}, emu::Dim3{gx, (unsigned)npairs, 1},
+            // mixed >= 3: the geometry sb::eta_sweep launches by default (4 rows per thread,
+            // 32 x 8 threads); the other paths run the 8-row variant (fewer fibers)
+            emu::run_block(emu::Dim3{32, (unsigned)(mixed >= 3 ? 8 : 4), 1}, emu::Dim3{bx, by, 0},
+                           emu::Dim3{gx, (unsigned)npairs, 1},
                            [&]() {
                                if (mixed >= 3)
-                                   thth_build_kernel<2, 8, unsigned>(g, etas, 0, neta, ld, idx.data(), nred,
+                                   thth_build_kernel<2, 4, unsigned>(g, etas, 0, neta, ld, idx.data(), nred,
                                                            M.data(), Mb.data(), &absmax_bits, span);
                                else if (mixed)
                                    thth_build_kernel<1, 8, unsigned>(g, etas, 0, neta, ld, idx.data(), nred,
