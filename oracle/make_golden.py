@@ -68,6 +68,24 @@ def golden_sspec_acf(pkg):
                         tdel=ds.tdel, acf=ds.acf)
 
 
+def golden_c1(pkg):
+    """BASELINE.json configs[0]: Dynspec.calc_sspec on a 256x256 synthetic dynamic spectrum
+    (the reference's own CPU case).  The input is regenerated from its seed by the test; the
+    fixture keeps the axes, a decimated copy of the secondary spectrum, three full rows and
+    the float64 sum."""
+    rng = np.random.default_rng(256)
+    nf, nt, dt, df = 256, 256, 8.0, 0.125
+    dyn = rng.exponential(1.0, (nf, nt))
+    ds = _ref_dynspec(pkg, dyn.copy(), dt, df)
+    ds.calc_sspec()
+    sec = np.asarray(ds.sspec)
+    np.savez_compressed(os.path.join(GOLD, "c1_sspec_256x256.npz"), seed=256, nf=nf, nt=nt,
+                        dt=dt, df=df, shape=np.array(sec.shape), fdop=ds.fdop, tdel=ds.tdel,
+                        sspec_dec=sec[::3, ::5], rows=np.array([0, 1, sec.shape[0] - 1]),
+                        sspec_rows=sec[[0, 1, sec.shape[0] - 1], :],
+                        finite_sum=float(np.sum(sec[np.isfinite(sec)])))
+
+
 def golden_thth(pkg):
     """ththmod on a chunk of Sample_Data.npz (tutorial recipe,
     docs/source/tutorials/thth_intro.rst:238-310) with seeded noise."""
@@ -375,6 +393,8 @@ def main():
     only = sys.argv[1:]
     if not only or "sspec" in only:
         golden_sspec_acf(pkg)
+    if not only or "c1" in only:
+        golden_c1(pkg)
     if not only or "thth" in only:
         golden_thth(pkg)
     if not only or "thin" in only:
